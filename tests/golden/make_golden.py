@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by executing the REFERENCE'S OWN SOURCE.
+
+Run in the build container only (needs /root/reference; the GPU box does not have
+it):  python tests/golden/make_golden.py
+
+The reference cannot be imported as modules (Python 2 syntax elsewhere in the
+files, TensorFlow 1.4 / tf.contrib.slim / `config` not installable).  So each
+hot-path function is cut out of its file by name, and exec'd unmodified in a
+namespace where ``tf`` / ``slim`` are tests/golden/tf_shim.py (TF op semantics
+restated over torch CPU fp32, autograd for the gradients) and ``np`` / ``dist``
+are the real numpy / scipy.  Pure-numpy functions (pixel_detect,
+restore_rectangle_rbox, order_points, sort_poly) run as they are.
+
+Nothing from the reference is copied into the repo: only the numeric
+inputs/outputs are stored.
+"""
+from __future__ import annotations
+
+import os
+import re
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import tf_shim as tf  # noqa: E402
+from tensorflow_ocr_b200 import synth  # noqa: E402
+
+REF = os.environ.get("PLH_REFERENCE", "/root/reference")
+
+
+def cut(path, name, indent=""):
+    """Source of ``def name`` (at the given indent) from a reference file, dedented."""
+    lines = open(os.path.join(REF, path)).read().split("\n")
+    start = None
+    for i, l in enumerate(lines):
+        if re.match(r"^%sdef %s\(" % (indent, re.escape(name)), l):
+            start = i
+            break
+    assert start is not None, (path, name)
+    end = len(lines)
+    for j in range(start + 1, len(lines)):
+        l = lines[j]
+        if l.strip() == "":
+            continue
+        cur = len(l) - len(l.lstrip())
+        if cur <= len(indent) and not l.lstrip().startswith("#"):
+            end = j
+            break
+    return textwrap.dedent("\n".join(lines[start:end])), (start + 1, end)
+
+
+def ns_tf():
+    return dict(tf=tf, slim=tf.slim, np=np, xrange=range)
+
+
+def T(x, grad=False):
+    t = torch.tensor(np.asarray(x), dtype=torch.float32)
+    t.requires_grad_(grad)
+    return t
+
+
+def save(name, **arrs):
+    out = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(out, **{k: np.asarray(v) for k, v in arrs.items()})
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
+# ----------------------------------------------------------------------------- nets/model.py
+def golden_model_loss():
+    ns = ns_tf()
+    spans = {}
+    for fn in ("dice_coefficient", "OHNM_single_image", "OHNM_batch", "get_pos_and_neg_masks", "loss"):
+        src, spans[fn] = cut("nets/model.py", fn)
+        exec(src, ns)
+    print("nets/model.py spans", spans)
+    # The reference hard-codes OHNM_batch(14, ...) (model.py:220) -> B must be 14.
+    B, H, W = 14, 16, 16
+    kinds = ["normal"] * B
+    kinds[12], kinds[13] = "no_pos", "many_pos"
+    imgs = [synth.make_image(91, i, H, W, "G", kinds[i]) for i in range(B)]
+    inp = {k: np.stack([im[k] for im in imgs]) for k in imgs[0]}
+    yp, yl = T(inp["pix_logits"], True), T(inp["link_logits"], True)
+    mask = torch.ones(B, H, W, 1)
+    out = ns["loss"](T(inp["pix_lab"]), yp, T(inp["link_lab"]), yl, mask)
+    out.backward()
+    # side values: the OHEM mask as the reference computes it
+    with torch.no_grad():
+        pl = tf.cast(tf.reshape(T(inp["pix_lab"]), [B, -1]), tf.int32)
+        sc = tf.slim.softmax(tf.reshape(yp, [B, -1, 2]))[:, :, 0]
+        pos, neg = ns["get_pos_and_neg_masks"](pl)
+        sel = ns["OHNM_batch"](14, sc, pos, neg)
+    save("model_loss_b14", pix_logits=inp["pix_logits"], link_logits=inp["link_logits"],
+         pix_lab=inp["pix_lab"], link_lab=inp["link_lab"], loss=out.detach().numpy(),
+         grad_pixel=yp.grad.numpy(), grad_link=yl.grad.numpy(),
+         ohem_mask=sel.numpy().reshape(B, H, W))
+
+    # NaN case (quirk Q2): a shard with no positive pixel at all.
+    imgs = [synth.make_image(92, i, 8, 8, "G", "no_pos") for i in range(B)]
+    inp = {k: np.stack([im[k] for im in imgs]) for k in imgs[0]}
+    yp, yl = T(inp["pix_logits"], True), T(inp["link_logits"], True)
+    out = ns["loss"](T(inp["pix_lab"]), yp, T(inp["link_lab"]), yl, torch.ones(B, 8, 8, 1))
+    out.backward()
+    # pixel logits are unconnected here (tf.cond takes no_pos -> constant 0): gradient None == zeros
+    gp = yp.grad.numpy() if yp.grad is not None else np.zeros_like(inp["pix_logits"])
+    save("model_loss_b14_nopos", pix_logits=inp["pix_logits"], link_logits=inp["link_logits"],
+         pix_lab=inp["pix_lab"], link_lab=inp["link_lab"], loss=out.detach().numpy(),
+         grad_pixel=gp, grad_link=yl.grad.numpy())
+
+    # dice_coefficient (model.py:145-159)
+    rng = np.random.default_rng(7)
+    t = (rng.uniform(size=(3, 9, 11, 1)) > 0.7).astype(np.float32)
+    p = rng.uniform(size=(3, 9, 11, 1)).astype(np.float32)
+    m = (rng.uniform(size=(3, 9, 11, 1)) > 0.1).astype(np.float32)
+    pt = T(p, True)
+    d = ns["dice_coefficient"](T(t), pt, T(m))
+    d.backward()
+    save("dice_coefficient", t=t, p=p, m=m, loss=d.detach().numpy(), grad=pt.grad.numpy())
+
+
+# ----------------------------------------------------------------------------- nets/model_vgg_16.py
+def golden_vgg16():
+    ns = ns_tf()
+    for fn in ("dice_coefficient", "loss", "cal_link_loss", "ohem_loss"):
+        src, span = cut("nets/model_vgg_16.py", fn)
+        print("nets/model_vgg_16.py", fn, span)
+        exec(src, ns)
+    B, H, W = 4, 12, 20
+    inp = synth.make_batch(93, B, H, W, "G")
+    rng = np.random.default_rng(11)
+    # dice head: predictions are probabilities (sigmoid outputs)
+    pp = (1 / (1 + np.exp(-(inp["pix_logits"][..., 1:2] - inp["pix_logits"][..., 0:1])))).astype(np.float32)
+    lk = inp["link_logits"].reshape(B, H, W, 8, 2)
+    lp = (1 / (1 + np.exp(-(lk[..., 1] - lk[..., 0])))).astype(np.float32)
+    m = (rng.uniform(size=(B, H, W, 1)) > 0.1).astype(np.float32)
+    ppt, lpt = T(pp, True), T(lp, True)
+    out = ns["loss"](T(inp["pix_lab"]), ppt, T(inp["link_lab"]), lpt, T(m))
+    out.backward()
+    save("vgg16_dice_loss", pix_lab=inp["pix_lab"], link_lab=inp["link_lab"], pix_prob=pp, link_prob=lp,
+         training_mask=m, loss=out.detach().numpy(), grad_pixel=ppt.grad.numpy(), grad_link=lpt.grad.numpy())
+
+    yp, yl = T(inp["pix_logits"], True), T(inp["link_logits"], True)
+    out = ns["ohem_loss"](T(inp["pix_lab"]), yp, T(inp["link_lab"]), yl, T(m))
+    out.backward()
+    save("vgg16_ohem_loss", pix_logits=inp["pix_logits"], link_logits=inp["link_logits"],
+         pix_lab=inp["pix_lab"], link_lab=inp["link_lab"], loss=out.detach().numpy(),
+         grad_pixel=yp.grad.numpy(), grad_link=yl.grad.numpy())
+
+
+# ----------------------------------------------------------------------------- nets/pixellink.py
+def golden_pixellink_build_loss():
+    src, span = cut("nets/pixellink.py", "build_loss", indent="    ")
+    print("nets/pixellink.py build_loss", span)
+    B, H, W = 5, 12, 20
+    kinds = ["normal", "normal", "normal", "no_pos", "many_pos"]
+    imgs = [synth.make_image(94, i, H, W, "G", kinds[i]) for i in range(B)]
+    inp = {k: np.stack([im[k] for im in imgs]) for k in imgs[0]}
+    config = types.SimpleNamespace(batch_size_per_gpu=B, max_neg_pos_ratio=3)
+    ns = ns_tf()
+    ns["config"] = config
+    exec(src, ns)
+    self = types.SimpleNamespace()
+    self.pixel_cls = T(inp["pix_logits"], True)
+    self.link_cls = T(inp["link_logits"], True)
+    self.pixel_scores = tf.slim.softmax(self.pixel_cls)
+    tf.reset_collections()
+    # capture the diagnostic OHNM mask: reduce_sum(seg_selected_mask) is its only consumer (:155)
+    captured = {}
+    real_sum = tf.reduce_sum
+
+    def spy_sum(x, axis=None):
+        if isinstance(x, torch.Tensor) and x.dtype == torch.float32 and tuple(x.shape) == (B, H, W) \
+                and "mask" not in captured and float(x.max()) <= 1.0 and float(x.min()) >= 0.0 \
+                and bool(((x == 0) | (x == 1)).all()):
+            captured["mask"] = x.detach().numpy().copy()
+        return real_sum(x, axis)
+
+    tf.reduce_sum = spy_sum
+    try:
+        ns["build_loss"](self, T(inp["pix_lab"][..., 0]), T(inp["link_lab"]))
+    finally:
+        tf.reduce_sum = real_sum
+    losses = tf.get_collection(tf.GraphKeys.LOSSES)
+    assert len(losses) == 2
+    total = losses[0] + losses[1]
+    total.backward()
+    save("pixellink_build_loss", pix_logits=inp["pix_logits"], link_logits=inp["link_logits"],
+         pix_lab=inp["pix_lab"], link_lab=inp["link_lab"],
+         losses=np.array([l.detach().numpy() for l in losses]),
+         grad_pixel=self.pixel_cls.grad.numpy(), grad_link=self.link_cls.grad.numpy(),
+         ohem_mask=captured["mask"])
+
+
+# ----------------------------------------------------------------------------- pure numpy pieces
+def golden_numpy_pieces():
+    ns = dict(np=np)
+    src, span = cut("tool/pixellink_fn.py", "pixel_detect")
+    print("tool/pixellink_fn.py pixel_detect", span)
+    exec(src, ns)
+    rng = np.random.default_rng(3)
+    H, W = 24, 40
+    score = rng.uniform(size=(1, H, W, 1)).astype(np.float32)
+    score[0, 5:15, 5:30, 0] = rng.uniform(0.7, 1.0, (10, 25))
+    geo = rng.uniform(0.6, 1.0, size=(8, 1, H, W, 2)).astype(np.float32)
+    res = ns["pixel_detect"](score, geo)
+    res2 = ns["pixel_detect"](score, geo, 0.75, 0.7)
+    save("pixel_detect", score=score, geo=geo, res=res, res_075_07=res2)
+
+    ns = dict(np=np)
+    for fn in ("restore_rectangle_rbox", "restore_rectangle"):
+        src, span = cut("datasets/icdar.py", fn)
+        print("datasets/icdar.py", fn, span)
+        exec(src, ns)
+    N = 64
+    origin = rng.uniform(0, 512, (N, 2)).astype(np.float32)
+    geom = np.concatenate([rng.uniform(1, 80, (N, 4)), rng.uniform(-0.7, 0.7, (N, 1))], 1).astype(np.float32)
+    geom[3, 4] = 0.0
+    out = ns["restore_rectangle"](origin, geom)
+    out_pos = ns["restore_rectangle"](origin[geom[:, 4] >= 0], geom[geom[:, 4] >= 0])
+    out_empty = ns["restore_rectangle"](origin[:0], geom[:0])
+    save("restore_rectangle", origin=origin, geometry=geom, out=out, out_pos_only=out_pos,
+         out_empty_shape=np.array(out_empty.shape))
+
+    import scipy.spatial.distance as dist
+    ns = dict(np=np, dist=dist)
+    for fn in ("order_points", "sort_poly"):
+        src, span = cut("test.py", fn)
+        print("test.py", fn, span)
+        exec(src, ns)
+    boxes = []
+    for _ in range(40):
+        c = rng.uniform(50, 400, 2)
+        a = rng.uniform(-np.pi / 2, np.pi / 2)
+        w, h = rng.uniform(10, 120), rng.uniform(5, 40)
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        p = (np.array([[-w, -h], [w, -h], [w, h], [-w, h]]) / 2) @ R.T + c
+        p = np.roll(p, int(rng.integers(0, 4)), 0)
+        boxes.append(p.astype(np.int64))
+    boxes = np.stack(boxes)
+    save("order_points", boxes=boxes, ordered=np.stack([ns["order_points"](b) for b in boxes]),
+         sorted_poly=np.stack([ns["sort_poly"](b) for b in boxes]))
+
+    # example.py:5,12 known answer: softmax of [[1,2],[3,4],[5,6],[7,8]] rows
+    x = torch.tensor([[[[1., 2.], [3., 4.], [5., 6.], [7., 8.]]]])
+    save("example_softmax", x=x.numpy(), y=tf.slim.softmax(x).numpy())
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    golden_model_loss()
+    golden_vgg16()
+    golden_pixellink_build_loss()
+    golden_numpy_pieces()
