@@ -1,0 +1,229 @@
+/*
+ * plhead.h — C ABI of libplhead.so: the B200-native (sm_100a) PixelLink / EAST
+ * per-pixel text-detection head.
+ *
+ * Drop-in boundary for the hot path of BowieHsu/tensorflow_ocr.
+ * The reference has no native code; its operator boundary is "Python callable
+ * handed numpy arrays" (tf.py_func, tool/pixellink_fn.py:114,157) plus plain
+ * Python functions building TF ops.  Each entry point below names the reference
+ * function (file:line under the reference root) whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - All tensor pointers are DEVICE pointers, NHWC, C-contiguous, fp32 unless
+ *    noted, 16-byte aligned.  The caller owns every buffer; the library
+ *    allocates nothing and keeps no state between calls.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work; they
+ *    never synchronise the host.  Re-entrant for distinct (stream, workspace).
+ *  - Return value: 0 ok; negative = argument / shape / alignment / workspace
+ *    error (PLH_E_*); positive = cudaError_t from a launch.  Nothing throws.
+ *  - Outputs are written in full (never accumulated into).
+ *  - NaN produced by empty link classes is DATA, not an error (nets/model.py:252-253).
+ */
+#ifndef PLHEAD_H_
+#define PLHEAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLH_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define PLH_API __attribute__((visibility("default")))
+#else
+#define PLH_API
+#endif
+
+/* error codes */
+#define PLH_OK 0
+#define PLH_E_NULL (-1)      /* required pointer is NULL */
+#define PLH_E_SHAPE (-2)     /* B/H/W/N out of range */
+#define PLH_E_ALIGN (-3)     /* pointer not 16-byte aligned */
+#define PLH_E_WORKSPACE (-4) /* workspace too small / NULL */
+#define PLH_E_PARAM (-5)     /* bad enum / parameter value */
+#define PLH_E_DEVICE (-6)    /* not an sm_100 device, or no CUDA device */
+
+/* ---- ops, for plh_workspace_bytes ---- */
+#define PLH_OP_LOSS 0
+#define PLH_OP_DECODE 1
+#define PLH_OP_DICE 2
+#define PLH_OP_EAST_LOSS 3
+#define PLH_OP_RESTORE 4
+#define PLH_OP_LOSS_DECODE 5 /* fused loss + decode sharing one logits read */
+
+/* ---- loss variants (which reference function the weights follow) ---- */
+#define PLH_VARIANT_MODEL 0     /* nets/model.py:204-261 loss(): OHEM 3:1, link CE x OHEM mask   */
+#define PLH_VARIANT_POS_ONLY 1  /* nets/model_vgg_16.py:243-282 ohem_loss(): positives only      */
+#define PLH_VARIANT_PIXELLINK 2 /* nets/pixellink.py:88-263 build_loss(): mean pixel CE, guarded */
+/* per-pixel term */
+#define PLH_TERM_CE 0    /* softmax cross entropy */
+#define PLH_TERM_FOCAL 1 /* focal loss, Lin et al. 2017 (NOT in the reference; parity unpinned) */
+
+typedef struct plh_loss_params {
+  int32_t variant;       /* PLH_VARIANT_* */
+  int32_t term;          /* PLH_TERM_* */
+  int32_t neg_pos_ratio; /* 3 (nets/model.py:171; config.max_neg_pos_ratio in nets/pixellink.py:116) */
+  float focal_alpha;     /* 0.25 */
+  float focal_gamma;     /* 2.0 */
+  int32_t reserved[3];
+} plh_loss_params;
+
+/* Layout of the `stats` output (device floats).  PLH_STATS_FLOATS + B entries. */
+#define PLH_STATS_FLOATS 64
+#define PLH_ST_TOTAL 0       /* returned loss: link + 2*pixel (model.py:261)               */
+#define PLH_ST_L_PIX 1       /* classification_loss (model.py:233) / pixel_cls_loss (pixellink.py:160) */
+#define PLH_ST_L_LINK 2      /* [8] per-direction link loss (model.py:254)                 */
+#define PLH_ST_N_SEG_POS 10  /* n_seg_pos (model.py:221; pixellink.py:155 = sum of selected) */
+#define PLH_ST_SUM_WP 11     /* [8] link_pos_n (model.py:249)                              */
+#define PLH_ST_SUM_WN 19     /* [8] link_neg_n (model.py:250)                              */
+#define PLH_ST_S_PIX 27      /* sum(term * selected_mask)                                  */
+#define PLH_ST_S_POS 28      /* [8] sum(term * W_link_pos)                                 */
+#define PLH_ST_S_NEG 36      /* [8] sum(term * W_link_neg)                                 */
+#define PLH_ST_LINK_TOTAL 44 /* weight_link_loss (model.py:256)                            */
+#define PLH_ST_N_SELECTED 45 /* number of pixels in the OHEM mask                          */
+#define PLH_ST_THR 64        /* [B] per-image OHEM threshold score, NaN = none selected    */
+
+/*
+ * PixelLink loss forward + backward, one fused pipeline.
+ * Replaces (per `variant`): nets/model.py:204-261 `loss` incl. OHNM_batch :186-197,
+ * OHNM_single_image :161-184, get_pos_and_neg_masks :199-202, slim.softmax :216;
+ * nets/model_vgg_16.py:243-282 `ohem_loss` + cal_link_loss :227-241;
+ * nets/pixellink.py:88-263 `PixelLinkNet.build_loss`; and TF autodiff of those.
+ *
+ *  pix_logits [B,H,W,2]  link_logits [B,H,W,16]  pix_lab [B,H,W(,1)]  link_lab [B,H,W,8]
+ *  train_mask: accepted, never read (nets/model.py ignores it), may be NULL.
+ *  stats      [PLH_STATS_FLOATS + B] floats (required)
+ *  grad_pix   [B,H,W,2]  / grad_link [B,H,W,16]: d loss / d logits for upstream
+ *             gradient 1.0; both NULL = forward only; otherwise both required.
+ *  ohem_mask  [B,H,W] uint8, optional: pixel_selected_mask (model.py:220).
+ *  decode_flags [B,H,W] uint16, optional: by-product for plh_decode_from_flags —
+ *             bit d (0..7) = link_d score > link_thresh, bit 8 = pixel score >
+ *             pixel_thresh (thresholds from `dp`, which may be NULL iff
+ *             decode_flags is NULL).
+ */
+struct plh_decode_params;
+PLH_API int plh_pixellink_loss(const float* pix_logits, const float* link_logits, const float* pix_lab,
+                       const float* link_lab, const float* train_mask, int B, int H, int W,
+                       const plh_loss_params* p, float* stats, float* grad_pix, float* grad_link,
+                       uint8_t* ohem_mask, uint16_t* decode_flags, const struct plh_decode_params* dp,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * OHEM selection only (nets/model.py:186-197 OHNM_batch with :161-184, or the
+ * nets/pixellink.py:106-150 variant when variant == PLH_VARIANT_PIXELLINK).
+ *  scores  [B,N] softmax probability of the NEGATIVE class
+ *  pos/neg [B,N] uint8 masks
+ *  n_pos   [B] int32 optional (device): overrides the count of pos_mask, as in
+ *          OHNM_single_image(scores, n_pos, neg_mask) where n_pos is an argument
+ *  selected_mask [B,N] float: pos + selected negatives;  thr [B] float.
+ */
+PLH_API int plh_ohnm_batch(const float* scores, const uint8_t* pos_mask, const uint8_t* neg_mask,
+                           const int32_t* n_pos, int B, int N, int variant, int neg_pos_ratio,
+                           float* selected_mask, float* thr, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/*
+ * nets/model.py:145-159 == nets/model_vgg_16.py:179-193 `dice_coefficient`:
+ * one scalar over the whole tensor; predictions are PROBABILITIES.
+ *  y_true / y_pred / mask [M] floats.  out [4]: loss, loss, I, U.
+ *  grad [M] optional: d loss / d y_pred = -2 m (t U - I) / U^2.
+ */
+PLH_API int plh_dice(const float* y_true, const float* y_pred, const float* mask, long long M, float* out, float* grad,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * nets/model_vgg_16.py:196-225 `loss`: 2*dice(pixel) + sum_d dice(link_d).
+ *  t_pix / p_pix [M,1], t_link / p_link [M,8], mask [M] (broadcast over channels).
+ *  out [28]: total, then (dice, I, U) for the pixel channel and the 8 link channels.
+ *  grad_pix [M,1] / grad_link [M,8] optional (both or neither).
+ */
+PLH_API int plh_dice_head(const float* t_pix, const float* p_pix, const float* t_link, const float* p_link,
+                  const float* mask, long long M, float* out, float* grad_pix, float* grad_link, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ---- decode ---- */
+typedef struct plh_decode_params {
+  float pixel_thresh; /* 0.8  (test_pixellink_fast.py:12) strict > */
+  float link_thresh;  /* 0.9  (test_pixellink_fast.py:13) strict > */
+  int32_t min_size;   /* 10   (test_pixellink_fast.py:174; 200 in test_pixellink.py:177): keep size > min_size */
+  int32_t max_boxes;  /* capacity K of the per-image box list */
+  double scale_x;     /* 4.0  = 1280/320 (test_pixellink_fast.py:196); must be >= 1 */
+  double scale_y;     /* 3.75 = 720/192  (test_pixellink_fast.py:197); must be >= 1 */
+  int32_t reserved[2];
+} plh_decode_params;
+
+/*
+ * PixelLink decode: test_pixellink_fast.py:110-202 (thresholds, directed
+ * 8-neighbour link graph from interior pixels, connected components, size
+ * filter, per-component cv2.minAreaRect -> cv2.boxPoints -> np.int0).
+ * Components are the weakly-connected components of the reference's edge set
+ * (SURVEY.md §8a D2), labelled by their minimum linear pixel index.
+ *
+ *  labels  [B,H,W] int32: -1 background / filtered, else min linear index y*W+x
+ *  boxes   [B,K,8] int32: x0,y0,...,x3,y3 in cv2.boxPoints order, components in
+ *          ascending label order; only the first min(n_boxes[b],K) rows are written
+ *  n_boxes [B] int32: number of components with size > min_size (may exceed K:
+ *          then only K are written)
+ *  rects   [B,K,5] float optional: cx, cy, w, h, angle of cv2.minAreaRect
+ *  comp    [B,K,2] int32 optional: label (min pixel index) and pixel count per box
+ * Limits: H <= 2048 rows, W*scale_x < 65536, H*scale_y < 65536.
+ */
+PLH_API int plh_decode(const float* pix_logits, const float* link_logits, int B, int H, int W,
+               const plh_decode_params* p, int32_t* labels, int32_t* boxes, int32_t* n_boxes, float* rects,
+               int32_t* comp, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, starting from the uint16 flags map emitted by plh_pixellink_loss. */
+PLH_API int plh_decode_from_flags(const uint16_t* flags, int B, int H, int W, const plh_decode_params* p,
+                          int32_t* labels, int32_t* boxes, int32_t* n_boxes, float* rects, int32_t* comp,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * cv2.minAreaRect -> cv2.boxPoints -> np.int0 for explicit point lists
+ * (test_pixellink_fast.py:199-200, test.py:190-191), one CTA per list.
+ *  pts [total,2] int32 (x,y) in the caller's order; offsets [n_sets+1] int32
+ *  boxes [n_sets,8] int32; rects [n_sets,5] float optional.  Each set <= 4096 points.
+ */
+PLH_API int plh_min_area_boxes(const int32_t* pts, const int32_t* offsets, int n_sets, int32_t* boxes, float* rects,
+                       void* stream);
+
+/*
+ * tool/pixellink_fn.py:120-154 `pixel_detect`: mask = score > thr_p AND, for all
+ * 8 directions, link score >= thr_l.   Inputs are softmax PROBABILITIES:
+ *  score [H,W] (score_map[0,:,:,0]);  link [8,H,W,2] (geo_map[:,0]); out [H,W] uint8.
+ */
+PLH_API int plh_pixel_detect(const float* score, const float* link, int H, int W, float score_map_thresh,
+                     float link_thresh, uint8_t* out, void* stream);
+
+/*
+ * datasets/icdar.py:410-483 `restore_rectangle_rbox`.
+ *  origin [N,2] fp32, geometry [N,5] fp32 (top,right,bottom,left,theta)
+ *  out [N,4,2] fp64, rows ordered theta>=0 first then theta<0 (icdar.py:479),
+ *  out_index [N] int32 optional: input row of each output row.
+ */
+PLH_API int plh_restore_rectangle(const float* origin, const float* geometry, int N, double* out, int32_t* out_index,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * EAST RBOX loss fwd+bwd — NOT in the reference; restated
+ * from upstream argman/EAST model.loss.  score [M] prob, geo [M,5].
+ *  out [8]: total, dice, L_g mean, I, U, sum(L_aabb*w), sum(L_theta*w), reserved
+ */
+PLH_API int plh_east_loss(const float* score_gt, const float* score_pred, const float* geo_gt, const float* geo_pred,
+                  const float* mask, long long M, float* out, float* grad_score, float* grad_geo,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- housekeeping ---- */
+/* `K` = plh_decode_params.max_boxes for the decode ops, ignored otherwise */
+PLH_API size_t plh_workspace_bytes(int op, int B, int H, int W, int K);
+PLH_API int plh_version(void);
+PLH_API const char* plh_strerror(int code);
+/* number of kernels the library has launched in this process (for bench.py's gpu_launches) */
+PLH_API long long plh_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLHEAD_H_ */

@@ -1,0 +1,471 @@
+// aux.cu — dice head, EAST RBOX loss, restore_rectangle, and housekeeping entry points.
+//
+//  dice      nets/model.py:145-159 == nets/model_vgg_16.py:179-193 dice_coefficient,
+//            nets/model_vgg_16.py:196-225 loss (2*dice(pixel) + sum_d dice(link_d))  [L7, L8]
+//  east      EAST RBOX loss — NOT in the reference; restated from upstream argman/EAST
+//            model.loss (parity unpinned)
+//  restore   datasets/icdar.py:410-483 restore_rectangle_rbox                        [E1]
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace plh {
+
+size_t loss_workspace_bytes(int B, int H, int W);             // loss.cu
+size_t decode_workspace_bytes(int B, int H, int W, int K);    // decode.cu
+
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxCTAs = kNumSMs * 8;
+
+struct RedHeader {
+  unsigned ticket;
+  int pad[31];
+};
+
+// ------------------------------------------------------------------ dice
+// Pass 1: per channel c: I_c = sum t*p*m, T_c = sum t*m, P_c = sum p*m  (fp32 products,
+// fp32 per-thread partials, fp64 across CTAs in a fixed order).
+// Channels: CA from tensor A ([M,CA]) followed by CB from tensor B ([M,CB]).
+template <int CA, int CB>
+__global__ void __launch_bounds__(kRedThreads)
+dice_reduce_kernel(const float* __restrict__ tA, const float* __restrict__ pA, const float* __restrict__ tB,
+                   const float* __restrict__ pB, const float* __restrict__ mask, long long M,
+                   float* __restrict__ partials, RedHeader* __restrict__ hdr, const float wA, const float wB,
+                   float* __restrict__ out) {
+  constexpr int C = CA + CB;
+  __shared__ float s_red[kRedThreads / 32][3 * C];
+  __shared__ bool s_last;
+  float acc[3 * C];
+#pragma unroll
+  for (int i = 0; i < 3 * C; ++i) acc[i] = 0.f;
+  const long long stride = (long long)gridDim.x * kRedThreads;
+  for (long long i = (long long)blockIdx.x * kRedThreads + threadIdx.x; i < M; i += stride) {
+    const float m = __ldg(mask + i);
+    float t[C], p[C];
+#pragma unroll
+    for (int c = 0; c < CA; ++c) t[c] = __ldg(tA + i * CA + c), p[c] = __ldg(pA + i * CA + c);
+    if (CB == 8) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(tB) + i * 2), b = __ldg(reinterpret_cast<const float4*>(tB) + i * 2 + 1);
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(pB) + i * 2), d4 = __ldg(reinterpret_cast<const float4*>(pB) + i * 2 + 1);
+      t[CA + 0] = a.x, t[CA + 1] = a.y, t[CA + 2] = a.z, t[CA + 3] = a.w;
+      t[CA + 4] = b.x, t[CA + 5] = b.y, t[CA + 6] = b.z, t[CA + 7] = b.w;
+      p[CA + 0] = c4.x, p[CA + 1] = c4.y, p[CA + 2] = c4.z, p[CA + 3] = c4.w;
+      p[CA + 4] = d4.x, p[CA + 5] = d4.y, p[CA + 6] = d4.z, p[CA + 7] = d4.w;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      acc[3 * c + 0] += t[c] * p[c] * m;  // y_true * y_pred * training_mask (model.py:155)
+      acc[3 * c + 1] += t[c] * m;
+      acc[3 * c + 2] += p[c] * m;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 3 * C; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRedThreads / 32; ++w) s += s_red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 32 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&hdr->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double s_fin[3 * C];
+  if (threadIdx.x < 3 * C) {
+    double s = 0.0;
+    for (unsigned c = 0; c < gridDim.x; ++c) s += (double)__ldcg(partials + (size_t)c * 32 + threadIdx.x);
+    s_fin[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // out: [0] total, then per channel: dice, I, U
+    float total = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float I = (float)s_fin[3 * c];
+      const float U = __fadd_rn(__fadd_rn((float)s_fin[3 * c + 1], (float)s_fin[3 * c + 2]), 1e-5f);  // model.py:154,156
+      const float dice = __fsub_rn(1.f, __fdiv_rn(__fmul_rn(2.f, I), U));                               // model.py:157
+      out[1 + 3 * c] = dice, out[2 + 3 * c] = I, out[3 + 3 * c] = U;
+      total += (c < CA ? wA : wB) * dice;
+    }
+    out[0] = total;
+    hdr->ticket = 0;
+  }
+}
+
+// Pass 2: grad wrt pred = -2 w m (t U - I) / U^2
+template <int CA, int CB>
+__global__ void __launch_bounds__(kRedThreads)
+dice_grad_kernel(const float* __restrict__ tA, const float* __restrict__ tB, const float* __restrict__ mask,
+                 long long M, const float* __restrict__ out, const float wA, const float wB,
+                 float* __restrict__ gA, float* __restrict__ gB) {
+  constexpr int C = CA + CB;
+  float I[C], U[C], k[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    I[c] = out[2 + 3 * c], U[c] = out[3 + 3 * c];
+    k[c] = (c < CA ? wA : wB) * -2.f;
+  }
+  const long long stride = (long long)gridDim.x * kRedThreads;
+  for (long long i = (long long)blockIdx.x * kRedThreads + threadIdx.x; i < M; i += stride) {
+    const float m = __ldg(mask + i);
+#pragma unroll
+    for (int c = 0; c < CA; ++c) {
+      const float t = __ldg(tA + i * CA + c);
+      gA[i * CA + c] = k[c] * m * (t * U[c] - I[c]) / (U[c] * U[c]);
+    }
+    if (CB == 8) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(tB) + i * 2), b = __ldg(reinterpret_cast<const float4*>(tB) + i * 2 + 1);
+      const float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float g[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] = k[CA + c] * m * (t[c] * U[CA + c] - I[CA + c]) / (U[CA + c] * U[CA + c]);
+      stg_stream4(reinterpret_cast<float4*>(gB) + i * 2, make_float4(g[0], g[1], g[2], g[3]));
+      stg_stream4(reinterpret_cast<float4*>(gB) + i * 2 + 1, make_float4(g[4], g[5], g[6], g[7]));
+    }
+  }
+}
+
+static size_t red_workspace_bytes() { return 256 + sizeof(float) * 32 * kRedMaxCTAs; }
+
+template <int CA, int CB>
+static int run_dice(const float* tA, const float* pA, const float* tB, const float* pB, const float* mask, long long M,
+                    float wA, float wB, float* out, float* gA, float* gB, void* workspace, size_t workspace_bytes,
+                    cudaStream_t s) {
+  if (!workspace || workspace_bytes < red_workspace_bytes() || !aligned16(workspace)) return PLH_E_WORKSPACE;
+  RedHeader* hdr = (RedHeader*)workspace;
+  float* partials = (float*)((char*)workspace + 256);
+  cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(RedHeader), s);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = (int)std::min<long long>((M + kRedThreads - 1) / kRedThreads, kRedMaxCTAs);
+  dice_reduce_kernel<CA, CB><<<grid, kRedThreads, 0, s>>>(tA, pA, tB, pB, mask, M, partials, hdr, wA, wB, out);
+  int rc = launch_status();
+  if (rc) return rc;
+  if (gA || gB) {
+    dice_grad_kernel<CA, CB><<<grid, kRedThreads, 0, s>>>(tA, tB, mask, M, out, wA, wB, gA, gB);
+    rc = launch_status();
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------ EAST RBOX loss (upstream argman/EAST)
+// L = mean(y_true * mask * (L_AABB + 20 L_theta)) + 0.01 * dice(y_true, y_pred, mask)
+__global__ void __launch_bounds__(kRedThreads)
+east_reduce_kernel(const float* __restrict__ sg, const float* __restrict__ sp, const float* __restrict__ gg,
+                   const float* __restrict__ gp, const float* __restrict__ mask, long long M,
+                   float* __restrict__ partials, RedHeader* __restrict__ hdr, float* __restrict__ out) {
+  __shared__ float s_red[kRedThreads / 32][5];
+  __shared__ bool s_last;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // I, T, P, sum aabb*w, sum theta*w
+  const long long stride = (long long)gridDim.x * kRedThreads;
+  for (long long i = (long long)blockIdx.x * kRedThreads + threadIdx.x; i < M; i += stride) {
+    const float m = __ldg(mask + i), t = __ldg(sg + i), p = __ldg(sp + i);
+    acc[0] += t * p * m, acc[1] += t * m, acc[2] += p * m;
+    const float w = t * m;
+    float g[5], q[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) g[c] = __ldg(gg + i * 5 + c), q[c] = __ldg(gp + i * 5 + c);
+    const float area_gt = (g[0] + g[2]) * (g[1] + g[3]);
+    const float area_pr = (q[0] + q[2]) * (q[1] + q[3]);
+    const float w_union = fminf(g[1], q[1]) + fminf(g[3], q[3]);
+    const float h_union = fminf(g[0], q[0]) + fminf(g[2], q[2]);
+    const float ai = w_union * h_union;
+    const float au = area_gt + area_pr - ai;
+    const float l_aabb = -logf((ai + 1.f) / (au + 1.f));
+    const float l_theta = 1.f - cosf(q[4] - g[4]);
+    acc[3] += l_aabb * w, acc[4] += l_theta * w;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRedThreads / 32; ++w) s += s_red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 32 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&hdr->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double s_fin[5];
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    for (unsigned c = 0; c < gridDim.x; ++c) s += (double)__ldcg(partials + (size_t)c * 32 + threadIdx.x);
+    s_fin[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float I = (float)s_fin[0];
+    const float U = (float)s_fin[1] + (float)s_fin[2] + 1e-5f;
+    const float dice = 1.f - 2.f * I / U;
+    const float lg = (float)((s_fin[3] + 20.0 * s_fin[4]) / (double)M);
+    out[0] = lg + 0.01f * dice;
+    out[1] = dice, out[2] = lg, out[3] = I, out[4] = U;
+    out[5] = (float)s_fin[3], out[6] = (float)s_fin[4], out[7] = 0.f;
+    hdr->ticket = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+east_grad_kernel(const float* __restrict__ sg, const float* __restrict__ gg, const float* __restrict__ gp,
+                 const float* __restrict__ mask, long long M, const float* __restrict__ out,
+                 float* __restrict__ grad_score, float* __restrict__ grad_geo) {
+  const float I = out[3], U = out[4];
+  const float invM = 1.f / (float)M;
+  const long long stride = (long long)gridDim.x * kRedThreads;
+  for (long long i = (long long)blockIdx.x * kRedThreads + threadIdx.x; i < M; i += stride) {
+    const float m = __ldg(mask + i), t = __ldg(sg + i);
+    grad_score[i] = 0.01f * -2.f * m * (t * U - I) / (U * U);
+    const float w = t * m * invM;
+    float g[5], q[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) g[c] = __ldg(gg + i * 5 + c), q[c] = __ldg(gp + i * 5 + c);
+    const float w_union = fminf(g[1], q[1]) + fminf(g[3], q[3]);
+    const float h_union = fminf(g[0], q[0]) + fminf(g[2], q[2]);
+    const float ai = w_union * h_union;
+    const float au = (g[0] + g[2]) * (g[1] + g[3]) + (q[0] + q[2]) * (q[1] + q[3]) - ai;
+    const float ri = 1.f / (ai + 1.f), ru = 1.f / (au + 1.f);
+    // tf.minimum(gt, pred): the gradient goes to pred only where pred < gt
+    const float dAi[4] = {q[0] < g[0] ? w_union : 0.f, q[1] < g[1] ? h_union : 0.f, q[2] < g[2] ? w_union : 0.f,
+                          q[3] < g[3] ? h_union : 0.f};
+    const float dAp[4] = {q[1] + q[3], q[0] + q[2], q[1] + q[3], q[0] + q[2]};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) grad_geo[i * 5 + c] = w * (-ri * dAi[c] + ru * (dAp[c] - dAi[c]));
+    grad_geo[i * 5 + 4] = w * 20.f * sinf(q[4] - g[4]);
+  }
+}
+
+// ------------------------------------------------------------------ restore_rectangle_rbox
+// icdar.py:479 returns the theta >= 0 rows first, then the theta < 0 rows (quirk Q16):
+// a stable partition, done with a block-count / scan / scatter triple.
+constexpr int kRRBlock = 1024;
+
+__global__ void __launch_bounds__(kRRBlock)
+rr_count_kernel(const float* __restrict__ geometry, int N, int* __restrict__ blockcnt) {
+  __shared__ int s_c;
+  if (threadIdx.x == 0) s_c = 0;
+  __syncthreads();
+  const int i = blockIdx.x * kRRBlock + threadIdx.x;
+  const bool nn = i < N && geometry[(size_t)i * 5 + 4] >= 0.f;
+  const unsigned m = __ballot_sync(0xffffffffu, nn);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_c, __popc(m));
+  __syncthreads();
+  if (threadIdx.x == 0) blockcnt[blockIdx.x] = s_c;
+}
+
+__global__ void __launch_bounds__(1024) rr_scan_kernel(int* __restrict__ blockcnt, int nb, int* __restrict__ total) {
+  // exclusive scan of blockcnt in place by one CTA
+  __shared__ int s_w[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nb; i0 += 1024) {
+    const int i = i0 + tid;
+    const int v = i < nb ? blockcnt[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int wv = s_w[lane];
+      int winc = wv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      s_w[lane] = winc - wv;
+    }
+    __syncthreads();
+    const int excl = s_base + s_w[warp] + inc - v;
+    if (i < nb) blockcnt[i] = excl;
+    __syncthreads();
+    if (tid == 1023) s_base = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) *total = s_base;
+}
+
+__global__ void __launch_bounds__(kRRBlock)
+rr_scatter_kernel(const float* __restrict__ origin, const float* __restrict__ geometry, int N,
+                  const int* __restrict__ blockoff, const int* __restrict__ total_nn, double* __restrict__ out,
+                  int32_t* __restrict__ out_index) {
+  __shared__ int s_w[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x * kRRBlock + tid;
+  const bool valid = i < N;
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, th = -1.f;
+  if (valid) {
+    const float* g = geometry + (size_t)i * 5;
+    d0 = g[0], d1 = g[1], d2 = g[2], d3 = g[3], th = g[4];
+  }
+  const bool nn = valid && th >= 0.f;
+  const unsigned m = __ballot_sync(0xffffffffu, nn);
+  if (lane == 0) s_w[warp] = __popc(m);
+  __syncthreads();
+  if (warp == 0) {
+    const int wv = s_w[lane];
+    int winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_w[lane] = winc - wv;
+  }
+  __syncthreads();
+  if (!valid) return;
+  const int nn_before = blockoff[blockIdx.x] + s_w[warp] + __popc(m & ((1u << lane) - 1u));
+  const int row = nn ? nn_before : *total_nn + (i - nn_before);
+  // fp32 sums of the distances (numpy fp32 arithmetic), fp32 cos/sin of the fp32 angle,
+  // products and sums in fp64 (numpy upcasts: np.zeros is float64), icdar.py:417-443 / :450-476
+  const float hh = -d0 - d2;
+  double px[5], py[5];
+  double c, s_;
+  if (nn) {
+    const float ww = d1 + d3;
+    px[0] = 0.0, py[0] = hh; px[1] = ww, py[1] = hh; px[2] = ww, py[2] = 0.0; px[3] = 0.0, py[3] = 0.0;
+    px[4] = d3, py[4] = -d2;
+    c = (double)(float)cos((double)th), s_ = (double)(float)sin((double)th);
+    // rotate_matrix_x = [cos, sin], rotate_matrix_y = [-sin, cos]
+  } else {
+    const float ww = -d1 - d3;
+    px[0] = ww, py[0] = hh; px[1] = 0.0, py[1] = hh; px[2] = 0.0, py[2] = 0.0; px[3] = ww, py[3] = 0.0;
+    px[4] = -d1, py[4] = -d2;
+    const float nth = -th;
+    c = (double)(float)cos((double)nth), s_ = -(double)(float)sin((double)nth);
+    // rotate_matrix_x = [cos(-a), -sin(-a)], rotate_matrix_y = [sin(-a), cos(-a)]
+  }
+  double rx[5], ry[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    rx[k] = __dadd_rn(__dmul_rn(c, px[k]), __dmul_rn(s_, py[k]));
+    ry[k] = __dadd_rn(__dmul_rn(-s_, px[k]), __dmul_rn(c, py[k]));
+  }
+  const double ox = (double)origin[(size_t)i * 2] - rx[4], oy = (double)origin[(size_t)i * 2 + 1] - ry[4];
+  double* o = out + (size_t)row * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[2 * k] = rx[k] + ox, o[2 * k + 1] = ry[k] + oy;
+  if (out_index) out_index[row] = i;
+}
+
+}  // namespace plh
+
+using namespace plh;
+
+extern "C" int plh_dice(const float* y_true, const float* y_pred, const float* mask, long long M, float* out,
+                        float* grad, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y_true || !y_pred || !mask || !out) return PLH_E_NULL;
+  if (M <= 0) return PLH_E_SHAPE;
+  return run_dice<1, 0>(y_true, y_pred, nullptr, nullptr, mask, M, 1.f, 0.f, out, grad, nullptr, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int plh_dice_head(const float* t_pix, const float* p_pix, const float* t_link, const float* p_link,
+                             const float* mask, long long M, float* out, float* grad_pix, float* grad_link,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (!t_pix || !p_pix || !t_link || !p_link || !mask || !out) return PLH_E_NULL;
+  if ((grad_pix == nullptr) != (grad_link == nullptr)) return PLH_E_NULL;
+  if (M <= 0) return PLH_E_SHAPE;
+  if (!aligned16(t_link) || !aligned16(p_link) || (grad_link && !aligned16(grad_link))) return PLH_E_ALIGN;
+  // model_vgg_16.py:205,223-225: classification (pixel) dice x2, the 8 link dice x1
+  return run_dice<1, 8>(t_pix, p_pix, t_link, p_link, mask, M, 2.f, 1.f, out, grad_pix, grad_link, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int plh_east_loss(const float* score_gt, const float* score_pred, const float* geo_gt,
+                             const float* geo_pred, const float* mask, long long M, float* out, float* grad_score,
+                             float* grad_geo, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!score_gt || !score_pred || !geo_gt || !geo_pred || !mask || !out) return PLH_E_NULL;
+  if ((grad_score == nullptr) != (grad_geo == nullptr)) return PLH_E_NULL;
+  if (M <= 0) return PLH_E_SHAPE;
+  if (!workspace || workspace_bytes < red_workspace_bytes() || !aligned16(workspace)) return PLH_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  RedHeader* hdr = (RedHeader*)workspace;
+  float* partials = (float*)((char*)workspace + 256);
+  cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(RedHeader), s);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = (int)std::min<long long>((M + kRedThreads - 1) / kRedThreads, kRedMaxCTAs);
+  east_reduce_kernel<<<grid, kRedThreads, 0, s>>>(score_gt, score_pred, geo_gt, geo_pred, mask, M, partials, hdr, out);
+  int rc = launch_status();
+  if (rc) return rc;
+  if (grad_score) {
+    east_grad_kernel<<<grid, kRedThreads, 0, s>>>(score_gt, geo_gt, geo_pred, mask, M, out, grad_score, grad_geo);
+    rc = launch_status();
+  }
+  return rc;
+}
+
+extern "C" int plh_restore_rectangle(const float* origin, const float* geometry, int N, double* out,
+                                     int32_t* out_index, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N == 0) return PLH_OK;
+  if (!origin || !geometry || !out) return PLH_E_NULL;
+  if (N < 0) return PLH_E_SHAPE;
+  const int nb = (N + kRRBlock - 1) / kRRBlock;
+  if (!workspace || workspace_bytes < (size_t)(nb + 1) * 4 + 256) return PLH_E_WORKSPACE;
+  int* blockcnt = (int*)workspace;
+  int* total = blockcnt + nb;
+  cudaStream_t s = (cudaStream_t)stream;
+  rr_count_kernel<<<nb, kRRBlock, 0, s>>>(geometry, N, blockcnt);
+  int rc = launch_status();
+  if (rc) return rc;
+  rr_scan_kernel<<<1, 1024, 0, s>>>(blockcnt, nb, total);
+  if ((rc = launch_status())) return rc;
+  rr_scatter_kernel<<<nb, kRRBlock, 0, s>>>(origin, geometry, N, blockcnt, total, out, out_index);
+  return launch_status();
+}
+
+extern "C" size_t plh_workspace_bytes(int op, int B, int H, int W, int K) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  switch (op) {
+    case PLH_OP_LOSS: return loss_workspace_bytes(B, H, W);
+    case PLH_OP_DECODE: return decode_workspace_bytes(B, H, W, K > 0 ? K : 1);
+    case PLH_OP_LOSS_DECODE:
+      return align_up(loss_workspace_bytes(B, H, W), 256) + decode_workspace_bytes(B, H, W, K > 0 ? K : 1);
+    case PLH_OP_DICE:
+    case PLH_OP_EAST_LOSS: return red_workspace_bytes();
+    case PLH_OP_RESTORE: return ((size_t)B * H * W / kRRBlock + 2) * 4 + 256;
+    default: return 0;
+  }
+}
+
+extern "C" int plh_version(void) { return PLH_VERSION; }
+
+extern "C" const char* plh_strerror(int code) {
+  switch (code) {
+    case PLH_OK: return "ok";
+    case PLH_E_NULL: return "required pointer is NULL";
+    case PLH_E_SHAPE: return "shape out of range";
+    case PLH_E_ALIGN: return "pointer not 16-byte aligned";
+    case PLH_E_WORKSPACE: return "workspace missing, misaligned or too small";
+    case PLH_E_PARAM: return "bad parameter value";
+    case PLH_E_DEVICE: return "no sm_100 CUDA device";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown plhead error";
+  }
+}
+
+extern "C" long long plh_launch_count(void) { return g_launch_count.load(); }

@@ -1,0 +1,59 @@
+// common.cuh — shared helpers for libplhead.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/plhead.h"
+
+namespace plh {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+extern std::atomic<long long> g_launch_count;
+
+inline int launch_status() {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? PLH_OK : (int)e;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// 128-bit streaming loads/stores: inputs are read once and outputs written once,
+// so keep them out of L1 (L2 still caches them for the later passes).
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_stream2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg_stream2(float2* p, float2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// The pixel score the OHEM selection ranks: softmax probability of the NEGATIVE
+// class with TensorFlow's formula exp(x-max)/sum (slim.softmax, nets/model.py:216-217).
+// Accurate expf + IEEE division on purpose: every kernel that needs the score calls
+// this one function, so the mask is self-consistent bit for bit.
+__device__ __forceinline__ float neg_class_score(float x0, float x1) {
+  const float m = fmaxf(x0, x1);
+  const float e0 = expf(x0 - m);
+  const float e1 = expf(x1 - m);
+  return __fdiv_rn(e0, __fadd_rn(e0, e1));
+}
+
+}  // namespace plh

@@ -1,0 +1,484 @@
+// decode.cu — PixelLink inference decode for sm_100a.
+//
+// Replaces test_pixellink_fast.py:110-202 / test_pixellink.py:107-217 (thresholds,
+// directed 8-neighbour link graph from interior pixels, connected components,
+// size filter, per-component minAreaRect -> boxPoints -> int0) and
+// tool/pixellink_fn.py:120-154 pixel_detect.
+//
+// Pipeline (one stream, no host sync):
+//   D0 flags      logits -> uint16 flags (bit d = link_d score > thr_l, bit 8 = pixel
+//                 score > thr_p), decided in logit-difference space (no exp), and
+//                 parent[v] = v / -1, size[v] = 0.       reads 72 B/px, writes 10 B/px
+//                 (or, in the fused path, flags come from the loss kernel and D0'
+//                 only initialises parent/size)
+//   D1 union      lock-free union-find over the reference's edge set, hooking the
+//                 larger root under the smaller (atomicMin) -> root = min pixel index
+//   D2 flatten    parent[v] = root, component sizes (warp-aggregated atomics),
+//                 border pixels that no edge reaches are dropped (not graph nodes)
+//   D3 compact    one CTA per image: roots with size > min_size in ascending order
+//                 -> box slots
+//   D4 labels     final label map + per-(component,row) min/max x (run-end atomics)
+//   D5 rects      one CTA per component: row extremes -> sort -> OpenCV-exact hull +
+//                 rotating calipers -> 4 integer corners (rect.cuh)
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "rect.cuh"
+
+namespace plh {
+
+float prob_to_logit_threshold(float t);  // loss.cu
+
+// neighbour table (tool/pixellink_fn.py:93-108; test_pixellink_fast.py:124-146)
+__constant__ int c_dy[8] = {0, 1, -1, 0, 1, -1, -1, 1};
+__constant__ int c_dx[8] = {-1, -1, -1, 1, 1, 1, 0, 0};
+
+constexpr int kFlagP = 1 << 8;
+
+struct DecodeWsLayout {
+  size_t flags, parent, size, comp_root, comp_size, rowmin, rowmax, total;
+};
+
+static DecodeWsLayout decode_ws_layout(int B, int H, int W, int K) {
+  DecodeWsLayout l;
+  const size_t px = (size_t)B * H * W;
+  size_t off = 0;
+  l.flags = off; off = align_up(off + px * 2, 256);
+  l.parent = off; off = align_up(off + px * 4, 256);
+  l.size = off; off = align_up(off + px * 4, 256);
+  l.comp_root = off; off = align_up(off + (size_t)B * K * 4, 256);
+  l.comp_size = off; off = align_up(off + (size_t)B * K * 4, 256);
+  l.rowmin = off; off = align_up(off + (size_t)B * K * H * 4, 256);
+  l.rowmax = off; off = align_up(off + (size_t)B * K * H * 4, 256);
+  l.total = off;
+  return l;
+}
+size_t decode_workspace_bytes(int B, int H, int W, int K) { return decode_ws_layout(B, H, W, K).total; }
+
+// ------------------------------------------------------------------ D0: flags from logits (+ init)
+__global__ void __launch_bounds__(256)
+decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restrict__ link_logits, long long total_px,
+                    float tp_logit, float tl_logit, uint16_t* __restrict__ flags, int* __restrict__ parent,
+                    int* __restrict__ size) {
+  const int lane = threadIdx.x & 31;
+  const int j = threadIdx.x & 3;
+  const long long Q = total_px * 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4* ll4 = reinterpret_cast<const float4*>(link_logits);
+  const float2* pl2 = reinterpret_cast<const float2*>(pix_logits);
+  for (long long w0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < Q; w0 += stride) {
+    const long long q = w0 + lane;
+    const bool valid = q < Q;
+    float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 P = make_float2(0.f, 0.f);
+    const long long px = q >> 2;
+    if (valid) {
+      L = ldg_stream4(ll4 + q);
+      P = __ldg(pl2 + px);
+    }
+    unsigned bits = ((L.y - L.x) > tl_logit ? 1u : 0u) << (2 * j) | ((L.w - L.z) > tl_logit ? 1u : 0u) << (2 * j + 1);
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+    if (valid && j == 0) {
+      const bool p = (P.y - P.x) > tp_logit;
+      flags[px] = (uint16_t)(bits | (p ? kFlagP : 0));
+      parent[px] = p ? (int)px : -1;
+      size[px] = 0;
+    }
+  }
+}
+
+// D0': init only (flags already produced by the fused loss kernel)
+__global__ void __launch_bounds__(256)
+decode_init_kernel(const uint16_t* __restrict__ flags, long long total_px, int* __restrict__ parent,
+                   int* __restrict__ size) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < total_px; px += stride) {
+    parent[px] = (flags[px] & kFlagP) ? (int)px : -1;
+    size[px] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ D1: union-find
+__device__ __forceinline__ int find_root(int* parent, int v) {
+  volatile int* P = parent;
+  int p = P[v];
+  while (p != v) {
+    const int gp = P[p];
+    if (gp != p) P[v] = gp;  // path halving; benign race (pointers only move rootwards)
+    v = p;
+    p = gp;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void unite(int* parent, int a, int b) {
+  while (true) {
+    a = find_root(parent, a);
+    b = find_root(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }  // hook the larger root under the smaller
+    const int old = atomicMin(&parent[a], b);
+    if (old == a) return;
+    a = old;  // somebody re-parented a meanwhile: retry from there
+  }
+}
+
+// Edge set of the reference (test_pixellink_fast.py:119-146): only INTERIOR pixels
+// (1 <= x <= W-2, 1 <= y <= H-2) that pass the pixel threshold emit edges, to the
+// neighbour in direction d iff link_d passes AND the neighbour passes the pixel
+// threshold.  Connectivity is taken undirected (weakly-connected components).
+__global__ void __launch_bounds__(256)
+decode_union_kernel(const uint16_t* __restrict__ flags, int H, int W, long long total_px, int* __restrict__ parent) {
+  const int N = H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
+    const unsigned f = flags[g];
+    if (!(f & kFlagP) || !(f & 0xffu)) continue;
+    const int v = (int)(g % N);
+    const int y = v / W, x = v - y * W;
+    if (x < 1 || x > W - 2 || y < 1 || y > H - 2) continue;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      if (f & (1u << d)) {
+        const long long u = g + c_dy[d] * W + c_dx[d];
+        if (flags[u] & kFlagP) unite(parent, (int)g, (int)u);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ D2: flatten + sizes
+__global__ void __launch_bounds__(256)
+decode_flatten_kernel(const uint16_t* __restrict__ flags, int H, int W, long long total_px, int* __restrict__ parent,
+                      int* __restrict__ size) {
+  const int N = H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long start = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  const int lane = threadIdx.x & 31;
+  for (long long w0 = start; w0 < total_px; w0 += stride) {
+    const long long g = w0 + lane;
+    int root = -1;
+    if (g < total_px && (flags[g] & kFlagP)) {
+      const int v = (int)(g % N);
+      const int y = v / W, x = v - y * W;
+      bool node = true;
+      if (x < 1 || x > W - 2 || y < 1 || y > H - 2) {
+        // a border pixel is a graph node only if some interior neighbour links to it
+        node = false;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          const int sy = y - c_dy[d], sx = x - c_dx[d];  // source s with s + off(d) == this pixel
+          if (sx >= 1 && sx <= W - 2 && sy >= 1 && sy <= H - 2) {
+            const unsigned fs = flags[g - (long long)c_dy[d] * W - c_dx[d]];
+            if ((fs & kFlagP) && (fs & (1u << d))) node = true;
+          }
+        }
+      }
+      if (node) {
+        root = find_root(parent, (int)g);
+        parent[g] = root;
+      } else {
+        parent[g] = -1;
+      }
+    }
+    // warp-aggregated size count
+    const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
+    if (root >= 0) {
+      const unsigned peers = __match_any_sync(active, root);
+      if ((__ffs(peers) - 1) == lane) atomicAdd(&size[root], __popc(peers));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ D3: per-image ordered compaction
+// After this kernel size[root] holds the box slot of a kept component (may be >= K:
+// kept, but no box row) or -1 for a filtered one.
+__global__ void __launch_bounds__(1024)
+decode_compact_kernel(const int* __restrict__ parent, int* __restrict__ size, int N, int min_size, int K,
+                      int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes,
+                      int* __restrict__ rowmin, int* __restrict__ rowmax, int H) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_total;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long base = (long long)b * N;
+  if (tid == 0) s_base = 0;
+  for (int i0 = 0; i0 < N; i0 += 1024) {
+    const int i = i0 + tid;
+    bool is_root = false, keep = false;
+    int sz = 0;
+    if (i < N) {
+      is_root = parent[base + i] == (int)(base + i);
+      if (is_root) {
+        sz = size[base + i];
+        keep = sz > min_size;  // test_pixellink_fast.py:174 `len(index_list) > 10`
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_warp[lane];
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      s_warp[lane] = inc - v;  // exclusive prefix over warps
+      if (lane == 31) s_total = inc;
+    }
+    __syncthreads();
+    const int slot = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
+    if (is_root) {
+      if (keep) {
+        size[base + i] = slot;
+        if (slot < K) {
+          comp_root[(size_t)b * K + slot] = i;
+          comp_size[(size_t)b * K + slot] = sz;
+        }
+      } else {
+        size[base + i] = -1;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_base += s_total;
+  }
+  __syncthreads();
+  const int total = s_base;
+  if (tid == 0) n_boxes[b] = total;
+  // initialise the row-extreme tables of the used slots
+  const int used = min(total, K);
+  for (int i = tid; i < used * H; i += 1024) {
+    rowmin[(size_t)b * K * H + i] = 0x7fffffff;
+    rowmax[(size_t)b * K * H + i] = -1;
+  }
+}
+
+// ------------------------------------------------------------------ D4: labels + row extremes
+__global__ void __launch_bounds__(256)
+decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ size, int H, int W, long long total_px,
+                     int K, int32_t* __restrict__ labels, int* __restrict__ rowmin, int* __restrict__ rowmax) {
+  const int N = H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
+    const int b = (int)(g / N);
+    const int v = (int)(g - (long long)b * N);
+    const int y = v / W, x = v - y * W;
+    const int r = parent[g];
+    int slot = -1;
+    if (r >= 0) slot = size[r];
+    labels[g] = slot >= 0 ? r - b * N : -1;
+    if (slot >= 0 && slot < K) {
+      // run ends only: the first / last pixel of each horizontal run of this component
+      const bool run_start = (x == 0) || (parent[g - 1] != r);
+      const bool run_end = (x == W - 1) || (parent[g + 1] != r);
+      const size_t row = ((size_t)b * K + slot) * H + y;
+      if (run_start) atomicMin(&rowmin[row], x);
+      if (run_end) atomicMax(&rowmax[row], x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ D5: one CTA per component
+__global__ void __launch_bounds__(256)
+decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ comp_root,
+                    const int* __restrict__ comp_size, const int* __restrict__ rowmin, const int* __restrict__ rowmax,
+                    int H, int W, int K, double sx, double sy, int npad, int32_t* __restrict__ boxes,
+                    float* __restrict__ rects, int32_t* __restrict__ comp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_n;
+  const int b = blockIdx.y, slot = blockIdx.x;
+  if (slot >= min(n_boxes[b], K)) return;
+  RectSmem S = rect_carve(smem, npad);
+  const size_t rowbase = ((size_t)b * K + slot) * H;
+  if (threadIdx.x == 0) s_n = 0;
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) S.keys[i] = ~0ull;
+  __syncthreads();
+  // candidates: (minx, y) and (maxx, y) of every occupied row; input index = row-major order
+  // (test_pixellink_fast.py:194-197: x*scale_x, y*scale_y assigned into an int64 array -> trunc)
+  const int root = comp_root[(size_t)b * K + slot];
+  const int y0 = root / W;  // the component's first row: its minimum pixel index lives there
+  for (int y = y0 + threadIdx.x; y < H; y += blockDim.x) {
+    const int mn = rowmin[rowbase + y], mx = rowmax[rowbase + y];
+    if (mx >= 0) {
+      const int py = (int)((double)y * sy);
+      const int pos = atomicAdd(&s_n, mn == mx ? 1 : 2);
+      S.keys[pos] = make_key((int)((double)mn * sx), py, 2 * y);
+      if (mn != mx) S.keys[pos + 1] = make_key((int)((double)mx * sx), py, 2 * y + 1);
+    }
+  }
+  __syncthreads();
+  const int total = s_n;
+  bitonic_sort(S.keys, npad);
+  if (threadIdx.x == 0) {
+    int box[8];
+    float rect[5];
+    min_area_box_sorted(S, total, npad, box, rect);
+    int32_t* ob = boxes + ((size_t)b * K + slot) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ob[i] = box[i];
+    if (rects) {
+      float* orc = rects + ((size_t)b * K + slot) * 5;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) orc[i] = rect[i];
+    }
+    if (comp) {
+      comp[((size_t)b * K + slot) * 2] = root;
+      comp[((size_t)b * K + slot) * 2 + 1] = comp_size[(size_t)b * K + slot];
+    }
+  }
+}
+
+// explicit point lists: one CTA per list
+__global__ void __launch_bounds__(256)
+min_area_boxes_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__ offsets, int npad,
+                      int32_t* __restrict__ boxes, float* __restrict__ rects) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  RectSmem S = rect_carve(smem, npad);
+  const int s = blockIdx.x;
+  const int o0 = offsets[s], total = offsets[s + 1] - o0;
+  for (int i = threadIdx.x; i < npad; i += blockDim.x)
+    S.keys[i] = i < total ? make_key(pts[2 * (o0 + i)], pts[2 * (o0 + i) + 1], i) : ~0ull;
+  __syncthreads();
+  bitonic_sort(S.keys, npad);
+  if (threadIdx.x == 0) {
+    int box[8];
+    float rect[5];
+    if (total > 0) {
+      min_area_box_sorted(S, total, npad, box, rect);
+    } else {
+      for (int i = 0; i < 8; ++i) box[i] = 0;
+      for (int i = 0; i < 5; ++i) rect[i] = 0.f;
+    }
+    for (int i = 0; i < 8; ++i) boxes[(size_t)s * 8 + i] = box[i];
+    if (rects)
+      for (int i = 0; i < 5; ++i) rects[(size_t)s * 5 + i] = rect[i];
+  }
+}
+
+// ------------------------------------------------------------------ D1 of the survey: pixel_detect
+// tool/pixellink_fn.py:120-154: mask = score > thr_p, cleared wherever any link_d[...,1] < thr_l.
+__global__ void pixel_detect_kernel(const float* __restrict__ score, const float* __restrict__ link, int N,
+                                    float thr_p, float thr_l, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  bool m = score[i] > thr_p;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) m = m && !(link[((size_t)d * N + i) * 2 + 1] < thr_l);
+  out[i] = m ? 1 : 0;
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static int decode_common(const uint16_t* flags_in, const float* pix_logits, const float* link_logits, int B, int H,
+                         int W, const plh_decode_params* p, int32_t* labels, int32_t* boxes, int32_t* n_boxes,
+                         float* rects, int32_t* comp, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  if (!p || !labels || !boxes || !n_boxes) return PLH_E_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || H > 2048 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (p->max_boxes <= 0 || p->min_size < 0 || !(p->scale_x >= 1.0) || !(p->scale_y >= 1.0) ||
+      W * p->scale_x >= 32768.0 || H * p->scale_y >= 32768.0)
+    return PLH_E_PARAM;
+  if (!aligned16(workspace) || !aligned16(labels)) return PLH_E_ALIGN;
+  const int K = p->max_boxes;
+  const DecodeWsLayout l = decode_ws_layout(B, H, W, K);
+  if (!workspace || workspace_bytes < l.total) return PLH_E_WORKSPACE;
+  char* ws = (char*)workspace;
+  uint16_t* flags = (uint16_t*)(ws + l.flags);
+  int* parent = (int*)(ws + l.parent);
+  int* size = (int*)(ws + l.size);
+  int* comp_root = (int*)(ws + l.comp_root);
+  int* comp_size = (int*)(ws + l.comp_size);
+  int* rowmin = (int*)(ws + l.rowmin);
+  int* rowmax = (int*)(ws + l.rowmax);
+  const long long total_px = (long long)B * H * W;
+  const int N = H * W;
+  int rc;
+  const int grid_px = (int)std::min<long long>((total_px + 255) / 256, kNumSMs * 16);
+  if (flags_in) {
+    flags = const_cast<uint16_t*>(flags_in);
+    decode_init_kernel<<<grid_px, 256, 0, s>>>(flags, total_px, parent, size);
+  } else {
+    const int grid = (int)std::min<long long>((total_px * 4 + 255) / 256, kNumSMs * 16);
+    decode_flags_kernel<<<grid, 256, 0, s>>>(pix_logits, link_logits, total_px,
+                                             prob_to_logit_threshold(p->pixel_thresh),
+                                             prob_to_logit_threshold(p->link_thresh), flags, parent, size);
+  }
+  if ((rc = launch_status())) return rc;
+  decode_union_kernel<<<grid_px, 256, 0, s>>>(flags, H, W, total_px, parent);
+  if ((rc = launch_status())) return rc;
+  decode_flatten_kernel<<<grid_px, 256, 0, s>>>(flags, H, W, total_px, parent, size);
+  if ((rc = launch_status())) return rc;
+  decode_compact_kernel<<<B, 1024, 0, s>>>(parent, size, N, p->min_size, K, comp_root, comp_size, n_boxes, rowmin,
+                                           rowmax, H);
+  if ((rc = launch_status())) return rc;
+  decode_labels_kernel<<<grid_px, 256, 0, s>>>(parent, size, H, W, total_px, K, labels, rowmin, rowmax);
+  if ((rc = launch_status())) return rc;
+  {
+    const int npad = next_pow2(std::max(2 * H, 32));
+    const size_t smem = rect_smem_bytes(npad);
+    static size_t attr_bytes = 0;
+    if (smem > 48 * 1024 && smem > attr_bytes) {
+      cudaError_t e = cudaFuncSetAttribute(decode_rects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      attr_bytes = smem;
+    }
+    decode_rects_kernel<<<dim3(K, B), 256, smem, s>>>(n_boxes, comp_root, comp_size, rowmin, rowmax, H, W, K,
+                                                      p->scale_x, p->scale_y, npad, boxes, rects, comp);
+    if ((rc = launch_status())) return rc;
+  }
+  return PLH_OK;
+}
+
+}  // namespace plh
+
+using namespace plh;
+
+extern "C" int plh_decode(const float* pix_logits, const float* link_logits, int B, int H, int W,
+                          const plh_decode_params* p, int32_t* labels, int32_t* boxes, int32_t* n_boxes, float* rects,
+                          int32_t* comp, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pix_logits || !link_logits) return PLH_E_NULL;
+  if (!aligned16(pix_logits) || !aligned16(link_logits)) return PLH_E_ALIGN;
+  return decode_common(nullptr, pix_logits, link_logits, B, H, W, p, labels, boxes, n_boxes, rects, comp, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int plh_decode_from_flags(const uint16_t* flags, int B, int H, int W, const plh_decode_params* p,
+                                     int32_t* labels, int32_t* boxes, int32_t* n_boxes, float* rects, int32_t* comp,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!flags) return PLH_E_NULL;
+  return decode_common(flags, nullptr, nullptr, B, H, W, p, labels, boxes, n_boxes, rects, comp, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int plh_min_area_boxes(const int32_t* pts, const int32_t* offsets, int n_sets, int32_t* boxes, float* rects,
+                                  void* stream) {
+  if (!pts || !offsets || !boxes) return PLH_E_NULL;
+  if (n_sets <= 0) return PLH_E_SHAPE;
+  const int npad = 4096;
+  const size_t smem = rect_smem_bytes(npad);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(min_area_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  min_area_boxes_kernel<<<n_sets, 256, smem, (cudaStream_t)stream>>>(pts, offsets, npad, boxes, rects);
+  return launch_status();
+}
+
+extern "C" int plh_pixel_detect(const float* score, const float* link, int H, int W, float score_map_thresh,
+                                float link_thresh, uint8_t* out, void* stream) {
+  if (!score || !link || !out) return PLH_E_NULL;
+  if (H <= 0 || W <= 0) return PLH_E_SHAPE;
+  const int N = H * W;
+  pixel_detect_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(score, link, N, score_map_thresh,
+                                                                         link_thresh, out);
+  return launch_status();
+}

@@ -1,0 +1,666 @@
+// loss.cu — PixelLink loss forward+backward for sm_100a.
+//
+// Replaces nets/model.py:145-261, nets/model_vgg_16.py:227-282 and
+// nets/pixellink.py:88-263 of the reference.
+//
+// Pipeline (three launches on one stream, no host sync):
+//   K1 ohem_select   one CTA per image: pixel scores -> radix keys in shared
+//                    memory -> exact k-th smallest by MSB-first bisection of the
+//                    fp32 bit pattern (30 count rounds, one __syncthreads each).
+//                    Reads 12 B/px.
+//   K2 ohem_counts   all SMs: selected mask M (1 B/px) + the 17 integer
+//                    normalisers (n_seg_pos, sum Wp[8], sum Wn[8]) which depend
+//                    only on labels and M.  Reads 44 B/px (12 of them L2 hits).
+//   K3 loss_main     all SMs, the HBM-bound pass: reads 108 B/px once, writes the
+//                    72 B/px of gradients once (normalisers are already known),
+//                    accumulates the 17 loss sums, last CTA finalises the scalars
+//                    in a fixed order (deterministic).
+// Algorithmic bytes: 180 B/px.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace plh {
+
+std::atomic<long long> g_launch_count{0};
+
+// ------------------------------------------------------------------ workspace layout
+struct LossHeader {  // 128 B, zeroed by cudaMemsetAsync at the start of every call
+  int n_seg_pos;
+  int cntP[8];
+  int cntN[8];
+  int n_selected;
+  unsigned ticket;
+  int pad[13];
+};
+static_assert(sizeof(LossHeader) == 128, "header size");
+
+struct ImageInfo {  // per image, written by K1
+  float thr;
+  int n_pos;
+  int n_neg;
+  int k;
+};
+
+constexpr int kMainThreads = 256;
+constexpr int kMainMaxCTAs = kNumSMs * 8;
+constexpr int kPartialFloats = 20;                 // 17 used
+constexpr int kSelectThreads = 1024;
+constexpr size_t kSmemKeysMaxBytes = 200 * 1024;   // keys of one image stay in shared memory up to 51200 px
+
+struct LossWsLayout {
+  size_t header, info, partials, mask, keys, total;
+};
+
+static LossWsLayout loss_ws_layout(int B, long long N) {
+  LossWsLayout l;
+  size_t off = 0;
+  l.header = off;
+  off += sizeof(LossHeader);
+  l.info = off;
+  off = align_up(off + sizeof(ImageInfo) * (size_t)B, 256);
+  l.partials = off;
+  off = align_up(off + sizeof(float) * kPartialFloats * kMainMaxCTAs, 256);
+  l.mask = off;
+  off = align_up(off + (size_t)B * N, 256);
+  l.keys = off;
+  if ((size_t)N * 4 > kSmemKeysMaxBytes) off = align_up(off + (size_t)B * N * 4, 256);
+  l.total = off;
+  return l;
+}
+
+size_t loss_workspace_bytes(int B, int H, int W) { return loss_ws_layout(B, (long long)H * W).total; }
+
+// ------------------------------------------------------------------ K1: per-image OHEM threshold
+// Key of a pixel: the fp32 bit pattern of its score (scores are >= 0, so the
+// unsigned order of the bits is the numeric order).
+//   KEYS_MODEL     (nets/model.py:175-176)     non-negatives are excluded (key 0xFFFFFFFF)
+//   KEYS_PIXELLINK (nets/pixellink.py:124-125) non-negatives become score 0 (key 0)
+enum { KEYS_MODEL = 0, KEYS_PIXELLINK = 1 };
+constexpr uint32_t kExcluded = 0xFFFFFFFFu;
+
+template <int KEYMODE, bool FROM_SCORES>
+__global__ void __launch_bounds__(kSelectThreads, 1)
+ohem_select_kernel(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
+                   const float* __restrict__ scores, const uint8_t* __restrict__ pos_mask,
+                   const uint8_t* __restrict__ neg_mask, const int* __restrict__ n_pos_override, int N, int ratio,
+                   uint32_t* __restrict__ keys_global, ImageInfo* __restrict__ info, float* __restrict__ thr_out) {
+  extern __shared__ __align__(16) uint32_t skeys[];
+  __shared__ int s_cnt[32];
+  __shared__ int s_np, s_nn;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  uint32_t* keys = keys_global ? keys_global + (size_t)b * N : skeys;
+
+  if (tid < 32) s_cnt[tid] = 0;
+  if (tid == 0) s_np = 0, s_nn = 0;
+  __syncthreads();
+
+  // ---- pass 1: scores -> keys, count positives / negatives
+  int npos = 0, nneg = 0;
+  const size_t base = (size_t)b * N;
+  constexpr int U = 4;
+  for (int i0 = tid; i0 < N; i0 += kSelectThreads * U) {
+    float sc[U];
+    bool isp[U], isn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kSelectThreads;
+      sc[u] = 0.f, isp[u] = false, isn[u] = false;
+      if (i < N) {
+        if (FROM_SCORES) {
+          sc[u] = scores[base + i];
+          isp[u] = pos_mask[base + i] != 0;
+          isn[u] = neg_mask[base + i] != 0;
+        } else {
+          const float2 x = __ldg(reinterpret_cast<const float2*>(pix_logits) + base + i);
+          const float l = __ldg(pix_lab + base + i);
+          sc[u] = neg_class_score(x.x, x.y);
+          if (KEYMODE == KEYS_MODEL) {  // int32 cast truncates (model.py:213), ==1 / ==0 (:199-202)
+            const int li = (int)l;
+            isp[u] = li == 1, isn[u] = li == 0;
+          } else {                      // pixellink.py:98-99: pos = labels > 0, neg = !pos
+            isp[u] = l > 0.f, isn[u] = !isp[u];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kSelectThreads;
+      if (i < N) {
+        npos += isp[u], nneg += isn[u];
+        uint32_t key = __float_as_uint(sc[u]);
+        if (!isn[u]) key = (KEYMODE == KEYS_MODEL) ? kExcluded : 0u;
+        keys[i] = key;
+      }
+    }
+  }
+  npos = __reduce_add_sync(0xffffffffu, npos);
+  nneg = __reduce_add_sync(0xffffffffu, nneg);
+  if (lane == 0) atomicAdd(&s_np, npos), atomicAdd(&s_nn, nneg);
+  __syncthreads();
+  npos = s_np, nneg = s_nn;
+  if (n_pos_override) npos = n_pos_override[b];  // OHNM_single_image(scores, n_pos, neg_mask): n_pos is an argument
+
+  // ---- k (model.py:170-173 / pixellink.py:116-120)
+  long long kk = (long long)npos * ratio;
+  const int cap = (KEYMODE == KEYS_MODEL) ? nneg : max(nneg, 1);
+  int k = (int)(kk < (long long)cap ? kk : (long long)cap);
+  const bool none = (npos <= 0) || (k <= 0);  // n_pos == 0 -> no_pos(); k == 0 -> "select none" 
+
+  float thr = __int_as_float(0x7fc00000);  // NaN: `score <= NaN` is false for every pixel
+  if (!none) {
+    // ---- exact k-th smallest key: build it MSB first.  Keys of real scores are
+    // <= bits(1.0f) = 0x3F800000 < 2^30; excluded keys never count.
+    uint32_t ans = 0;
+    const bool vec = ((N & 3) == 0);
+    for (int bit = 29; bit >= 0; --bit) {
+      const uint32_t t = ans | ((1u << bit) - 1u);
+      int c = 0;
+      if (vec) {
+        const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+        const int n4 = N >> 2;
+#pragma unroll 4
+        for (int i = tid; i < n4; i += kSelectThreads) {
+          const uint4 v = k4[i];
+          c += (v.x <= t) + (v.y <= t) + (v.z <= t) + (v.w <= t);
+        }
+      } else {
+        for (int i = tid; i < N; i += kSelectThreads) c += (keys[i] <= t);
+      }
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0 && c) atomicAdd(&s_cnt[bit], c);
+      __syncthreads();
+      if (s_cnt[bit] < k) ans |= (1u << bit);
+    }
+    thr = __uint_as_float(ans);
+  }
+  if (tid == 0) {
+    if (info) info[b] = ImageInfo{thr, npos, nneg, none ? 0 : k};
+    if (thr_out) thr_out[b] = thr;
+  }
+}
+
+// ------------------------------------------------------------------ K2: mask + integer normalisers
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+ohem_counts_kernel(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
+                   const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N, long long total_px,
+                   uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr) {
+  __shared__ int s_c[18];
+  const int tid = threadIdx.x;
+  if (tid < 18) s_c[tid] = 0;
+  __syncthreads();
+  int cP[8], cN[8], nsp = 0, nsel = 0;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) cP[d] = 0, cN[d] = 0;
+
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long px = (long long)blockIdx.x * blockDim.x + tid; px < total_px; px += stride) {
+    const float4 la = __ldg(reinterpret_cast<const float4*>(link_lab) + px * 2);
+    const float4 lb = __ldg(reinterpret_cast<const float4*>(link_lab) + px * 2 + 1);
+    const float l = __ldg(pix_lab + px);
+    bool pos, neg;
+    if (VARIANT == PLH_VARIANT_PIXELLINK) pos = l > 0.f, neg = !pos;
+    else { const int li = (int)l; pos = li == 1, neg = li == 0; }
+    bool M = pos;
+    if (VARIANT != PLH_VARIANT_POS_ONLY && neg) {
+      const float thr = info[px / N].thr;
+      const float2 x = __ldg(reinterpret_cast<const float2*>(pix_logits) + px);
+      M = neg_class_score(x.x, x.y) <= thr;  // model.py:178 ties at the threshold are all selected
+    }
+    mask[px] = M ? 1 : 0;
+    nsel += M;
+    if (VARIANT == PLH_VARIANT_PIXELLINK) nsp += M;  // pixellink.py:155 n_seg_pos = sum(selected mask)
+    else nsp += pos;                                 // model.py:221    n_seg_pos = sum(pos mask)
+    const bool Ml = (VARIANT == PLH_VARIANT_PIXELLINK) ? true : M;  // pixellink.py:193-194: not x OHEM mask
+    const float lv[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      bool lp, ln;
+      if (VARIANT == PLH_VARIANT_PIXELLINK) lp = lv[d] > 0.f, ln = !lp;
+      else { const int li = (int)lv[d]; lp = li == 1, ln = li == 0; }
+      cP[d] += (lp && Ml), cN[d] += (ln && Ml);
+    }
+  }
+  const int lane = tid & 31;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    const int a = __reduce_add_sync(0xffffffffu, cP[d]);
+    const int c = __reduce_add_sync(0xffffffffu, cN[d]);
+    if (lane == 0) {
+      if (a) atomicAdd(&s_c[1 + d], a);
+      if (c) atomicAdd(&s_c[9 + d], c);
+    }
+  }
+  nsp = __reduce_add_sync(0xffffffffu, nsp);
+  nsel = __reduce_add_sync(0xffffffffu, nsel);
+  if (lane == 0) {
+    if (nsp) atomicAdd(&s_c[0], nsp);
+    if (nsel) atomicAdd(&s_c[17], nsel);
+  }
+  __syncthreads();
+  if (tid < 18 && s_c[tid]) atomicAdd(reinterpret_cast<int*>(hdr) + tid, s_c[tid]);  // header ints 0..17
+}
+
+// ------------------------------------------------------------------ K3: main fused pass
+struct MainArgs {
+  const float* pix_logits;
+  const float* link_logits;
+  const float* pix_lab;
+  const float* link_lab;
+  const uint8_t* mask;
+  LossHeader* hdr;
+  float* partials;
+  float* stats;
+  float* grad_pix;
+  float* grad_link;
+  uint16_t* flags;
+  long long total_px;
+  float alpha, gamma;
+  float tp_logit, tl_logit;  // decode thresholds moved to logit-difference space
+};
+
+// One 2-way softmax term.  Returns the per-element loss term and d(term)/d(logit 1);
+// d/d(logit 0) is its negative.  Fast intrinsics: nothing here feeds a mask decision.
+template <int TERM>
+__device__ __forceinline__ void term_and_grad(float x0, float x1, bool lab1, float alpha, float gamma,
+                                              float& term, float& g1) {
+  const float d = x1 - x0;
+  const float ad = fabsf(d);
+  const float e = __expf(-ad);
+  const float den = 1.f + e;
+  const float r = __fdividef(1.f, den);
+  const float qbig = r, qsmall = e * r;
+  const bool one_is_max = d >= 0.f;
+  const float q1 = one_is_max ? qbig : qsmall;
+  // CE = log(sum exp(x - max)) - (x_label - max)
+  const float ce = __logf(den) + ((lab1 == one_is_max) ? 0.f : ad);
+  if (TERM == PLH_TERM_CE) {
+    term = ce;
+    g1 = q1 - (lab1 ? 1.f : 0.f);
+  } else {
+    const float pt = lab1 ? q1 : (one_is_max ? qsmall : qbig);
+    const float logpt = -ce;
+    const float at = lab1 ? alpha : 1.f - alpha;
+    const float om = 1.f - pt;
+    const float mod = (gamma == 2.f) ? om * om : __powf(om, gamma);
+    term = -(at * mod * logpt);
+    const float gt = at * mod * (gamma * pt * logpt - om);
+    g1 = lab1 ? gt : -gt;
+  }
+}
+
+template <int VARIANT>
+__device__ __forceinline__ void classify(float l, bool& p, bool& n) {
+  if (VARIANT == PLH_VARIANT_PIXELLINK) p = l > 0.f, n = !p;
+  else { const int li = (int)l; p = li == 1, n = li == 0; }
+}
+
+template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
+__global__ void __launch_bounds__(kMainThreads)
+loss_main_kernel(const MainArgs a, const int B, const int N) {
+  __shared__ float s_red[kMainThreads / 32][4][5];
+  __shared__ double s_fin[17];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int j = tid & 3;  // which quarter of a pixel: link directions 2j and 2j+1
+
+  // ---- normalisers (final: K2 completed before this launch)
+  const LossHeader* hdr = a.hdr;
+  float pix_scale, invP[2], invN[2];
+  {
+    const float nsp = (float)hdr->n_seg_pos;
+    if (VARIANT == PLH_VARIANT_MODEL) pix_scale = nsp > 0.f ? __fdiv_rn(2.f, nsp) : 0.f;  // model.py:226-233
+    else if (VARIANT == PLH_VARIANT_POS_ONLY) pix_scale = __fdiv_rn(2.f, nsp);            // vgg16 :267 unguarded
+    else pix_scale = __fdiv_rn(2.f, (float)((long long)B * N));                          // pixellink.py:160,170
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float cp = (float)hdr->cntP[2 * j + c], cn = (float)hdr->cntN[2 * j + c];
+      if (VARIANT == PLH_VARIANT_PIXELLINK) {  // pixellink.py:198-211 zero guards
+        invP[c] = cp != 0.f ? __fdiv_rn(1.f, cp) : 0.f;
+        invN[c] = cn != 0.f ? __fdiv_rn(1.f, cn) : 0.f;
+      } else {                                 // model.py:252-253 unguarded: 0/0 = NaN is data
+        invP[c] = __fdiv_rn(1.f, cp);
+        invN[c] = __fdiv_rn(1.f, cn);
+      }
+    }
+  }
+
+  float sp[2] = {0.f, 0.f}, sn[2] = {0.f, 0.f}, spx = 0.f;
+  const long long Q = a.total_px * 4;
+  const long long stride = (long long)gridDim.x * kMainThreads;
+  const float4* ll4 = reinterpret_cast<const float4*>(a.link_logits);
+  const float2* lab2 = reinterpret_cast<const float2*>(a.link_lab);
+  const float2* pl2 = reinterpret_cast<const float2*>(a.pix_logits);
+
+  constexpr int U = 2;
+  // warp-uniform trip count (the quad shuffles below need every lane in the loop)
+  for (long long w0 = (long long)blockIdx.x * kMainThreads + (tid & ~31); w0 < Q; w0 += stride * U) {
+    const long long q0 = w0 + lane;
+    float4 L[U];
+    float2 LB[U], P[U];
+    float PLB[U];
+    uint8_t MK[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = q0 + u * stride;
+      L[u] = make_float4(0.f, 0.f, 0.f, 0.f), LB[u] = make_float2(0.f, 0.f), P[u] = make_float2(0.f, 0.f);
+      PLB[u] = 0.f, MK[u] = 0;
+      if (q < Q) {
+        const long long px = q >> 2;
+        L[u] = ldg_stream4(ll4 + q);
+        LB[u] = ldg_stream2(lab2 + q);
+        P[u] = __ldg(pl2 + px);
+        PLB[u] = __ldg(a.pix_lab + px);
+        MK[u] = (VARIANT == PLH_VARIANT_PIXELLINK) ? (uint8_t)1 : __ldg(a.mask + px);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = q0 + u * stride;
+      const bool valid = q < Q;  // Q % 4 == 0 and strides are multiples of 4: a quad is valid as a whole
+      const long long px = q >> 2;
+      const float Mf = (float)MK[u];
+      // ---- two link directions
+      {
+        bool p0, n0, p1, n1;
+        classify<VARIANT>(LB[u].x, p0, n0);
+        classify<VARIANT>(LB[u].y, p1, n1);
+        float t0, g0, t1, g1;
+        term_and_grad<TERM>(L[u].x, L[u].y, p0, a.alpha, a.gamma, t0, g0);
+        term_and_grad<TERM>(L[u].z, L[u].w, p1, a.alpha, a.gamma, t1, g1);
+        if (valid) {
+          const float w0 = Mf * (p0 ? invP[0] : (n0 ? invN[0] : 0.f));
+          const float w1 = Mf * (p1 ? invP[1] : (n1 ? invN[1] : 0.f));
+          sp[0] += p0 ? t0 * Mf : 0.f, sn[0] += n0 ? t0 * Mf : 0.f;
+          sp[1] += p1 ? t1 * Mf : 0.f, sn[1] += n1 ? t1 * Mf : 0.f;
+          const float a0 = w0 * g0, a1 = w1 * g1;
+          if (GRAD) stg_stream4(reinterpret_cast<float4*>(a.grad_link) + q, make_float4(-a0, a0, -a1, a1));
+        }
+      }
+      // ---- pixel term (quad-redundant; lane j == 0 owns the store and the sum)
+      {
+        bool pp, pn;
+        classify<VARIANT>(PLB[u], pp, pn);
+        float t, g1;
+        term_and_grad<TERM>(P[u].x, P[u].y, pp, a.alpha, a.gamma, t, g1);
+        if (valid && j == 0) {
+          spx += t * Mf;
+          if (GRAD) {
+            const float gp = (Mf * pix_scale) * g1;
+            stg_stream2(reinterpret_cast<float2*>(a.grad_pix) + px, make_float2(-gp, gp));
+          }
+        }
+      }
+      if (FLAGS) {
+        unsigned bits = ((L[u].y - L[u].x) > a.tl_logit ? 1u : 0u) << (2 * j) |
+                        ((L[u].w - L[u].z) > a.tl_logit ? 1u : 0u) << (2 * j + 1);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+        if (valid && j == 0)
+          a.flags[px] = (uint16_t)(bits | (((P[u].y - P[u].x) > a.tp_logit ? 1u : 0u) << 8));
+      }
+    }
+  }
+
+  // ---- block reduction of the 17 sums (lanes with equal j hold the same directions)
+#pragma unroll
+  for (int o = 4; o <= 16; o <<= 1) {
+    sp[0] += __shfl_xor_sync(0xffffffffu, sp[0], o);
+    sp[1] += __shfl_xor_sync(0xffffffffu, sp[1], o);
+    sn[0] += __shfl_xor_sync(0xffffffffu, sn[0], o);
+    sn[1] += __shfl_xor_sync(0xffffffffu, sn[1], o);
+    spx += __shfl_xor_sync(0xffffffffu, spx, o);
+  }
+  if (lane < 4) {
+    s_red[warp][lane][0] = sp[0], s_red[warp][lane][1] = sp[1];
+    s_red[warp][lane][2] = sn[0], s_red[warp][lane][3] = sn[1];
+    s_red[warp][lane][4] = spx;
+  }
+  __syncthreads();
+  if (tid < 17) {
+    // partial index: 0..7 s_pos[d], 8..15 s_neg[d], 16 s_pix ; d = 2*jj + c
+    int jj, slot;
+    if (tid < 16) { const int d = tid & 7; jj = d >> 1; slot = (tid < 8 ? 0 : 2) + (d & 1); }
+    else { jj = 0; slot = 4; }
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kMainThreads / 32; ++w) s += s_red[w][jj][slot];
+    a.partials[(size_t)blockIdx.x * kPartialFloats + tid] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&a.hdr->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+
+  // ---- last CTA: deterministic final reduction + scalars
+  __threadfence();
+  if (tid < 17) {
+    double s = 0.0;
+    for (unsigned c = 0; c < gridDim.x; ++c) s += (double)__ldcg(a.partials + (size_t)c * kPartialFloats + tid);
+    s_fin[tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float* st = a.stats;
+    const float nsp = (float)hdr->n_seg_pos;
+    const float s_pix = (float)s_fin[16];
+    float L_pix;
+    if (VARIANT == PLH_VARIANT_MODEL) L_pix = nsp > 0.f ? __fdiv_rn(s_pix, nsp) : 0.f;
+    else if (VARIANT == PLH_VARIANT_POS_ONLY) L_pix = __fdiv_rn(s_pix, nsp);
+    else L_pix = (float)(s_fin[16] / (double)((long long)B * N));
+    double link_total = 0.0;
+    for (int d = 0; d < 8; ++d) {
+      const float cp = (float)hdr->cntP[d], cn = (float)hdr->cntN[d];
+      const float s_pos = (float)s_fin[d], s_neg = (float)s_fin[8 + d];
+      float Ld;
+      if (VARIANT == PLH_VARIANT_PIXELLINK)
+        Ld = (cp != 0.f ? s_pos * __fdiv_rn(1.f, cp) : 0.f) + (cn != 0.f ? s_neg * __fdiv_rn(1.f, cn) : 0.f);
+      else
+        Ld = __fdiv_rn(s_pos, cp) + __fdiv_rn(s_neg, cn);
+      st[PLH_ST_L_LINK + d] = Ld;
+      st[PLH_ST_SUM_WP + d] = cp;
+      st[PLH_ST_SUM_WN + d] = cn;
+      st[PLH_ST_S_POS + d] = s_pos;
+      st[PLH_ST_S_NEG + d] = s_neg;
+      link_total += (double)Ld;
+    }
+    st[PLH_ST_L_PIX] = L_pix;
+    st[PLH_ST_N_SEG_POS] = nsp;
+    st[PLH_ST_S_PIX] = s_pix;
+    st[PLH_ST_LINK_TOTAL] = (float)link_total;
+    st[PLH_ST_N_SELECTED] = (float)hdr->n_selected;
+    st[PLH_ST_TOTAL] = (float)link_total + 2.f * L_pix;  // model.py:261 / pixellink.py:170,254
+    for (int i = 46; i < PLH_STATS_FLOATS; ++i) st[i] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ standalone OHNM_batch apply
+__global__ void ohnm_apply_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ pos,
+                                  const uint8_t* __restrict__ neg, const float* __restrict__ thr, int N,
+                                  long long total, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const float t = thr[i / N];
+    const bool sel = neg[i] && (scores[i] <= t);
+    out[i] = (pos[i] ? 1.f : 0.f) + (sel ? 1.f : 0.f);  // model.py:196 float(pos) + selected_neg
+  }
+}
+
+// ------------------------------------------------------------------ host side
+// Probability threshold -> threshold on the logit difference d = x1 - x0.
+// The 2-way softmax score exp(x1-m)/(exp(x0-m)+exp(x1-m)) is a monotone function
+// of fl(x1-x0) only, so `score > t` is decided exactly by `d > d*`, where d* is the
+// largest fp32 difference whose fp32 softmax score is still <= t (found by bisection
+// over the fp32 bit patterns with the same TF formula).  No transcendental per pixel.
+static float softmax1_from_diff(float d) {
+  // x0 = 0, x1 = d (TF: subtract the max, exp, normalise), all in fp32
+  const float m = d > 0.f ? d : 0.f;
+  const float e0 = expf(0.f - m), e1 = expf(d - m);
+  return e1 / (e0 + e1);
+}
+static inline int32_t ordered_bits(float f) {
+  int32_t i;
+  memcpy(&i, &f, 4);
+  return i >= 0 ? i : (int32_t)(0x80000000u - (uint32_t)i);  // monotone map float -> int
+}
+static inline float from_ordered_bits(int32_t i) {
+  const int32_t r = i >= 0 ? i : (int32_t)(0x80000000u - (uint32_t)i);
+  float f;
+  memcpy(&f, &r, 4);
+  return f;
+}
+float prob_to_logit_threshold(float t) {
+  // largest d with softmax1(d) <= t  (then score > t  <=>  d > d*)
+  if (!(t > 0.f)) return -INFINITY;  // every score > t unless score == 0; keep simple: all pass
+  if (t >= 1.f) return INFINITY;
+  int32_t lo = ordered_bits(-200.f), hi = ordered_bits(200.f);  // softmax1(lo) = 0 <= t, softmax1(hi) = 1 > t
+  while (hi - lo > 1) {
+    const int32_t mid = lo + (hi - lo) / 2;
+    if (softmax1_from_diff(from_ordered_bits(mid)) <= t) lo = mid;
+    else hi = mid;
+  }
+  return from_ordered_bits(lo);
+}
+
+template <int VARIANT, int TERM>
+static void launch_main(bool grad, bool flags, int grid, cudaStream_t s, const MainArgs& a, int B, int N) {
+  if (grad && flags) loss_main_kernel<VARIANT, TERM, true, true><<<grid, kMainThreads, 0, s>>>(a, B, N);
+  else if (grad) loss_main_kernel<VARIANT, TERM, true, false><<<grid, kMainThreads, 0, s>>>(a, B, N);
+  else if (flags) loss_main_kernel<VARIANT, TERM, false, true><<<grid, kMainThreads, 0, s>>>(a, B, N);
+  else loss_main_kernel<VARIANT, TERM, false, false><<<grid, kMainThreads, 0, s>>>(a, B, N);
+}
+
+template <int KEYMODE, bool FROM_SCORES>
+static int launch_select(const float* pix_logits, const float* pix_lab, const float* scores, const uint8_t* pos,
+                         const uint8_t* neg, const int* n_pos_override, int B, int N, int ratio,
+                         uint32_t* keys_global, ImageInfo* info, float* thr_out, cudaStream_t s) {
+  auto kern = ohem_select_kernel<KEYMODE, FROM_SCORES>;
+  size_t smem = keys_global ? 0 : (size_t)N * 4;
+  static bool attr_set = false;  // idempotent; benign if raced
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemKeysMaxBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  kern<<<B, kSelectThreads, smem, s>>>(pix_logits, pix_lab, scores, pos, neg, n_pos_override, N, ratio, keys_global,
+                                       info, thr_out);
+  return launch_status();
+}
+
+}  // namespace plh
+
+using namespace plh;
+
+extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_logits, const float* pix_lab,
+                                  const float* link_lab, const float* /*train_mask: never read, model.py Q3*/,
+                                  int B, int H, int W, const plh_loss_params* p, float* stats, float* grad_pix,
+                                  float* grad_link, uint8_t* ohem_mask, uint16_t* decode_flags,
+                                  const plh_decode_params* dp, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  if (!pix_logits || !link_logits || !pix_lab || !link_lab || !p || !stats) return PLH_E_NULL;
+  if ((grad_pix == nullptr) != (grad_link == nullptr)) return PLH_E_NULL;
+  if (decode_flags && !dp) return PLH_E_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (p->variant < 0 || p->variant > 2 || p->term < 0 || p->term > 1 || p->neg_pos_ratio < 0) return PLH_E_PARAM;
+  if (!aligned16(pix_logits) || !aligned16(link_logits) || !aligned16(pix_lab) || !aligned16(link_lab) ||
+      !aligned16(stats) || (grad_pix && (!aligned16(grad_pix) || !aligned16(grad_link))) || !aligned16(workspace))
+    return PLH_E_ALIGN;
+  const int N = H * W;
+  const LossWsLayout l = loss_ws_layout(B, N);
+  if (!workspace || workspace_bytes < l.total) return PLH_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  LossHeader* hdr = (LossHeader*)(ws + l.header);
+  ImageInfo* info = (ImageInfo*)(ws + l.info);
+  float* partials = (float*)(ws + l.partials);
+  uint8_t* mask = ohem_mask ? ohem_mask : (uint8_t*)(ws + l.mask);
+  uint32_t* keys_global = ((size_t)N * 4 > kSmemKeysMaxBytes) ? (uint32_t*)(ws + l.keys) : nullptr;
+  const long long total_px = (long long)B * N;
+
+  cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(LossHeader), s);
+  if (e != cudaSuccess) return (int)e;
+  int rc;
+  // K1 (not needed for the positives-only variant: there is no mining, vgg16 :265)
+  if (p->variant == PLH_VARIANT_MODEL)
+    rc = launch_select<KEYS_MODEL, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
+                                          p->neg_pos_ratio, keys_global, info, stats + PLH_ST_THR, s);
+  else if (p->variant == PLH_VARIANT_PIXELLINK)
+    rc = launch_select<KEYS_PIXELLINK, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
+                                              p->neg_pos_ratio, keys_global, info, stats + PLH_ST_THR, s);
+  else {
+    // thr[b] = NaN
+    e = cudaMemsetAsync(stats + PLH_ST_THR, 0xff, sizeof(float) * B, s);
+    rc = e == cudaSuccess ? PLH_OK : (int)e;
+  }
+  if (rc) return rc;
+  // K2
+  {
+    const int grid = (int)std::min<long long>((total_px + 255) / 256, kNumSMs * 8);
+    if (p->variant == PLH_VARIANT_MODEL)
+      ohem_counts_kernel<PLH_VARIANT_MODEL><<<grid, 256, 0, s>>>(pix_logits, pix_lab, link_lab, info, N, total_px, mask, hdr);
+    else if (p->variant == PLH_VARIANT_POS_ONLY)
+      ohem_counts_kernel<PLH_VARIANT_POS_ONLY><<<grid, 256, 0, s>>>(pix_logits, pix_lab, link_lab, info, N, total_px, mask, hdr);
+    else
+      ohem_counts_kernel<PLH_VARIANT_PIXELLINK><<<grid, 256, 0, s>>>(pix_logits, pix_lab, link_lab, info, N, total_px, mask, hdr);
+    if ((rc = launch_status())) return rc;
+  }
+  // K3
+  {
+    MainArgs a;
+    a.pix_logits = pix_logits, a.link_logits = link_logits, a.pix_lab = pix_lab, a.link_lab = link_lab;
+    a.mask = mask, a.hdr = hdr, a.partials = partials, a.stats = stats;
+    a.grad_pix = grad_pix, a.grad_link = grad_link, a.flags = decode_flags;
+    a.total_px = total_px, a.alpha = p->focal_alpha, a.gamma = p->focal_gamma;
+    a.tp_logit = dp ? prob_to_logit_threshold(dp->pixel_thresh) : 0.f;
+    a.tl_logit = dp ? prob_to_logit_threshold(dp->link_thresh) : 0.f;
+    const long long Q = total_px * 4;
+    const int grid = (int)std::min<long long>((Q + kMainThreads * 2 - 1) / (kMainThreads * 2), kMainMaxCTAs);
+    const bool g = grad_pix != nullptr, f = decode_flags != nullptr;
+#define PLH_DISPATCH(V, T) launch_main<V, T>(g, f, grid, s, a, B, N)
+    if (p->term == PLH_TERM_CE) {
+      if (p->variant == PLH_VARIANT_MODEL) PLH_DISPATCH(PLH_VARIANT_MODEL, PLH_TERM_CE);
+      else if (p->variant == PLH_VARIANT_POS_ONLY) PLH_DISPATCH(PLH_VARIANT_POS_ONLY, PLH_TERM_CE);
+      else PLH_DISPATCH(PLH_VARIANT_PIXELLINK, PLH_TERM_CE);
+    } else {
+      if (p->variant == PLH_VARIANT_MODEL) PLH_DISPATCH(PLH_VARIANT_MODEL, PLH_TERM_FOCAL);
+      else if (p->variant == PLH_VARIANT_POS_ONLY) PLH_DISPATCH(PLH_VARIANT_POS_ONLY, PLH_TERM_FOCAL);
+      else PLH_DISPATCH(PLH_VARIANT_PIXELLINK, PLH_TERM_FOCAL);
+    }
+#undef PLH_DISPATCH
+    if ((rc = launch_status())) return rc;
+  }
+  return PLH_OK;
+}
+
+extern "C" int plh_ohnm_batch(const float* scores, const uint8_t* pos_mask, const uint8_t* neg_mask,
+                              const int32_t* n_pos, int B, int N, int variant, int neg_pos_ratio,
+                              float* selected_mask, float* thr, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  if (!scores || !pos_mask || !neg_mask || !selected_mask || !thr) return PLH_E_NULL;
+  if (B <= 0 || N <= 0 || (long long)B * N > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (variant != PLH_VARIANT_MODEL && variant != PLH_VARIANT_PIXELLINK) return PLH_E_PARAM;
+  uint32_t* keys_global = nullptr;
+  if ((size_t)N * 4 > kSmemKeysMaxBytes) {
+    if (!workspace || workspace_bytes < (size_t)B * N * 4 || !aligned16(workspace)) return PLH_E_WORKSPACE;
+    keys_global = (uint32_t*)workspace;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = variant == PLH_VARIANT_MODEL
+               ? launch_select<KEYS_MODEL, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B, N,
+                                                 neg_pos_ratio, keys_global, nullptr, thr, s)
+               : launch_select<KEYS_PIXELLINK, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B, N,
+                                                     neg_pos_ratio, keys_global, nullptr, thr, s);
+  if (rc) return rc;
+  const long long total = (long long)B * N;
+  const int grid = (int)std::min<long long>((total + 255) / 256, kNumSMs * 8);
+  ohnm_apply_kernel<<<grid, 256, 0, s>>>(scores, pos_mask, neg_mask, thr, N, total, selected_mask);
+  return launch_status();
+}

@@ -1,0 +1,336 @@
+// rect.cuh — cv2.minAreaRect -> cv2.boxPoints -> np.int0 for one integer point set,
+// restated step by step for one CTA (model: oracle/minarearect.py, which is pinned
+// bit-exactly against OpenCV 4.13.0; reference call sites test_pixellink_fast.py:199-200,
+// test.py:190-191).  OpenCV's convexHull is Sklansky's scan over points sorted by
+// (x, y, input index); minAreaRect runs fp32 rotating calipers over that hull.
+//
+// Every fp32 operation uses the _rn intrinsics so that nvcc never contracts a
+// multiply-add: the rounding sequence is OpenCV's.
+#pragma once
+#include "common.cuh"
+
+namespace plh {
+
+struct RectSmem {
+  unsigned long long* keys;  // [npad] sort keys: x<<32 | y<<16... see make_key
+  int* stack;                // [n + 2] x 2 (upper/lower scans reuse)
+  int* hullbuf;              // [n]
+  float* hx;                 // [n] hull points / edge vectors / inverse lengths
+  float* hy;
+  float* vx;
+  float* vy;
+  float* inv;
+};
+
+__host__ __device__ inline size_t rect_smem_bytes(int npad) {
+  // keys 8 + stack 2*4 (two stacks of npad+2 -> rounded) + hullbuf 4 + 5 floats 20
+  return (size_t)npad * 8 + (size_t)(npad + 4) * 4 * 4 + (size_t)npad * 4 + (size_t)npad * 20 + 64;
+}
+
+__device__ inline RectSmem rect_carve(unsigned char* base, int npad) {
+  RectSmem s;
+  s.keys = reinterpret_cast<unsigned long long*>(base);
+  base += (size_t)npad * 8;
+  s.stack = reinterpret_cast<int*>(base);
+  base += (size_t)(npad + 4) * 4 * 4;
+  s.hullbuf = reinterpret_cast<int*>(base);
+  base += (size_t)npad * 4;
+  s.hx = reinterpret_cast<float*>(base);
+  s.hy = s.hx + npad;
+  s.vx = s.hy + npad;
+  s.vy = s.vx + npad;
+  s.inv = s.vy + npad;
+  return s;
+}
+
+// key orders by (x, y, index); x,y in [0, 65535] after +bias, index < 2^20
+__device__ __forceinline__ unsigned long long make_key(int x, int y, int idx) {
+  return ((unsigned long long)(unsigned)(x + 32768) << 40) | ((unsigned long long)(unsigned)(y + 32768) << 20) |
+         (unsigned long long)(unsigned)idx;
+}
+__device__ __forceinline__ int key_x(unsigned long long k) { return (int)(k >> 40) - 32768; }
+__device__ __forceinline__ int key_y(unsigned long long k) { return (int)((k >> 20) & 0xFFFFFu) - 32768; }
+__device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(k & 0xFFFFFu); }
+
+// In-place bitonic sort of keys[0..npad) by the whole CTA (npad a power of two; pad = ~0).
+__device__ inline void bitonic_sort(unsigned long long* keys, int npad) {
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) keys[i] = b, keys[ixj] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int sgn(long long v) { return (v > 0) - (v < 0); }
+
+// OpenCV convhull.cpp Sklansky_ over the sorted keys; returns the stack size.
+__device__ inline int sklansky(const unsigned long long* keys, int start, int end, int* stack, int nsign, int sign2) {
+  const int incr = end > start ? 1 : -1;
+  int pprev = start, pcur = pprev + incr, pnext = pcur + incr;
+  int stacksize = 3;
+  if (start == end || (key_x(keys[start]) == key_x(keys[end]) && key_y(keys[start]) == key_y(keys[end]))) {
+    stack[0] = start;
+    return 1;
+  }
+  stack[0] = pprev, stack[1] = pcur, stack[2] = pnext;
+  end += incr;
+  while (pnext != end) {
+    const int cury = key_y(keys[pcur]);
+    const int nexty = key_y(keys[pnext]);
+    const int by = nexty - cury;
+    if (sgn(by) != nsign) {
+      const int ax = key_x(keys[pcur]) - key_x(keys[pprev]);
+      const int bx = key_x(keys[pnext]) - key_x(keys[pcur]);
+      const int ay = cury - key_y(keys[pprev]);
+      const long long convexity = (long long)ay * bx - (long long)ax * by;
+      if (sgn(convexity) == sign2 && (ax != 0 || ay != 0)) {
+        pprev = pcur;
+        pcur = pnext;
+        pnext += incr;
+        stack[stacksize] = pnext;
+        stacksize++;
+      } else {
+        if (pprev == start) {
+          pcur = pnext;
+          stack[1] = pcur;
+          pnext += incr;
+          stack[2] = pnext;
+        } else {
+          stack[stacksize - 2] = pnext;
+          pcur = pprev;
+          pprev = stack[stacksize - 4];
+          stacksize--;
+        }
+      }
+    } else {
+      pnext += incr;
+      stack[stacksize - 1] = pnext;
+    }
+  }
+  return --stacksize;
+}
+
+// Runs on ONE thread after the keys are sorted.  total = number of real points.
+// out_box: 8 ints (x0,y0..x3,y3), out_rect: 5 floats or nullptr.
+__device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npad, int* out_box, float* out_rect) {
+  const unsigned long long* keys = S.keys;
+  int* hullbuf = S.hullbuf;
+  int nout = 0;
+  // ---- cv::convexHull(points, clockwise=false, returnPoints=true)
+  int miny_ind = 0, maxy_ind = 0;
+  for (int i = 1; i < total; ++i) {
+    const int y = key_y(keys[i]);
+    if (key_y(keys[miny_ind]) > y) miny_ind = i;
+    if (key_y(keys[maxy_ind]) < y) maxy_ind = i;
+  }
+  if (key_x(keys[0]) == key_x(keys[total - 1]) && key_y(keys[0]) == key_y(keys[total - 1])) {
+    hullbuf[nout++] = 0;  // sorted position; converted below
+  } else {
+    int* stack = S.stack;
+    int* tl_stack = stack;
+    int tl_count = sklansky(keys, 0, maxy_ind, tl_stack, -1, 1);
+    int* tr_stack = stack + tl_count;
+    int tr_count = sklansky(keys, total - 1, maxy_ind, tr_stack, -1, -1);
+    {  // !clockwise: swap
+      int* t = tl_stack; tl_stack = tr_stack; tr_stack = t;
+      int c = tl_count; tl_count = tr_count; tr_count = c;
+    }
+    for (int i = 0; i < tl_count - 1; ++i) hullbuf[nout++] = tl_stack[i];
+    for (int i = tr_count - 1; i > 0; --i) hullbuf[nout++] = tr_stack[i];
+    const int stop_idx = tr_count > 2 ? tr_stack[1] : (tl_count > 2 ? tl_stack[tl_count - 2] : -1);
+    // lower half reuses a second stack area (the upper stacks are no longer needed,
+    // but stop_idx was already captured)
+    int* stack2 = S.stack + (npad + 4) * 2;
+    int* bl_stack = stack2;
+    int bl_count = sklansky(keys, 0, miny_ind, bl_stack, 1, -1);
+    int* br_stack = stack2 + bl_count;
+    int br_count = sklansky(keys, total - 1, miny_ind, br_stack, 1, 1);
+    if (stop_idx >= 0) {
+      const int check_idx = bl_count > 2 ? bl_stack[1] : (bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1);
+      if (check_idx == stop_idx ||
+          (check_idx >= 0 && key_x(keys[check_idx]) == key_x(keys[stop_idx]) &&
+           key_y(keys[check_idx]) == key_y(keys[stop_idx]))) {
+        bl_count = min(bl_count, 2);
+        br_count = min(br_count, 2);
+      }
+    }
+    for (int i = 0; i < bl_count - 1; ++i) hullbuf[nout++] = bl_stack[i];
+    for (int i = br_count - 1; i > 0; --i) hullbuf[nout++] = br_stack[i];
+    // cyclic shift towards a monotone sequence of INPUT indices
+    if (nout >= 3) {
+      int min_idx = 0, max_idx = 0, lt = 0;
+      auto IDX = [&](int i) { return key_idx(keys[hullbuf[i]]); };
+      for (int i = 1; i < nout; ++i) {
+        const int idx = IDX(i);
+        lt += IDX(i - 1) < idx;
+        if (lt > 1 && lt <= i - 2) break;
+        if (idx < IDX(min_idx)) min_idx = i;
+        if (idx > IDX(max_idx)) max_idx = i;
+      }
+      const int mmdist = abs(max_idx - min_idx);
+      if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
+        const int ascending = (max_idx + 1) % nout == min_idx;
+        const int i0 = ascending ? min_idx : max_idx;
+        int j = i0;
+        if (i0 > 0) {
+          int* tmp = S.stack;  // free again
+          int i;
+          for (i = 0; i < nout; ++i) {
+            const int curr_idx = IDX(j);
+            tmp[i] = hullbuf[j];
+            const int next_j = j + 1 < nout ? j + 1 : 0;
+            const int next_idx = IDX(next_j);
+            if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
+            j = next_j;
+          }
+          if (i == nout)
+            for (i = 0; i < nout; ++i) hullbuf[i] = tmp[i];
+        }
+      }
+    }
+  }
+  const int n = nout;
+  float* hx = S.hx; float* hy = S.hy; float* vx = S.vx; float* vy = S.vy; float* inv = S.inv;
+  for (int i = 0; i < n; ++i) {
+    hx[i] = (float)key_x(keys[hullbuf[i]]);
+    hy[i] = (float)key_y(keys[hullbuf[i]]);
+  }
+  // ---- cv::minAreaRect
+  float cx = 0.f, cy = 0.f, w = 0.f, h = 0.f;
+  double angle = 0.0;
+  if (n > 2) {
+    // rotatingCalipers(CALIPERS_MINAREARECT)
+    int left = 0, bottom = 0, right = 0, top = 0;
+    float left_x, right_x, top_y, bottom_y;
+    float pt0x = hx[0], pt0y = hy[0];
+    left_x = right_x = pt0x;
+    top_y = bottom_y = pt0y;
+    for (int i = 0; i < n; ++i) {
+      if (pt0x < left_x) left_x = pt0x, left = i;
+      if (pt0x > right_x) right_x = pt0x, right = i;
+      if (pt0y > top_y) top_y = pt0y, top = i;
+      if (pt0y < bottom_y) bottom_y = pt0y, bottom = i;
+      const float nx = (i + 1 < n) ? hx[i + 1] : hx[0];
+      const float ny = (i + 1 < n) ? hy[i + 1] : hy[0];
+      const double dx = (double)nx - (double)pt0x;
+      const double dy = (double)ny - (double)pt0y;
+      vx[i] = (float)dx;
+      vy[i] = (float)dy;
+      inv[i] = (float)__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+      pt0x = nx, pt0y = ny;
+    }
+    float orientation = 0.f;
+    {
+      double ax = vx[n - 1], ay = vy[n - 1];
+      for (int i = 0; i < n; ++i) {
+        const double bx = vx[i], by = vy[i];
+        const double convexity = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));
+        if (convexity != 0) {
+          orientation = convexity > 0 ? 1.f : -1.f;
+          break;
+        }
+        ax = bx, ay = by;
+      }
+    }
+    float base_a = orientation, base_b = 0.f;
+    int seq[4] = {bottom, right, top, left};
+    float minarea = 3.402823466e+38f;
+    int b_left = 0, b_bottom = 0;
+    float b_a = 0.f, b_w = 0.f, b_b = 0.f, b_h = 0.f;
+    for (int k = 0; k < n; ++k) {
+      // edge vectors rotated into a common frame; the first one met when rotating is the main edge
+      float rx[4], ry[4];
+      rx[0] = vx[seq[0]], ry[0] = vy[seq[0]];
+      rx[1] = vy[seq[1]], ry[1] = -vx[seq[1]];
+      rx[2] = -vx[seq[2]], ry[2] = -vy[seq[2]];
+      rx[3] = -vy[seq[3]], ry[3] = vx[seq[3]];
+      int main_element = 0;
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        const float tx = ry[i], ty = -rx[i];  // rotate90CW(rv[i])
+        if (__fadd_rn(__fmul_rn(tx, rx[main_element]), __fmul_rn(ty, ry[main_element])) < 0.f) main_element = i;
+      }
+      {
+        const int pindex = seq[main_element];
+        const float lead_x = __fmul_rn(vx[pindex], inv[pindex]);
+        const float lead_y = __fmul_rn(vy[pindex], inv[pindex]);
+        switch (main_element) {
+          case 0: base_a = lead_x, base_b = lead_y; break;
+          case 1: base_a = lead_y, base_b = -lead_x; break;
+          case 2: base_a = -lead_x, base_b = -lead_y; break;
+          default: base_a = -lead_y, base_b = lead_x; break;
+        }
+      }
+      seq[main_element] += 1;
+      if (seq[main_element] == n) seq[main_element] = 0;
+      float dx = __fsub_rn(hx[seq[1]], hx[seq[3]]);
+      float dy = __fsub_rn(hy[seq[1]], hy[seq[3]]);
+      const float width = __fadd_rn(__fmul_rn(dx, base_a), __fmul_rn(dy, base_b));
+      dx = __fsub_rn(hx[seq[2]], hx[seq[0]]);
+      dy = __fsub_rn(hy[seq[2]], hy[seq[0]]);
+      const float height = __fadd_rn(__fmul_rn(-dx, base_b), __fmul_rn(dy, base_a));
+      const float area = __fmul_rn(width, height);
+      if (area <= minarea) {
+        minarea = area;
+        b_left = seq[3], b_a = base_a, b_w = width, b_b = base_b, b_h = height, b_bottom = seq[0];
+      }
+    }
+    const float A1 = b_a, B1 = b_b, A2 = -b_b, B2 = b_a;
+    const float C1 = __fadd_rn(__fmul_rn(A1, hx[b_left]), __fmul_rn(hy[b_left], B1));
+    const float C2 = __fadd_rn(__fmul_rn(A2, hx[b_bottom]), __fmul_rn(hy[b_bottom], B2));
+    const float idet = __fdiv_rn(1.f, __fsub_rn(__fmul_rn(A1, B2), __fmul_rn(A2, B1)));
+    const float ox = __fmul_rn(__fsub_rn(__fmul_rn(C1, B2), __fmul_rn(C2, B1)), idet);
+    const float oy = __fmul_rn(__fsub_rn(__fmul_rn(A1, C2), __fmul_rn(A2, C1)), idet);
+    const float o2 = __fmul_rn(A1, b_w), o3 = __fmul_rn(B1, b_w);
+    const float o4 = __fmul_rn(A2, b_h), o5 = __fmul_rn(B2, b_h);
+    cx = __fadd_rn(ox, __fmul_rn(__fadd_rn(o2, o4), 0.5f));
+    cy = __fadd_rn(oy, __fmul_rn(__fadd_rn(o3, o5), 0.5f));
+    w = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)o2, (double)o2), __dmul_rn((double)o3, (double)o3)));
+    h = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)o4, (double)o4), __dmul_rn((double)o5, (double)o5)));
+    angle = atan2((double)o3, (double)o2);
+  } else if (n == 2) {
+    cx = __fmul_rn(__fadd_rn(hx[0], hx[1]), 0.5f);
+    cy = __fmul_rn(__fadd_rn(hy[0], hy[1]), 0.5f);
+    const double dx = (double)__fsub_rn(hx[1], hx[0]);
+    const double dy = (double)__fsub_rn(hy[1], hy[0]);
+    w = (float)__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    h = 0.f;
+    angle = atan2(dy, dx);
+  } else if (n == 1) {
+    cx = hx[0], cy = hy[0];
+  }
+  angle = __ddiv_rn(__dmul_rn(angle, 180.0), 3.1415926535897932384626433832795);
+  // OpenCV 4.13 reports the angle in [-90, 0): fold by 180 into [-90, 90), then a >= 0 -> a - 90, swap w/h
+  if (angle >= 90.0) angle -= 180.0;
+  else if (angle < -90.0) angle += 180.0;
+  if (angle >= 0.0) {
+    angle -= 90.0;
+    const float t = w; w = h; h = t;
+  }
+  const float fangle = (float)angle;
+  if (out_rect) out_rect[0] = cx, out_rect[1] = cy, out_rect[2] = w, out_rect[3] = h, out_rect[4] = fangle;
+  // ---- cv::boxPoints (RotatedRect::points) then np.int0 (truncate toward zero)
+  const double ra = __ddiv_rn(__dmul_rn((double)fangle, 3.1415926535897932384626433832795), 180.0);
+  const float b = __fmul_rn((float)cos(ra), 0.5f);
+  const float a = __fmul_rn((float)sin(ra), 0.5f);
+  const float p0x = __fsub_rn(__fsub_rn(cx, __fmul_rn(a, h)), __fmul_rn(b, w));
+  const float p0y = __fsub_rn(__fadd_rn(cy, __fmul_rn(b, h)), __fmul_rn(a, w));
+  const float p1x = __fsub_rn(__fadd_rn(cx, __fmul_rn(a, h)), __fmul_rn(b, w));
+  const float p1y = __fsub_rn(__fsub_rn(cy, __fmul_rn(b, h)), __fmul_rn(a, w));
+  const float p2x = __fsub_rn(__fmul_rn(2.f, cx), p0x);
+  const float p2y = __fsub_rn(__fmul_rn(2.f, cy), p0y);
+  const float p3x = __fsub_rn(__fmul_rn(2.f, cx), p1x);
+  const float p3y = __fsub_rn(__fmul_rn(2.f, cy), p1y);
+  out_box[0] = (int)p0x, out_box[1] = (int)p0y, out_box[2] = (int)p1x, out_box[3] = (int)p1y;
+  out_box[4] = (int)p2x, out_box[5] = (int)p2y, out_box[6] = (int)p3x, out_box[7] = (int)p3y;
+}
+
+}  // namespace plh

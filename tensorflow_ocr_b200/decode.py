@@ -1,0 +1,96 @@
+"""PixelLink inference decode — the part the reference only has inline in its scripts
+(test_pixellink_fast.py:95-217, test_pixellink.py:94-230, test.py:24-74,182-218).
+
+``decode_pixellink`` is the explicitly named addition of SURVEY.md §8b; ``pixel_detect``,
+``order_points`` and ``sort_poly`` keep the names they have in the reference's ``test.py``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import head
+from .tool.pixellink_fn import pixel_detect as _pixel_detect_fn
+
+__all__ = ["decode_pixellink", "pixel_detect", "order_points", "sort_poly", "write_result_txt"]
+
+
+def decode_pixellink(pixel_logits, link_logits, pixel_thresh=0.8, link_thresh=0.9, min_size=10,
+                     scale=(4.0, 3.75), max_boxes=128):
+    """Logits -> (labels, boxes, counts), test_pixellink_fast.py:110-202 on the GPU.
+
+    pixel_logits [B,H,W,2] (or [H,W,2]), link_logits [B,H,W,16].
+      labels int32 [B,H,W]: -1 background / filtered component, else the component's
+             minimum linear pixel index (canonical labelling)
+      boxes  list of B int32 arrays [n_b,4,2] in cv2.boxPoints order, components in
+             ascending label order (np.int0(cv2.boxPoints(cv2.minAreaRect(pts))))
+      counts list of B int32 arrays [n_b]: pixel count of each component
+    numpy in -> numpy out; CUDA tensors in -> CUDA tensors (one sync to read n_boxes).
+    """
+    pl, np_in = head.to_device(pixel_logits)
+    ll, _ = head.to_device(link_logits, device=pl.device)
+    single = pl.dim() == 3
+    if single:
+        pl, ll = pl.unsqueeze(0), ll.unsqueeze(0)
+    cfg = head.DecodeConfig(pixel_thresh, link_thresh, min_size, (float(scale[0]), float(scale[1])), max_boxes)
+    out = head.decode_raw(pl, ll, cfg, want_rects=False)
+    n = out["n_boxes"].cpu().numpy()
+    if (n > max_boxes).any():
+        raise ValueError("an image has %d components; raise max_boxes (=%d)" % (int(n.max()), max_boxes))
+    labels = out["labels"]
+    boxes = [out["boxes"][b, : n[b]] for b in range(len(n))]
+    counts = [out["comp"][b, : n[b], 1] for b in range(len(n))]
+    if np_in:
+        labels = labels.cpu().numpy()
+        boxes = [b.cpu().numpy() for b in boxes]
+        counts = [c.cpu().numpy() for c in counts]
+    if single:
+        return labels[0], boxes[0], counts[0]
+    return labels, boxes, counts
+
+
+def pixel_detect(score_map, geo_map, score_map_thresh=0.8, link_thresh=0.8):
+    """Name of test.py:45-74.  The reference's twin there is buggy (`res[link_text[0],
+    link_text[1]] = 0` clears two cells instead of every failing pixel, and raises when
+    a direction has < 2 failing pixels — SURVEY.md quirk Q8); this implements the intended
+    semantics of tool/pixellink_fn.py:120-154 on test.py's input layout:
+    ``score_map`` [1,H,W,1], ``geo_map`` [1,H,W,16] with channel 2i+1 = link_i score."""
+    sm, np_in = head.to_device(score_map)
+    gm, _ = head.to_device(geo_map, device=sm.device)
+    if sm.dim() != 4 or gm.dim() != 4 or gm.shape[-1] != 16:
+        raise ValueError("expected score_map [1,H,W,1] and geo_map [1,H,W,16]")
+    H, W = sm.shape[1], sm.shape[2]
+    g = gm[0].reshape(H, W, 8, 2).permute(2, 0, 1, 3).unsqueeze(1).contiguous()  # [8,1,H,W,2]
+    out = _pixel_detect_fn(sm, g, score_map_thresh, link_thresh)
+    return out.cpu().numpy() if np_in else out
+
+
+def order_points(pts):
+    """test.py:24-35 — host-side ordering of one 4-point box (tl, tr, br, bl)."""
+    pts = np.asarray(pts)
+    x_sorted = pts[np.argsort(pts[:, 0]), :]
+    left_most, right_most = x_sorted[:2, :], x_sorted[2:, :]
+    left_most = left_most[np.argsort(left_most[:, 1]), :]
+    tl, bl = left_most
+    d = np.sqrt(((right_most.astype(np.float64) - tl.astype(np.float64)) ** 2).sum(1))
+    br, tr = right_most[np.argsort(d)[::-1], :]
+    return np.array([tl, tr, br, bl], dtype="int32")
+
+
+def sort_poly(p):
+    """test.py:37-43."""
+    p = np.asarray(p)
+    min_axis = np.argmin(np.sum(p, axis=1))
+    p = p[[min_axis, (min_axis + 1) % 4, (min_axis + 2) % 4, (min_axis + 3) % 4]]
+    if abs(p[0, 0] - p[1, 0]) > abs(p[0, 1] - p[1, 1]):
+        return p
+    return p[[0, 3, 2, 1]]
+
+
+def write_result_txt(path, boxes):
+    """ICDAR result line format of test_pixellink_fast.py:209-217 / test.py:212-218."""
+    with open(path, "w") as f:
+        for box in boxes:
+            box = np.asarray(box)
+            f.write("{},{},{},{},{},{},{},{}\r\n".format(box[0, 0], box[0, 1], box[1, 0], box[1, 1],
+                                                        box[2, 0], box[2, 1], box[3, 0], box[3, 1]))

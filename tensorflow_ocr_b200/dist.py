@@ -1,0 +1,44 @@
+"""Batch sharding across GPUs.
+
+The head shards by image, exactly like the reference's in-graph towers
+(multigpu_train.py:111-125 ``tf.split`` + one tower per GPU): every rank runs the
+fused head on its contiguous ``B/G`` slice with shard-local normalisers, so the
+gradients need no communication.  The only collective is one all-reduce of the
+loss scalars for reporting (the reference prints the last tower's loss only,
+multigpu_train.py:125,171 — quirk Q18).  Decode needs no communication.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+__all__ = ["shard_bounds", "shard_batch", "allreduce_loss_stats"]
+
+
+def shard_bounds(B: int, world_size: int, rank: int):
+    """Contiguous split identical to tf.split(axis=0) into equal parts; the remainder
+    (when B % world_size != 0) goes to the first ranks."""
+    base, rem = divmod(B, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(arrays: dict, world_size: int, rank: int) -> dict:
+    B = next(iter(arrays.values())).shape[0]
+    lo, hi = shard_bounds(B, world_size, rank)
+    return {k: v[lo:hi] for k, v in arrays.items()}
+
+
+def allreduce_loss_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum-all-reduce the first PLH_STATS_FLOATS loss scalars (<= 256 B, latency bound) and
+    return the cross-shard MEAN of the loss terms (tower average) together with the
+    summed counts.  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    v = stats[:_lib.STATS_FLOATS].clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+        w = dist.get_world_size(group)
+        mean_idx = [_lib.ST_TOTAL, _lib.ST_L_PIX, _lib.ST_LINK_TOTAL] + list(range(_lib.ST_L_LINK, _lib.ST_L_LINK + 8))
+        v[mean_idx] = v[mean_idx] / w
+    return v

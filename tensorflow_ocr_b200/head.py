@@ -1,0 +1,334 @@
+"""Host-side engine: thin, allocation-caching wrappers that hand device pointers to
+the C ABI (include/plhead.h).  torch is used for device memory, streams and
+host<->device copies only; every arithmetic step of the head runs in libplhead.so.
+
+All functions here are asynchronous with respect to the host (they enqueue on
+torch's current CUDA stream and return device tensors) unless the caller passed
+numpy arrays, in which case the results are copied back (tf.py_func-style,
+tool/pixellink_fn.py:114,157).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["DecodeConfig", "LossConfig", "pixellink_loss_raw", "decode_raw", "loss_and_decode_raw",
+           "ohnm_batch_raw", "dice_raw", "dice_head_raw", "east_loss_raw", "restore_rectangle_raw",
+           "pixel_detect_raw", "min_area_boxes_raw", "to_device", "launch_count"]
+
+
+# ----------------------------------------------------------------------------- configuration
+@dataclass(frozen=True)
+class LossConfig:
+    """Constants the reference hard-codes in the head (SURVEY.md §5 "Config / flags")."""
+    variant: int = _lib.VARIANT_MODEL
+    term: int = _lib.TERM_CE
+    neg_pos_ratio: int = 3        # nets/model.py:171
+    focal_alpha: float = 0.25     # Lin et al. 2017 (not in the reference)
+    focal_gamma: float = 2.0
+
+    def c_struct(self):
+        return _lib.LossParams(self.variant, self.term, self.neg_pos_ratio, self.focal_alpha, self.focal_gamma)
+
+
+@dataclass(frozen=True)
+class DecodeConfig:
+    pixel_thresh: float = 0.8               # test_pixellink_fast.py:12
+    link_thresh: float = 0.9                # test_pixellink_fast.py:13
+    min_size: int = 10                      # test_pixellink_fast.py:174 (200 in test_pixellink.py:177)
+    scale: Tuple[float, float] = (4.0, 3.75)  # (1280/320, 720/192) test_pixellink_fast.py:196-197
+    max_boxes: int = 128
+
+    def c_struct(self):
+        return _lib.DecodeParams(self.pixel_thresh, self.link_thresh, self.min_size, self.max_boxes,
+                                 float(self.scale[0]), float(self.scale[1]))
+
+
+# ----------------------------------------------------------------------------- plumbing
+def _require_gpu(device: Optional[torch.device] = None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("tensorflow_ocr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    major, _ = torch.cuda.get_device_capability(dev)
+    if major != 10:
+        raise RuntimeError("libplhead.so is built for sm_100a only; device %s has capability %d.x" % (dev, major))
+    return dev
+
+
+def to_device(x, dtype=torch.float32, device=None):
+    """numpy / torch (any device) -> contiguous CUDA tensor of `dtype`.  Returns (tensor, was_numpy)."""
+    was_numpy = not isinstance(x, torch.Tensor)
+    if was_numpy:
+        dev = _require_gpu(device)
+        t = torch.as_tensor(np.ascontiguousarray(x))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(dev, non_blocking=True), True
+    t = x
+    if not t.is_cuda:
+        t = t.to(_require_gpu(device))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous(), False
+
+
+_ws_cache = {}
+
+
+def _workspace(op: int, B: int, H: int, W: int, K: int, device: torch.device) -> torch.Tensor:
+    """Caller-owned workspace, cached per (device, stream, op, shape): the library keeps no state."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, op, B, H, W, K)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        n = _lib.load().plh_workspace_bytes(op, B, H, W, K)
+        if n == 0:
+            raise ValueError("bad shape for workspace query: op=%d B=%d H=%d W=%d" % (op, B, H, W))
+        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        if len(_ws_cache) > 64:
+            _ws_cache.clear()
+        _ws_cache[key] = ws
+    return ws
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count() -> int:
+    return int(_lib.load().plh_launch_count())
+
+
+# ----------------------------------------------------------------------------- loss
+def _check_head_shapes(pix_logits, link_logits, pix_lab, link_lab):
+    if pix_logits.dim() != 4 or pix_logits.shape[-1] != 2:
+        raise ValueError("pixel logits must be [B,H,W,2], got %s" % (tuple(pix_logits.shape),))
+    B, H, W, _ = pix_logits.shape
+    if tuple(link_logits.shape) != (B, H, W, 16):
+        raise ValueError("link logits must be [B,H,W,16], got %s" % (tuple(link_logits.shape),))
+    if pix_lab is not None and pix_lab.numel() != B * H * W:
+        raise ValueError("pixel labels must have B*H*W elements, got %s" % (tuple(pix_lab.shape),))
+    if link_lab is not None and tuple(link_lab.shape) != (B, H, W, 8):
+        raise ValueError("link labels must be [B,H,W,8], got %s" % (tuple(link_lab.shape),))
+    return B, H, W
+
+
+def pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, cfg: LossConfig = LossConfig(),
+                       want_grad: bool = True, want_mask: bool = False,
+                       decode: Optional[DecodeConfig] = None, out: Optional[dict] = None) -> dict:
+    """Fused PixelLink loss fwd+bwd on CUDA tensors (plh_pixellink_loss).
+
+    Returns device tensors: stats [64+B], grad_pixel, grad_link (if want_grad),
+    ohem_mask uint8 [B,H,W] (if want_mask), flags uint16 [B,H,W] (if decode is given).
+    `out` may carry preallocated tensors of those names to be reused.
+    """
+    lib = _lib.load()
+    B, H, W = _check_head_shapes(pix_logits, link_logits, pix_lab, link_lab)
+    dev = pix_logits.device
+    _require_gpu(dev)
+    out = {} if out is None else out
+
+    def buf(name, shape, dtype):
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            out[name] = t
+        return t
+
+    stats = buf("stats", (_lib.STATS_FLOATS + B,), torch.float32)
+    gp = buf("grad_pixel", (B, H, W, 2), torch.float32) if want_grad else None
+    gl = buf("grad_link", (B, H, W, 16), torch.float32) if want_grad else None
+    mask = buf("ohem_mask", (B, H, W), torch.uint8) if want_mask else None
+    flags = buf("flags", (B, H, W), torch.int16) if decode is not None else None
+    ws = _workspace(_lib.OP_LOSS, B, H, W, 0, dev)
+    lp = cfg.c_struct()
+    dp = decode.c_struct() if decode is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.plh_pixellink_loss(_p(pix_logits), _p(link_logits), _p(pix_lab), _p(link_lab), None, B, H, W,
+                                    C.byref(lp), _p(stats), _p(gp), _p(gl), _p(mask), _p(flags),
+                                    C.byref(dp) if dp is not None else None, _p(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_pixellink_loss")
+    return out
+
+
+def ohnm_batch_raw(scores, pos_mask, neg_mask, variant=_lib.VARIANT_MODEL, ratio=3, n_pos=None):
+    """plh_ohnm_batch: scores [B,N] fp32, masks [B,N] uint8 -> (selected fp32 [B,N], thr [B])."""
+    lib = _lib.load()
+    B, N = scores.shape
+    dev = scores.device
+    _require_gpu(dev)
+    sel = torch.empty((B, N), dtype=torch.float32, device=dev)
+    thr = torch.empty((B,), dtype=torch.float32, device=dev)
+    ws = torch.empty(max(B * N * 4, 16), dtype=torch.uint8, device=dev) if N * 4 > 200 * 1024 else None
+    with torch.cuda.device(dev):
+        rc = lib.plh_ohnm_batch(_p(scores), _p(pos_mask), _p(neg_mask), _p(n_pos), B, N, variant, ratio, _p(sel),
+                                _p(thr), _p(ws), 0 if ws is None else ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_ohnm_batch")
+    return sel, thr
+
+
+# ----------------------------------------------------------------------------- decode
+def _decode_outputs(B, H, W, K, dev, out, want_rects):
+    out = {} if out is None else out
+
+    def buf(name, shape, dtype):
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            out[name] = t
+        return t
+
+    labels = buf("labels", (B, H, W), torch.int32)
+    boxes = buf("boxes", (B, K, 4, 2), torch.int32)
+    n_boxes = buf("n_boxes", (B,), torch.int32)
+    comp = buf("comp", (B, K, 2), torch.int32)
+    rects = buf("rects", (B, K, 5), torch.float32) if want_rects else None
+    return out, labels, boxes, n_boxes, comp, rects
+
+
+def decode_raw(pix_logits, link_logits, cfg: DecodeConfig = DecodeConfig(), out: Optional[dict] = None,
+               want_rects: bool = True) -> dict:
+    """plh_decode on CUDA tensors.  Returns labels int32 [B,H,W], boxes int32 [B,K,4,2],
+    n_boxes int32 [B], comp int32 [B,K,2] (label, size), rects fp32 [B,K,5]."""
+    lib = _lib.load()
+    B, H, W = _check_head_shapes(pix_logits, link_logits, None, None)
+    dev = pix_logits.device
+    _require_gpu(dev)
+    K = cfg.max_boxes
+    out, labels, boxes, n_boxes, comp, rects = _decode_outputs(B, H, W, K, dev, out, want_rects)
+    ws = _workspace(_lib.OP_DECODE, B, H, W, K, dev)
+    dp = cfg.c_struct()
+    with torch.cuda.device(dev):
+        rc = lib.plh_decode(_p(pix_logits), _p(link_logits), B, H, W, C.byref(dp), _p(labels), _p(boxes),
+                            _p(n_boxes), _p(rects), _p(comp), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_decode")
+    return out
+
+
+def decode_from_flags_raw(flags, cfg: DecodeConfig = DecodeConfig(), out: Optional[dict] = None,
+                          want_rects: bool = True) -> dict:
+    lib = _lib.load()
+    B, H, W = flags.shape
+    dev = flags.device
+    K = cfg.max_boxes
+    out, labels, boxes, n_boxes, comp, rects = _decode_outputs(B, H, W, K, dev, out, want_rects)
+    ws = _workspace(_lib.OP_DECODE, B, H, W, K, dev)
+    dp = cfg.c_struct()
+    with torch.cuda.device(dev):
+        rc = lib.plh_decode_from_flags(_p(flags), B, H, W, C.byref(dp), _p(labels), _p(boxes), _p(n_boxes),
+                                       _p(rects), _p(comp), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_decode_from_flags")
+    return out
+
+
+def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossConfig = LossConfig(),
+                        dcfg: DecodeConfig = DecodeConfig(), out: Optional[dict] = None,
+                        want_rects: bool = False) -> dict:
+    """The fused head step: loss fwd+bwd and decode sharing ONE read of the logits
+    (the loss kernel emits the 2 B/px threshold flags the decode starts from)."""
+    out = pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg, True, False, dcfg, out)
+    return decode_from_flags_raw(out["flags"], dcfg, out, want_rects)
+
+
+def min_area_boxes_raw(pts: torch.Tensor, offsets: torch.Tensor, want_rects=True):
+    """plh_min_area_boxes: pts int32 [total,2], offsets int32 [n+1] -> boxes int32 [n,4,2], rects [n,5]."""
+    lib = _lib.load()
+    dev = pts.device
+    _require_gpu(dev)
+    n = offsets.numel() - 1
+    boxes = torch.empty((n, 4, 2), dtype=torch.int32, device=dev)
+    rects = torch.empty((n, 5), dtype=torch.float32, device=dev) if want_rects else None
+    with torch.cuda.device(dev):
+        rc = lib.plh_min_area_boxes(_p(pts), _p(offsets), n, _p(boxes), _p(rects), _stream(dev))
+    _lib.check(rc, "plh_min_area_boxes")
+    return boxes, rects
+
+
+def pixel_detect_raw(score, link, thr_p, thr_l):
+    """plh_pixel_detect: score [H,W], link [8,H,W,2] probabilities -> uint8 [H,W]."""
+    lib = _lib.load()
+    H, W = score.shape
+    dev = score.device
+    _require_gpu(dev)
+    outm = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_pixel_detect(_p(score), _p(link), H, W, float(thr_p), float(thr_l), _p(outm), _stream(dev))
+    _lib.check(rc, "plh_pixel_detect")
+    return outm
+
+
+# ----------------------------------------------------------------------------- dice / EAST
+def dice_raw(y_true, y_pred, mask, want_grad=True):
+    lib = _lib.load()
+    dev = y_pred.device
+    _require_gpu(dev)
+    M = y_pred.numel()
+    outv = torch.empty((4,), dtype=torch.float32, device=dev)
+    grad = torch.empty_like(y_pred) if want_grad else None
+    ws = _workspace(_lib.OP_DICE, 1, 1, 1, 0, dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_dice(_p(y_true), _p(y_pred), _p(mask), M, _p(outv), _p(grad), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_dice")
+    return outv, grad
+
+
+def dice_head_raw(t_pix, p_pix, t_link, p_link, mask, want_grad=True):
+    lib = _lib.load()
+    dev = p_pix.device
+    _require_gpu(dev)
+    M = p_pix.numel()
+    if p_link.numel() != 8 * M or mask.numel() != M:
+        raise ValueError("dice head expects pixel [M,1], link [M,8], mask [M]")
+    outv = torch.empty((28,), dtype=torch.float32, device=dev)
+    gp = torch.empty_like(p_pix) if want_grad else None
+    gl = torch.empty_like(p_link) if want_grad else None
+    ws = _workspace(_lib.OP_DICE, 1, 1, 1, 0, dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_dice_head(_p(t_pix), _p(p_pix), _p(t_link), _p(p_link), _p(mask), M, _p(outv), _p(gp), _p(gl),
+                               _p(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_dice_head")
+    return outv, gp, gl
+
+
+def east_loss_raw(score_gt, score_pred, geo_gt, geo_pred, mask, want_grad=True):
+    lib = _lib.load()
+    dev = score_pred.device
+    _require_gpu(dev)
+    M = score_pred.numel()
+    if geo_pred.numel() != 5 * M:
+        raise ValueError("EAST geometry must be [...,5]")
+    outv = torch.empty((8,), dtype=torch.float32, device=dev)
+    gs = torch.empty_like(score_pred) if want_grad else None
+    gg = torch.empty_like(geo_pred) if want_grad else None
+    ws = _workspace(_lib.OP_EAST_LOSS, 1, 1, 1, 0, dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_east_loss(_p(score_gt), _p(score_pred), _p(geo_gt), _p(geo_pred), _p(mask), M, _p(outv),
+                               _p(gs), _p(gg), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_east_loss")
+    return outv, gs, gg
+
+
+def restore_rectangle_raw(origin, geometry, want_index=False):
+    lib = _lib.load()
+    dev = origin.device
+    _require_gpu(dev)
+    N = origin.shape[0]
+    outp = torch.empty((N, 4, 2), dtype=torch.float64, device=dev)
+    idx = torch.empty((N,), dtype=torch.int32, device=dev) if want_index else None
+    if N == 0:
+        return outp, idx
+    ws = torch.empty((N // 1024 + 2) * 4 + 256, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_restore_rectangle(_p(origin), _p(geometry), N, _p(outp), _p(idx), _p(ws), ws.numel(),
+                                       _stream(dev))
+    _lib.check(rc, "plh_restore_rectangle")
+    return outp, idx

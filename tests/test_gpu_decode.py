@@ -1,0 +1,159 @@
+"""Parity of the CUDA decode (through the C ABI) against the oracle / OpenCV: bit-exact
+labels (canonical min-index) and integer box corners."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode(inp, **kw):
+    import torch
+    from tensorflow_ocr_b200 import head
+    dev = torch.device("cuda", 0)
+    cfg = head.DecodeConfig(**kw)
+    out = head.decode_raw(torch.as_tensor(inp["pix_logits"]).to(dev), torch.as_tensor(inp["link_logits"]).to(dev), cfg)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _check(inp, out, min_size=10, scale=(4.0, 3.75), pixel_thresh=0.8, link_thresh=0.9):
+    from oracle import decode as D
+    B = inp["pix_logits"].shape[0]
+    nb = 0
+    for b in range(B):
+        lab, boxes, sizes, rects = D.decode_pixellink(inp["pix_logits"][b], inp["link_logits"][b], pixel_thresh,
+                                                      link_thresh, min_size, scale)
+        assert np.array_equal(out["labels"][b], lab), "labels differ in image %d" % b
+        n = len(boxes)
+        assert out["n_boxes"][b] == n
+        assert np.array_equal(out["comp"][b, :n, 1], sizes)
+        assert np.array_equal(out["comp"][b, :n, 0], np.unique(lab[lab >= 0]))
+        assert np.array_equal(out["boxes"][b, :n], boxes), "box corners differ in image %d" % b
+        assert np.array_equal(out["rects"][b, :n], rects), "rects differ in image %d" % b
+        nb += n
+    return nb
+
+
+@pytest.mark.parametrize("family", ["G", "S"])
+@pytest.mark.parametrize("B,H,W", [(4, 128, 128), (3, 48, 80), (2, 192, 320), (5, 33, 47)])
+def test_decode_vs_oracle(family, B, H, W, cuda_dev):
+    from tensorflow_ocr_b200 import synth
+    inp = synth.make_batch(11, B, H, W, family, edge_images=(B >= 4))
+    out = _decode(inp, max_boxes=256)
+    nb = _check(inp, out)
+    assert nb > 0 or H < 40
+
+
+def test_decode_variants(cuda_dev):
+    """full-res script constants (test_pixellink.py:177,209-215): min_size 200, no scaling;
+    and a 2s configuration (scale 2.0, 1.875)."""
+    from tensorflow_ocr_b200 import synth
+    inp = synth.make_batch(12, 2, 160, 256, "G")
+    out = _decode(inp, min_size=200, scale=(1.0, 1.0), max_boxes=64, pixel_thresh=0.6, link_thresh=0.6)
+    _check(inp, out, min_size=200, scale=(1.0, 1.0), pixel_thresh=0.6, link_thresh=0.6)
+    out = _decode(inp, min_size=0, scale=(2.0, 1.875), max_boxes=4096, pixel_thresh=0.7, link_thresh=0.7)
+    _check(inp, out, min_size=0, scale=(2.0, 1.875), pixel_thresh=0.7, link_thresh=0.7)
+
+
+def test_decode_literal_dfs_crosscheck():
+    """Oracle-only: on symmetric links without positive border pixels the canonical
+    components equal the reference's literal DFS grouping."""
+    from oracle import decode as D
+    from tensorflow_ocr_b200 import synth
+    for i in range(3):
+        im = synth.make_image(13, i, 40, 56, "S")
+        P, L = D.thresholds(im["pix_logits"], im["link_logits"])
+        P[0, :] = P[-1, :] = False
+        P[:, 0] = P[:, -1] = False
+        lab, roots, sizes = D.link_components(P, L, 10)
+        g, n = D.link_components_literal(P, L, 10)
+        assert n == len(roots)
+        for gid in range(1, n + 1):
+            px = np.argwhere(g == gid)
+            r = lab[px[0][0], px[0][1]]
+            assert r >= 0 and np.array_equal(lab == r, g == gid)
+
+
+def test_min_area_boxes_vs_cv2(cuda_dev):
+    """CUDA rotating calipers vs cv2.minAreaRect/boxPoints/np.int0 on explicit point lists."""
+    import cv2
+    import torch
+    from tensorflow_ocr_b200 import head
+    rng = np.random.default_rng(5)
+    sets = []
+    for t in range(400):
+        mode = t % 5
+        if mode == 0:
+            n = int(rng.integers(1, 300))
+            pts = rng.integers(0, int(rng.integers(5, 1300)), (n, 2))
+        elif mode == 1:
+            H, W = int(rng.integers(10, 120)), int(rng.integers(10, 160))
+            img = np.zeros((H, W), np.uint8)
+            cv2.ellipse(img, (W // 2, H // 2), (int(rng.integers(2, W // 2)), int(rng.integers(2, H // 2))),
+                        float(rng.uniform(0, 180)), 0, 360, 1, -1)
+            yx = np.argwhere(img > 0)
+            pts = np.stack([yx[:, 1] * 2.0, yx[:, 0] * 1.875], 1).astype(np.int64)
+        elif mode == 2:
+            n = int(rng.integers(1, 5))
+            p0 = rng.integers(0, 200, 2)
+            d = rng.integers(-5, 6, 2)
+            pts = np.array([p0 + d * k for k in range(n)])
+        elif mode == 3:
+            H, W = int(rng.integers(3, 60)), int(rng.integers(3, 60))
+            img = np.zeros((H, W), np.uint8)
+            y0, x0 = int(rng.integers(0, H)), int(rng.integers(0, W))
+            img[y0:y0 + int(rng.integers(1, 10)), x0:x0 + int(rng.integers(1, 30))] = 1
+            yx = np.argwhere(img > 0)
+            pts = np.stack([yx[:, 1] * 4.0, yx[:, 0] * 3.75], 1).astype(np.int64)
+        else:
+            H, W = int(rng.integers(8, 60)), int(rng.integers(8, 80))
+            img = np.zeros((H, W), np.uint8)
+            box = cv2.boxPoints(((rng.uniform(0, W), rng.uniform(0, H)), (rng.uniform(3, 50), rng.uniform(2, 15)),
+                                 rng.uniform(-90, 90)))
+            cv2.fillPoly(img, [np.round(box).astype(np.int32)], 1)
+            yx = np.argwhere(img > 0)
+            pts = np.stack([yx[:, 1] * 4.0, yx[:, 0] * 3.75], 1).astype(np.int64)
+        if len(pts) == 0 or len(pts) > 4096:
+            continue
+        pts = np.array(sorted(pts.tolist(), key=lambda t: (t[1], t[0])), np.int32).reshape(-1, 2)
+        sets.append(pts)
+    offs = np.zeros(len(sets) + 1, np.int32)
+    offs[1:] = np.cumsum([len(s) for s in sets])
+    allp = np.concatenate(sets).astype(np.int32)
+    boxes, rects = head.min_area_boxes_raw(torch.as_tensor(allp).to(cuda_dev), torch.as_tensor(offs).to(cuda_dev))
+    boxes, rects = boxes.cpu().numpy(), rects.cpu().numpy()
+    bad = 0
+    for i, s in enumerate(sets):
+        r = cv2.minAreaRect(s)
+        ref_box = np.intp(cv2.boxPoints(r))
+        ref_rect = np.array([r[0][0], r[0][1], r[1][0], r[1][1], r[2]], np.float32)
+        if not (np.array_equal(boxes[i], ref_box) and np.array_equal(rects[i], ref_rect)):
+            bad += 1
+    assert bad == 0, "%d / %d point sets differ from cv2" % (bad, len(sets))
+
+
+def test_pixel_detect(golden_dir, cuda_dev):
+    from tensorflow_ocr_b200.tool import pixellink_fn
+    g = np.load(golden_dir + "/pixel_detect.npz")
+    assert np.array_equal(pixellink_fn.pixel_detect(g["score"], g["geo"]), g["res"])
+    assert np.array_equal(pixellink_fn.pixel_detect(g["score"], g["geo"], 0.75, 0.7), g["res_075_07"])
+
+
+def test_fused_loss_decode_flags(cuda_dev):
+    """The fused path (flags emitted by the loss kernel) decodes identically to the standalone decode."""
+    import torch
+    from tensorflow_ocr_b200 import head, synth
+    inp = synth.make_batch(14, 6, 64, 96, "G", edge_images=True)
+    t = {k: torch.as_tensor(inp[k]).to(cuda_dev) for k in ("pix_logits", "link_logits", "pix_lab", "link_lab")}
+    dcfg = head.DecodeConfig(max_boxes=128)
+    fused = head.loss_and_decode_raw(t["pix_logits"], t["link_logits"], t["pix_lab"], t["link_lab"], head.LossConfig(),
+                                     dcfg, want_rects=True)
+    alone = head.decode_raw(t["pix_logits"], t["link_logits"], dcfg)
+    torch.cuda.synchronize()
+    for k in ("labels", "n_boxes"):
+        assert torch.equal(fused[k], alone[k])
+    n = alone["n_boxes"].cpu().numpy()
+    for b in range(6):
+        assert torch.equal(fused["boxes"][b, :n[b]], alone["boxes"][b, :n[b]])
+    out = {k: v.cpu().numpy() for k, v in fused.items()}
+    _check(inp, out)
