@@ -16,7 +16,7 @@ size_t loss_workspace_bytes(int B, int H, int W);             // loss.cu
 size_t decode_workspace_bytes(int B, int H, int W, int K);    // decode.cu
 
 constexpr int kRedThreads = 256;
-constexpr int kRedMaxCTAs = kNumSMs * 8;
+constexpr int kRedMaxCTAs = kNumSMs * 4;
 
 struct RedHeader {
   unsigned ticket;
@@ -82,12 +82,8 @@ dice_reduce_kernel(const float* __restrict__ tA, const float* __restrict__ pA, c
   if (!s_last) return;
   __threadfence();
   __shared__ double s_fin[3 * C];
-  if (threadIdx.x < 3 * C) {
-    double s = 0.0;
-    for (unsigned c = 0; c < gridDim.x; ++c) s += (double)__ldcg(partials + (size_t)c * 32 + threadIdx.x);
-    s_fin[threadIdx.x] = s;
-  }
-  __syncthreads();
+  __shared__ double s_tmp[(kRedThreads / (3 * C)) * 3 * C];
+  block_final_reduce<3 * C, kRedThreads>(partials, 32, gridDim.x, s_fin, s_tmp);
   if (threadIdx.x == 0) {
     // out: [0] total, then per channel: dice, I, U
     float total = 0.f;
@@ -207,12 +203,8 @@ east_reduce_kernel(const float* __restrict__ sg, const float* __restrict__ sp, c
   if (!s_last) return;
   __threadfence();
   __shared__ double s_fin[5];
-  if (threadIdx.x < 5) {
-    double s = 0.0;
-    for (unsigned c = 0; c < gridDim.x; ++c) s += (double)__ldcg(partials + (size_t)c * 32 + threadIdx.x);
-    s_fin[threadIdx.x] = s;
-  }
-  __syncthreads();
+  __shared__ double s_tmp[(kRedThreads / 5) * 5];
+  block_final_reduce<5, kRedThreads>(partials, 32, gridDim.x, s_fin, s_tmp);
   if (threadIdx.x == 0) {
     const float I = (float)s_fin[0];
     const float U = (float)s_fin[1] + (float)s_fin[2] + 1e-5f;

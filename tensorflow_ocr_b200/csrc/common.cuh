@@ -56,4 +56,27 @@ __device__ __forceinline__ float neg_class_score(float x0, float x1) {
   return __fdiv_rn(e0, __fadd_rn(e0, e1));
 }
 
+// Deterministic block-wide sum of per-CTA partial vectors.  Thread t owns value t % NV and
+// CTAs g, g+G, ... (g = t / NV, G = T / NV groups): one fp64 accumulator per thread,
+// independent loads, then a fixed-order sum over the groups.  Result in s_out[NV]
+// (shared, valid after the trailing __syncthreads).  s_tmp holds (T / NV) * NV doubles.
+template <int NV, int T>
+__device__ __forceinline__ void block_final_reduce(const float* partials, int stride, unsigned ncta, double* s_out,
+                                                   double* s_tmp) {
+  constexpr int G = T / NV;
+  const int g = threadIdx.x / NV, i = threadIdx.x - g * NV;
+  if (g < G) {
+    double acc = 0.0;
+    for (unsigned c = g; c < ncta; c += G) acc += (double)__ldcg(partials + (size_t)c * stride + i);
+    s_tmp[g * NV + i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int gg = 0; gg < G; ++gg) s += s_tmp[gg * NV + threadIdx.x];
+    s_out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
 }  // namespace plh

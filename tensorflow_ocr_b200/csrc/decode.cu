@@ -15,8 +15,8 @@
 //                 larger root under the smaller (atomicMin) -> root = min pixel index
 //   D2 flatten    parent[v] = root, component sizes (warp-aggregated atomics),
 //                 border pixels that no edge reaches are dropped (not graph nodes)
-//   D3 compact    one CTA per image: roots with size > min_size in ascending order
-//                 -> box slots
+//   D3 roots      roots with size > min_size take a box slot (ascending-label order is
+//                 restored by ranking in D5)
 //   D4 labels     final label map + per-(component,row) min/max x (run-end atomics)
 //   D5 rects      one CTA per component: row extremes -> sort -> OpenCV-exact hull +
 //                 rotating calipers -> 4 integer corners (rect.cuh)
@@ -113,6 +113,18 @@ __device__ __forceinline__ int find_root(int* parent, int v) {
   return v;
 }
 
+// Read-only find (no path compression): used by the flatten pass, where a compressing
+// store could overwrite another thread's final `parent[v] = root`.
+__device__ __forceinline__ int find_root_ro(const int* parent, int v) {
+  const volatile int* P = parent;
+  int p = P[v];
+  while (p != v) {
+    v = p;
+    p = P[v];
+  }
+  return v;
+}
+
 __device__ __forceinline__ void unite(int* parent, int a, int b) {
   while (true) {
     a = find_root(parent, a);
@@ -177,7 +189,7 @@ decode_flatten_kernel(const uint16_t* __restrict__ flags, int H, int W, long lon
         }
       }
       if (node) {
-        root = find_root(parent, (int)g);
+        root = find_root_ro(parent, (int)g);
         parent[g] = root;
       } else {
         parent[g] = -1;
@@ -192,68 +204,28 @@ decode_flatten_kernel(const uint16_t* __restrict__ flags, int H, int W, long lon
   }
 }
 
-// ------------------------------------------------------------------ D3: per-image ordered compaction
-// After this kernel size[root] holds the box slot of a kept component (may be >= K:
-// kept, but no box row) or -1 for a filtered one.
-__global__ void __launch_bounds__(1024)
-decode_compact_kernel(const int* __restrict__ parent, int* __restrict__ size, int N, int min_size, int K,
-                      int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes,
-                      int* __restrict__ rowmin, int* __restrict__ rowmax, int H) {
-  __shared__ int s_warp[32];
-  __shared__ int s_base, s_total;
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long base = (long long)b * N;
-  if (tid == 0) s_base = 0;
-  for (int i0 = 0; i0 < N; i0 += 1024) {
-    const int i = i0 + tid;
-    bool is_root = false, keep = false;
-    int sz = 0;
-    if (i < N) {
-      is_root = parent[base + i] == (int)(base + i);
-      if (is_root) {
-        sz = size[base + i];
-        keep = sz > min_size;  // test_pixellink_fast.py:174 `len(index_list) > 10`
+// ------------------------------------------------------------------ D3: kept roots -> box slots
+// Every root with size > min_size takes a slot (arrival order; the ascending-label order
+// of the output is restored by ranking in D5).  Afterwards size[root] holds the slot of a
+// kept component (may be >= K: kept in the label map, but no box row) or -1 for a filtered one.
+__global__ void __launch_bounds__(256)
+decode_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int N, int total_px, int min_size, int K,
+                    int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
+    if (parent[g] != g) continue;
+    const int sz = size[g];
+    if (sz > min_size) {  // test_pixellink_fast.py:174 `len(index_list) > 10`
+      const int b = g / N;
+      const int slot = atomicAdd(&n_boxes[b], 1);
+      size[g] = slot;
+      if (slot < K) {
+        comp_root[(size_t)b * K + slot] = g - b * N;
+        comp_size[(size_t)b * K + slot] = sz;
       }
+    } else {
+      size[g] = -1;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_warp[warp] = __popc(m);
-    __syncthreads();
-    if (warp == 0) {
-      const int v = s_warp[lane];
-      int inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      s_warp[lane] = inc - v;  // exclusive prefix over warps
-      if (lane == 31) s_total = inc;
-    }
-    __syncthreads();
-    const int slot = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
-    if (is_root) {
-      if (keep) {
-        size[base + i] = slot;
-        if (slot < K) {
-          comp_root[(size_t)b * K + slot] = i;
-          comp_size[(size_t)b * K + slot] = sz;
-        }
-      } else {
-        size[base + i] = -1;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) s_base += s_total;
-  }
-  __syncthreads();
-  const int total = s_base;
-  if (tid == 0) n_boxes[b] = total;
-  // initialise the row-extreme tables of the used slots
-  const int used = min(total, K);
-  for (int i = tid; i < used * H; i += 1024) {
-    rowmin[(size_t)b * K * H + i] = 0x7fffffff;
-    rowmax[(size_t)b * K * H + i] = -1;
   }
 }
 
@@ -289,17 +261,25 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
                     int H, int W, int K, double sx, double sy, int npad, int32_t* __restrict__ boxes,
                     float* __restrict__ rects, int32_t* __restrict__ comp) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int s_n;
+  __shared__ int s_n, s_rank;
   const int b = blockIdx.y, slot = blockIdx.x;
-  if (slot >= min(n_boxes[b], K)) return;
+  const int nb = min(n_boxes[b], K);
+  if (slot >= nb) return;
   RectSmem S = rect_carve(smem, npad);
   const size_t rowbase = ((size_t)b * K + slot) * H;
-  if (threadIdx.x == 0) s_n = 0;
+  if (threadIdx.x == 0) s_n = 0, s_rank = 0;
   for (int i = threadIdx.x; i < npad; i += blockDim.x) S.keys[i] = ~0ull;
   __syncthreads();
+  const int root = comp_root[(size_t)b * K + slot];
+  // output position = rank of this component's label among the image's kept components
+  {
+    int r = 0;
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) r += comp_root[(size_t)b * K + j] < root;
+    r = __reduce_add_sync(0xffffffffu, r);
+    if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_rank, r);
+  }
   // candidates: (minx, y) and (maxx, y) of every occupied row; input index = row-major order
   // (test_pixellink_fast.py:194-197: x*scale_x, y*scale_y assigned into an int64 array -> trunc)
-  const int root = comp_root[(size_t)b * K + slot];
   const int y0 = root / W;  // the component's first row: its minimum pixel index lives there
   for (int y = y0 + threadIdx.x; y < H; y += blockDim.x) {
     const int mn = rowmin[rowbase + y], mx = rowmax[rowbase + y];
@@ -312,22 +292,26 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
   }
   __syncthreads();
   const int total = s_n;
-  bitonic_sort(S.keys, npad);
+  const int rank = s_rank;
+  // sort only as many as needed (power of two >= total)
+  int nsort = 32;
+  while (nsort < total) nsort <<= 1;
+  bitonic_sort(S.keys, nsort);
+  int box[8];
+  float rect[5];
+  min_area_box_sorted(S, total, npad, box, rect);
   if (threadIdx.x == 0) {
-    int box[8];
-    float rect[5];
-    min_area_box_sorted(S, total, npad, box, rect);
-    int32_t* ob = boxes + ((size_t)b * K + slot) * 8;
+    int32_t* ob = boxes + ((size_t)b * K + rank) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) ob[i] = box[i];
     if (rects) {
-      float* orc = rects + ((size_t)b * K + slot) * 5;
+      float* orc = rects + ((size_t)b * K + rank) * 5;
 #pragma unroll
       for (int i = 0; i < 5; ++i) orc[i] = rect[i];
     }
     if (comp) {
-      comp[((size_t)b * K + slot) * 2] = root;
-      comp[((size_t)b * K + slot) * 2 + 1] = comp_size[(size_t)b * K + slot];
+      comp[((size_t)b * K + rank) * 2] = root;
+      comp[((size_t)b * K + rank) * 2 + 1] = comp_size[(size_t)b * K + slot];
     }
   }
 }
@@ -340,19 +324,16 @@ min_area_boxes_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict
   RectSmem S = rect_carve(smem, npad);
   const int s = blockIdx.x;
   const int o0 = offsets[s], total = offsets[s + 1] - o0;
-  for (int i = threadIdx.x; i < npad; i += blockDim.x)
+  int nsort = 32;
+  while (nsort < total) nsort <<= 1;
+  for (int i = threadIdx.x; i < nsort; i += blockDim.x)
     S.keys[i] = i < total ? make_key(pts[2 * (o0 + i)], pts[2 * (o0 + i) + 1], i) : ~0ull;
   __syncthreads();
-  bitonic_sort(S.keys, npad);
+  bitonic_sort(S.keys, nsort);
+  int box[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float rect[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (total > 0) min_area_box_sorted(S, total, npad, box, rect);
   if (threadIdx.x == 0) {
-    int box[8];
-    float rect[5];
-    if (total > 0) {
-      min_area_box_sorted(S, total, npad, box, rect);
-    } else {
-      for (int i = 0; i < 8; ++i) box[i] = 0;
-      for (int i = 0; i < 5; ++i) rect[i] = 0.f;
-    }
     for (int i = 0; i < 8; ++i) boxes[(size_t)s * 8 + i] = box[i];
     if (rects)
       for (int i = 0; i < 5; ++i) rects[(size_t)s * 5 + i] = rect[i];
@@ -415,8 +396,14 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   if ((rc = launch_status())) return rc;
   decode_flatten_kernel<<<grid_px, 256, 0, s>>>(flags, H, W, total_px, parent, size);
   if ((rc = launch_status())) return rc;
-  decode_compact_kernel<<<B, 1024, 0, s>>>(parent, size, N, p->min_size, K, comp_root, comp_size, n_boxes, rowmin,
-                                           rowmax, H);
+  {
+    cudaError_t e = cudaMemsetAsync(n_boxes, 0, sizeof(int) * (size_t)B, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(rowmin, 0x7f, sizeof(int) * (size_t)B * K * H, s);  // 0x7f7f7f7f = +big
+    if (e == cudaSuccess) e = cudaMemsetAsync(rowmax, 0xff, sizeof(int) * (size_t)B * K * H, s);  // -1
+    if (e != cudaSuccess) return (int)e;
+  }
+  decode_roots_kernel<<<grid_px, 256, 0, s>>>(parent, size, N, (int)total_px, p->min_size, K, comp_root, comp_size,
+                                              n_boxes);
   if ((rc = launch_status())) return rc;
   decode_labels_kernel<<<grid_px, 256, 0, s>>>(parent, size, H, W, total_px, K, labels, rowmin, rowmax);
   if ((rc = launch_status())) return rc;

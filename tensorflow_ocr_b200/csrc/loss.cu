@@ -3,14 +3,15 @@
 // Replaces nets/model.py:145-261, nets/model_vgg_16.py:227-282 and
 // nets/pixellink.py:88-263 of the reference.
 //
-// Pipeline (three launches on one stream, no host sync):
-//   K1 ohem_select   one CTA per image: pixel scores -> radix keys in shared
-//                    memory -> exact k-th smallest by MSB-first bisection of the
-//                    fp32 bit pattern (30 count rounds, one __syncthreads each).
-//                    Reads 12 B/px.
-//   K2 ohem_counts   all SMs: selected mask M (1 B/px) + the 17 integer
-//                    normalisers (n_seg_pos, sum Wp[8], sum Wn[8]) which depend
-//                    only on labels and M.  Reads 44 B/px (12 of them L2 hits).
+// Pipeline (four launches on one stream, no host sync):
+//   K0 score_keys    all SMs: pixel softmax score -> 32-bit radix key per pixel
+//                    (4 B/px, stays in L2) + per-image n_pos / n_neg.  Reads 12 B/px.
+//   K1 ohem_select   one CTA per image: keys into REGISTERS, exact k-th smallest by
+//                    MSB-first bisection of the fp32 bit pattern (30 count rounds,
+//                    one __syncthreads each, no atomics).
+//   K2 ohem_counts   all SMs: selected mask M (1 B/px) + the 17 integer normalisers
+//                    (n_seg_pos, sum Wp[8], sum Wn[8]), which depend only on labels
+//                    and M.  Reads 37 B/px.
 //   K3 loss_main     all SMs, the HBM-bound pass: reads 108 B/px once, writes the
 //                    72 B/px of gradients once (normalisers are already known),
 //                    accumulates the 17 loss sums, last CTA finalises the scalars
@@ -37,18 +38,18 @@ struct LossHeader {  // 128 B, zeroed by cudaMemsetAsync at the start of every c
 };
 static_assert(sizeof(LossHeader) == 128, "header size");
 
-struct ImageInfo {  // per image, written by K1
-  float thr;
+struct ImageInfo {  // per image; n_pos / n_neg accumulate in K0 (zeroed with the header), rest from K1
   int n_pos;
   int n_neg;
-  int k;
+  unsigned thr_key;  // bit pattern of the threshold score
+  int valid;         // 0: select no negatives
 };
 
 constexpr int kMainThreads = 256;
-constexpr int kMainMaxCTAs = kNumSMs * 8;
+constexpr int kMainMaxCTAs = kNumSMs * 4;
 constexpr int kPartialFloats = 20;                 // 17 used
 constexpr int kSelectThreads = 1024;
-constexpr size_t kSmemKeysMaxBytes = 200 * 1024;   // keys of one image stay in shared memory up to 51200 px
+constexpr size_t kSmemKeysMaxBytes = 200 * 1024;   // keys of one image fit in shared memory up to 51200 px
 
 struct LossWsLayout {
   size_t header, info, partials, mask, keys, total;
@@ -59,137 +60,148 @@ static LossWsLayout loss_ws_layout(int B, long long N) {
   size_t off = 0;
   l.header = off;
   off += sizeof(LossHeader);
-  l.info = off;
+  l.info = off;                                   // contiguous with the header: one memset clears both
   off = align_up(off + sizeof(ImageInfo) * (size_t)B, 256);
   l.partials = off;
   off = align_up(off + sizeof(float) * kPartialFloats * kMainMaxCTAs, 256);
   l.mask = off;
   off = align_up(off + (size_t)B * N, 256);
   l.keys = off;
-  if ((size_t)N * 4 > kSmemKeysMaxBytes) off = align_up(off + (size_t)B * N * 4, 256);
+  off = align_up(off + (size_t)B * N * 4, 256);
   l.total = off;
   return l;
 }
 
 size_t loss_workspace_bytes(int B, int H, int W) { return loss_ws_layout(B, (long long)H * W).total; }
 
-// ------------------------------------------------------------------ K1: per-image OHEM threshold
+// ------------------------------------------------------------------ K0: scores -> keys
 // Key of a pixel: the fp32 bit pattern of its score (scores are >= 0, so the
 // unsigned order of the bits is the numeric order).
 //   KEYS_MODEL     (nets/model.py:175-176)     non-negatives are excluded (key 0xFFFFFFFF)
 //   KEYS_PIXELLINK (nets/pixellink.py:124-125) non-negatives become score 0 (key 0)
 enum { KEYS_MODEL = 0, KEYS_PIXELLINK = 1 };
 constexpr uint32_t kExcluded = 0xFFFFFFFFu;
+constexpr int kKeysThreads = 256;
 
 template <int KEYMODE, bool FROM_SCORES>
-__global__ void __launch_bounds__(kSelectThreads, 1)
-ohem_select_kernel(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
-                   const float* __restrict__ scores, const uint8_t* __restrict__ pos_mask,
-                   const uint8_t* __restrict__ neg_mask, const int* __restrict__ n_pos_override, int N, int ratio,
-                   uint32_t* __restrict__ keys_global, ImageInfo* __restrict__ info, float* __restrict__ thr_out) {
-  extern __shared__ __align__(16) uint32_t skeys[];
-  __shared__ int s_cnt[32];
+__global__ void __launch_bounds__(kKeysThreads)
+score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
+                  const float* __restrict__ scores, const uint8_t* __restrict__ pos_mask,
+                  const uint8_t* __restrict__ neg_mask, int N, uint32_t* __restrict__ keys,
+                  ImageInfo* __restrict__ info) {
   __shared__ int s_np, s_nn;
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  uint32_t* keys = keys_global ? keys_global + (size_t)b * N : skeys;
-
-  if (tid < 32) s_cnt[tid] = 0;
   if (tid == 0) s_np = 0, s_nn = 0;
   __syncthreads();
-
-  // ---- pass 1: scores -> keys, count positives / negatives
-  int npos = 0, nneg = 0;
   const size_t base = (size_t)b * N;
-  constexpr int U = 4;
-  for (int i0 = tid; i0 < N; i0 += kSelectThreads * U) {
-    float sc[U];
-    bool isp[U], isn[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kSelectThreads;
-      sc[u] = 0.f, isp[u] = false, isn[u] = false;
-      if (i < N) {
-        if (FROM_SCORES) {
-          sc[u] = scores[base + i];
-          isp[u] = pos_mask[base + i] != 0;
-          isn[u] = neg_mask[base + i] != 0;
-        } else {
-          const float2 x = __ldg(reinterpret_cast<const float2*>(pix_logits) + base + i);
-          const float l = __ldg(pix_lab + base + i);
-          sc[u] = neg_class_score(x.x, x.y);
-          if (KEYMODE == KEYS_MODEL) {  // int32 cast truncates (model.py:213), ==1 / ==0 (:199-202)
-            const int li = (int)l;
-            isp[u] = li == 1, isn[u] = li == 0;
-          } else {                      // pixellink.py:98-99: pos = labels > 0, neg = !pos
-            isp[u] = l > 0.f, isn[u] = !isp[u];
-          }
-        }
+  int npos = 0, nneg = 0;
+  for (int i = blockIdx.x * kKeysThreads + tid; i < N; i += gridDim.x * kKeysThreads) {
+    float sc;
+    bool isp, isn;
+    if (FROM_SCORES) {
+      sc = scores[base + i];
+      isp = pos_mask[base + i] != 0, isn = neg_mask[base + i] != 0;
+    } else {
+      const float2 x = __ldg(reinterpret_cast<const float2*>(pix_logits) + base + i);
+      const float l = __ldg(pix_lab + base + i);
+      sc = neg_class_score(x.x, x.y);
+      if (KEYMODE == KEYS_MODEL) {  // int32 cast truncates (model.py:213), ==1 / ==0 (:199-202)
+        const int li = (int)l;
+        isp = li == 1, isn = li == 0;
+      } else {                      // pixellink.py:98-99: pos = labels > 0, neg = !pos
+        isp = l > 0.f, isn = !isp;
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kSelectThreads;
-      if (i < N) {
-        npos += isp[u], nneg += isn[u];
-        uint32_t key = __float_as_uint(sc[u]);
-        if (!isn[u]) key = (KEYMODE == KEYS_MODEL) ? kExcluded : 0u;
-        keys[i] = key;
-      }
-    }
+    npos += isp, nneg += isn;
+    uint32_t key = __float_as_uint(sc);
+    if (!isn) key = (KEYMODE == KEYS_MODEL) ? kExcluded : 0u;
+    keys[base + i] = key;
   }
   npos = __reduce_add_sync(0xffffffffu, npos);
   nneg = __reduce_add_sync(0xffffffffu, nneg);
-  if (lane == 0) atomicAdd(&s_np, npos), atomicAdd(&s_nn, nneg);
+  if ((tid & 31) == 0) {
+    if (npos) atomicAdd(&s_np, npos);
+    if (nneg) atomicAdd(&s_nn, nneg);
+  }
   __syncthreads();
-  npos = s_np, nneg = s_nn;
-  if (n_pos_override) npos = n_pos_override[b];  // OHNM_single_image(scores, n_pos, neg_mask): n_pos is an argument
+  if (tid == 0) {
+    if (s_np) atomicAdd(&info[b].n_pos, s_np);
+    if (s_nn) atomicAdd(&info[b].n_neg, s_nn);
+  }
+}
 
+// ------------------------------------------------------------------ K1: per-image OHEM threshold
+// Exact k-th smallest key, built MSB first: bit b of the answer is 1 iff fewer than k
+// keys are <= (prefix | all lower bits set).  Keys of real scores are <= bits(1.0f) =
+// 0x3F800000 < 2^30, so 30 rounds; excluded keys (0xFFFFFFFF) never count.
+// KPT > 0: the image's keys live in registers (KPT per thread); KPT == 0: they are read
+// from `keys` (shared memory copy if it fits, else global/L2) every round.
+template <int KPT>
+__global__ void __launch_bounds__(kSelectThreads, 1)
+ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int* __restrict__ n_pos_override, int N, int ratio,
+                   int keymode, int use_smem, ImageInfo* __restrict__ info, float* __restrict__ thr_out) {
+  extern __shared__ __align__(16) uint32_t skeys[];
+  __shared__ int s_w[2][32];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t* gkeys = keys_all + (size_t)b * N;
+
+  int npos = info[b].n_pos;
+  const int nneg = info[b].n_neg;
+  if (n_pos_override) npos = n_pos_override[b];  // OHNM_single_image(scores, n_pos, neg_mask): n_pos is an argument
   // ---- k (model.py:170-173 / pixellink.py:116-120)
-  long long kk = (long long)npos * ratio;
-  const int cap = (KEYMODE == KEYS_MODEL) ? nneg : max(nneg, 1);
-  int k = (int)(kk < (long long)cap ? kk : (long long)cap);
+  const long long kk = (long long)npos * ratio;
+  const int cap = (keymode == KEYS_MODEL) ? nneg : max(nneg, 1);
+  const int k = (int)(kk < (long long)cap ? kk : (long long)cap);
   const bool none = (npos <= 0) || (k <= 0);  // n_pos == 0 -> no_pos(); k == 0 -> "select none" 
 
-  float thr = __int_as_float(0x7fc00000);  // NaN: `score <= NaN` is false for every pixel
+  uint32_t ans = 0;
   if (!none) {
-    // ---- exact k-th smallest key: build it MSB first.  Keys of real scores are
-    // <= bits(1.0f) = 0x3F800000 < 2^30; excluded keys never count.
-    uint32_t ans = 0;
-    const bool vec = ((N & 3) == 0);
+    uint32_t rk[KPT > 0 ? KPT : 1];
+    const uint32_t* keys = gkeys;
+    if (KPT > 0) {
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const int i = tid + j * kSelectThreads;
+        rk[j] = i < N ? __ldg(gkeys + i) : kExcluded;
+      }
+    } else if (use_smem) {
+      for (int i = tid; i < N; i += kSelectThreads) skeys[i] = __ldg(gkeys + i);
+      keys = skeys;
+      __syncthreads();
+    }
     for (int bit = 29; bit >= 0; --bit) {
       const uint32_t t = ans | ((1u << bit) - 1u);
       int c = 0;
-      if (vec) {
-        const uint4* k4 = reinterpret_cast<const uint4*>(keys);
-        const int n4 = N >> 2;
-#pragma unroll 4
-        for (int i = tid; i < n4; i += kSelectThreads) {
-          const uint4 v = k4[i];
-          c += (v.x <= t) + (v.y <= t) + (v.z <= t) + (v.w <= t);
-        }
+      if (KPT > 0) {
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) c += (rk[j] <= t);
       } else {
         for (int i = tid; i < N; i += kSelectThreads) c += (keys[i] <= t);
       }
       c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0 && c) atomicAdd(&s_cnt[bit], c);
+      int* sw = s_w[bit & 1];  // double-buffered: one barrier per round
+      if (lane == 0) sw[warp] = c;
       __syncthreads();
-      if (s_cnt[bit] < k) ans |= (1u << bit);
+      const int total = __reduce_add_sync(0xffffffffu, sw[lane]);
+      if (total < k) ans |= (1u << bit);
     }
-    thr = __uint_as_float(ans);
   }
   if (tid == 0) {
-    if (info) info[b] = ImageInfo{thr, npos, nneg, none ? 0 : k};
-    if (thr_out) thr_out[b] = thr;
+    info[b].thr_key = ans;
+    info[b].valid = none ? 0 : 1;
+    // NaN when nothing is selected: `score <= NaN` is false for every pixel
+    if (thr_out) thr_out[b] = none ? __int_as_float(0x7fc00000) : __uint_as_float(ans);
   }
 }
 
 // ------------------------------------------------------------------ K2: mask + integer normalisers
 template <int VARIANT>
 __global__ void __launch_bounds__(256)
-ohem_counts_kernel(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
-                   const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N, long long total_px,
+ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ pix_lab,
+                   const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N, int total_px,
                    uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr) {
   __shared__ int s_c[18];
   const int tid = threadIdx.x;
@@ -199,19 +211,18 @@ ohem_counts_kernel(const float* __restrict__ pix_logits, const float* __restrict
 #pragma unroll
   for (int d = 0; d < 8; ++d) cP[d] = 0, cN[d] = 0;
 
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long px = (long long)blockIdx.x * blockDim.x + tid; px < total_px; px += stride) {
-    const float4 la = __ldg(reinterpret_cast<const float4*>(link_lab) + px * 2);
-    const float4 lb = __ldg(reinterpret_cast<const float4*>(link_lab) + px * 2 + 1);
+  const int stride = gridDim.x * blockDim.x;
+  for (int px = blockIdx.x * blockDim.x + tid; px < total_px; px += stride) {
+    const float4 la = __ldg(reinterpret_cast<const float4*>(link_lab) + (size_t)px * 2);
+    const float4 lb = __ldg(reinterpret_cast<const float4*>(link_lab) + (size_t)px * 2 + 1);
     const float l = __ldg(pix_lab + px);
     bool pos, neg;
     if (VARIANT == PLH_VARIANT_PIXELLINK) pos = l > 0.f, neg = !pos;
     else { const int li = (int)l; pos = li == 1, neg = li == 0; }
     bool M = pos;
     if (VARIANT != PLH_VARIANT_POS_ONLY && neg) {
-      const float thr = info[px / N].thr;
-      const float2 x = __ldg(reinterpret_cast<const float2*>(pix_logits) + px);
-      M = neg_class_score(x.x, x.y) <= thr;  // model.py:178 ties at the threshold are all selected
+      const ImageInfo ii = info[px / N];
+      M = ii.valid && (__ldg(keys + px) <= ii.thr_key);  // model.py:178 ties at the threshold are all selected
     }
     mask[px] = M ? 1 : 0;
     nsel += M;
@@ -442,12 +453,8 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
 
   // ---- last CTA: deterministic final reduction + scalars
   __threadfence();
-  if (tid < 17) {
-    double s = 0.0;
-    for (unsigned c = 0; c < gridDim.x; ++c) s += (double)__ldcg(a.partials + (size_t)c * kPartialFloats + tid);
-    s_fin[tid] = s;
-  }
-  __syncthreads();
+  __shared__ double s_tmp[(kMainThreads / 17) * 17];
+  block_final_reduce<17, kMainThreads>(a.partials, kPartialFloats, gridDim.x, s_fin, s_tmp);
   if (tid == 0) {
     float* st = a.stats;
     const float nsp = (float)hdr->n_seg_pos;
@@ -521,13 +528,13 @@ float prob_to_logit_threshold(float t) {
   // largest d with softmax1(d) <= t  (then score > t  <=>  d > d*)
   if (!(t > 0.f)) return -INFINITY;  // every score > t unless score == 0; keep simple: all pass
   if (t >= 1.f) return INFINITY;
-  int32_t lo = ordered_bits(-200.f), hi = ordered_bits(200.f);  // softmax1(lo) = 0 <= t, softmax1(hi) = 1 > t
+  long long lo = ordered_bits(-200.f), hi = ordered_bits(200.f);  // softmax1(lo) = 0 <= t, softmax1(hi) = 1 > t
   while (hi - lo > 1) {
-    const int32_t mid = lo + (hi - lo) / 2;
-    if (softmax1_from_diff(from_ordered_bits(mid)) <= t) lo = mid;
+    const long long mid = lo + (hi - lo) / 2;
+    if (softmax1_from_diff(from_ordered_bits((int32_t)mid)) <= t) lo = mid;
     else hi = mid;
   }
-  return from_ordered_bits(lo);
+  return from_ordered_bits((int32_t)lo);
 }
 
 template <int VARIANT, int TERM>
@@ -538,20 +545,37 @@ static void launch_main(bool grad, bool flags, int grid, cudaStream_t s, const M
   else loss_main_kernel<VARIANT, TERM, false, false><<<grid, kMainThreads, 0, s>>>(a, B, N);
 }
 
+// K0 + K1
 template <int KEYMODE, bool FROM_SCORES>
-static int launch_select(const float* pix_logits, const float* pix_lab, const float* scores, const uint8_t* pos,
-                         const uint8_t* neg, const int* n_pos_override, int B, int N, int ratio,
-                         uint32_t* keys_global, ImageInfo* info, float* thr_out, cudaStream_t s) {
-  auto kern = ohem_select_kernel<KEYMODE, FROM_SCORES>;
-  size_t smem = keys_global ? 0 : (size_t)N * 4;
-  static bool attr_set = false;  // idempotent; benign if raced
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemKeysMaxBytes);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+static int launch_keys_and_select(const float* pix_logits, const float* pix_lab, const float* scores,
+                                  const uint8_t* pos, const uint8_t* neg, const int* n_pos_override, int B, int N,
+                                  int ratio, uint32_t* keys, ImageInfo* info, float* thr_out, cudaStream_t s) {
+  {
+    const int per_image = std::max(1, std::min((N + kKeysThreads - 1) / kKeysThreads, (kNumSMs * 8 + B - 1) / B));
+    score_keys_kernel<KEYMODE, FROM_SCORES><<<dim3(per_image, B), kKeysThreads, 0, s>>>(pix_logits, pix_lab, scores,
+                                                                                        pos, neg, N, keys, info);
+    const int rc = launch_status();
+    if (rc) return rc;
   }
-  kern<<<B, kSelectThreads, smem, s>>>(pix_logits, pix_lab, scores, pos, neg, n_pos_override, N, ratio, keys_global,
-                                       info, thr_out);
+  if (N <= kSelectThreads * 4) {
+    ohem_select_kernel<4><<<B, kSelectThreads, 0, s>>>(keys, n_pos_override, N, ratio, KEYMODE, 0, info, thr_out);
+  } else if (N <= kSelectThreads * 16) {
+    ohem_select_kernel<16><<<B, kSelectThreads, 0, s>>>(keys, n_pos_override, N, ratio, KEYMODE, 0, info, thr_out);
+  } else if (N <= kSelectThreads * 36) {
+    ohem_select_kernel<36><<<B, kSelectThreads, 0, s>>>(keys, n_pos_override, N, ratio, KEYMODE, 0, info, thr_out);
+  } else {
+    const bool use_smem = (size_t)N * 4 <= kSmemKeysMaxBytes;
+    static bool attr_set = false;  // idempotent; benign if raced
+    if (use_smem && !attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(ohem_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kSmemKeysMaxBytes);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    ohem_select_kernel<0><<<B, kSelectThreads, use_smem ? (size_t)N * 4 : 0, s>>>(keys, n_pos_override, N, ratio,
+                                                                                  KEYMODE, use_smem ? 1 : 0, info,
+                                                                                  thr_out);
+  }
   return launch_status();
 }
 
@@ -568,7 +592,7 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   if (!pix_logits || !link_logits || !pix_lab || !link_lab || !p || !stats) return PLH_E_NULL;
   if ((grad_pix == nullptr) != (grad_link == nullptr)) return PLH_E_NULL;
   if (decode_flags && !dp) return PLH_E_NULL;
-  if (B <= 0 || H <= 0 || W <= 0 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || (long long)B * H * W > (1ll << 29)) return PLH_E_SHAPE;
   if (p->variant < 0 || p->variant > 2 || p->term < 0 || p->term > 1 || p->neg_pos_ratio < 0) return PLH_E_PARAM;
   if (!aligned16(pix_logits) || !aligned16(link_logits) || !aligned16(pix_lab) || !aligned16(link_lab) ||
       !aligned16(stats) || (grad_pix && (!aligned16(grad_pix) || !aligned16(grad_link))) || !aligned16(workspace))
@@ -582,34 +606,33 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   ImageInfo* info = (ImageInfo*)(ws + l.info);
   float* partials = (float*)(ws + l.partials);
   uint8_t* mask = ohem_mask ? ohem_mask : (uint8_t*)(ws + l.mask);
-  uint32_t* keys_global = ((size_t)N * 4 > kSmemKeysMaxBytes) ? (uint32_t*)(ws + l.keys) : nullptr;
-  const long long total_px = (long long)B * N;
+  uint32_t* keys = (uint32_t*)(ws + l.keys);
+  const int total_px = B * N;
 
-  cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(LossHeader), s);
+  cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(LossHeader) + sizeof(ImageInfo) * (size_t)B, s);
   if (e != cudaSuccess) return (int)e;
   int rc;
-  // K1 (not needed for the positives-only variant: there is no mining, vgg16 :265)
+  // K0 + K1 (not needed for the positives-only variant: there is no mining, vgg16 :265)
   if (p->variant == PLH_VARIANT_MODEL)
-    rc = launch_select<KEYS_MODEL, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
-                                          p->neg_pos_ratio, keys_global, info, stats + PLH_ST_THR, s);
+    rc = launch_keys_and_select<KEYS_MODEL, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
+                                                   p->neg_pos_ratio, keys, info, stats + PLH_ST_THR, s);
   else if (p->variant == PLH_VARIANT_PIXELLINK)
-    rc = launch_select<KEYS_PIXELLINK, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
-                                              p->neg_pos_ratio, keys_global, info, stats + PLH_ST_THR, s);
+    rc = launch_keys_and_select<KEYS_PIXELLINK, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
+                                                       p->neg_pos_ratio, keys, info, stats + PLH_ST_THR, s);
   else {
-    // thr[b] = NaN
-    e = cudaMemsetAsync(stats + PLH_ST_THR, 0xff, sizeof(float) * B, s);
+    e = cudaMemsetAsync(stats + PLH_ST_THR, 0xff, sizeof(float) * B, s);  // thr[b] = NaN
     rc = e == cudaSuccess ? PLH_OK : (int)e;
   }
   if (rc) return rc;
   // K2
   {
-    const int grid = (int)std::min<long long>((total_px + 255) / 256, kNumSMs * 8);
+    const int grid = std::min((total_px + 255) / 256, kNumSMs * 4);
     if (p->variant == PLH_VARIANT_MODEL)
-      ohem_counts_kernel<PLH_VARIANT_MODEL><<<grid, 256, 0, s>>>(pix_logits, pix_lab, link_lab, info, N, total_px, mask, hdr);
+      ohem_counts_kernel<PLH_VARIANT_MODEL><<<grid, 256, 0, s>>>(keys, pix_lab, link_lab, info, N, total_px, mask, hdr);
     else if (p->variant == PLH_VARIANT_POS_ONLY)
-      ohem_counts_kernel<PLH_VARIANT_POS_ONLY><<<grid, 256, 0, s>>>(pix_logits, pix_lab, link_lab, info, N, total_px, mask, hdr);
+      ohem_counts_kernel<PLH_VARIANT_POS_ONLY><<<grid, 256, 0, s>>>(keys, pix_lab, link_lab, info, N, total_px, mask, hdr);
     else
-      ohem_counts_kernel<PLH_VARIANT_PIXELLINK><<<grid, 256, 0, s>>>(pix_logits, pix_lab, link_lab, info, N, total_px, mask, hdr);
+      ohem_counts_kernel<PLH_VARIANT_PIXELLINK><<<grid, 256, 0, s>>>(keys, pix_lab, link_lab, info, N, total_px, mask, hdr);
     if ((rc = launch_status())) return rc;
   }
   // K3
@@ -621,7 +644,7 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
     a.total_px = total_px, a.alpha = p->focal_alpha, a.gamma = p->focal_gamma;
     a.tp_logit = dp ? prob_to_logit_threshold(dp->pixel_thresh) : 0.f;
     a.tl_logit = dp ? prob_to_logit_threshold(dp->link_thresh) : 0.f;
-    const long long Q = total_px * 4;
+    const long long Q = (long long)total_px * 4;
     const int grid = (int)std::min<long long>((Q + kMainThreads * 2 - 1) / (kMainThreads * 2), kMainMaxCTAs);
     const bool g = grad_pix != nullptr, f = decode_flags != nullptr;
 #define PLH_DISPATCH(V, T) launch_main<V, T>(g, f, grid, s, a, B, N)
@@ -645,19 +668,21 @@ extern "C" int plh_ohnm_batch(const float* scores, const uint8_t* pos_mask, cons
                               float* selected_mask, float* thr, void* workspace, size_t workspace_bytes,
                               void* stream) {
   if (!scores || !pos_mask || !neg_mask || !selected_mask || !thr) return PLH_E_NULL;
-  if (B <= 0 || N <= 0 || (long long)B * N > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (B <= 0 || N <= 0 || (long long)B * N > (1ll << 29)) return PLH_E_SHAPE;
   if (variant != PLH_VARIANT_MODEL && variant != PLH_VARIANT_PIXELLINK) return PLH_E_PARAM;
-  uint32_t* keys_global = nullptr;
-  if ((size_t)N * 4 > kSmemKeysMaxBytes) {
-    if (!workspace || workspace_bytes < (size_t)B * N * 4 || !aligned16(workspace)) return PLH_E_WORKSPACE;
-    keys_global = (uint32_t*)workspace;
-  }
+  // workspace: ImageInfo[B] | keys[B*N]
+  const size_t info_bytes = align_up(sizeof(ImageInfo) * (size_t)B, 256);
+  if (!workspace || !aligned16(workspace) || workspace_bytes < info_bytes + (size_t)B * N * 4) return PLH_E_WORKSPACE;
+  ImageInfo* info = (ImageInfo*)workspace;
+  uint32_t* keys = (uint32_t*)((char*)workspace + info_bytes);
   cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(ImageInfo) * (size_t)B, s);
+  if (e != cudaSuccess) return (int)e;
   int rc = variant == PLH_VARIANT_MODEL
-               ? launch_select<KEYS_MODEL, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B, N,
-                                                 neg_pos_ratio, keys_global, nullptr, thr, s)
-               : launch_select<KEYS_PIXELLINK, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B, N,
-                                                     neg_pos_ratio, keys_global, nullptr, thr, s);
+               ? launch_keys_and_select<KEYS_MODEL, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B, N,
+                                                          neg_pos_ratio, keys, info, thr, s)
+               : launch_keys_and_select<KEYS_PIXELLINK, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B,
+                                                              N, neg_pos_ratio, keys, info, thr, s);
   if (rc) return rc;
   const long long total = (long long)B * N;
   const int grid = (int)std::min<long long>((total + 255) / 256, kNumSMs * 8);

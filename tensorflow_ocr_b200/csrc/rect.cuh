@@ -118,27 +118,57 @@ __device__ inline int sklansky(const unsigned long long* keys, int start, int en
   return --stacksize;
 }
 
-// Runs on ONE thread after the keys are sorted.  total = number of real points.
-// out_box: 8 ints (x0,y0..x3,y3), out_rect: 5 floats or nullptr.
+// Called by the WHOLE CTA (>= 128 threads) after the keys are sorted.  total = number of
+// real points.  The four Sklansky scans run concurrently on four warps; the short
+// sequential tail (assembly, calipers over the hull) runs on thread 0.
+// out_box: 8 ints (x0,y0..x3,y3), out_rect: 5 floats or nullptr — written by thread 0 only.
 __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npad, int* out_box, float* out_rect) {
+  __shared__ int s_ind[2];     // miny_ind, maxy_ind
+  __shared__ int s_count[4];   // tl, tr, bl, br stack sizes
   const unsigned long long* keys = S.keys;
   int* hullbuf = S.hullbuf;
-  int nout = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- cv::convexHull(points, clockwise=false, returnPoints=true)
-  int miny_ind = 0, maxy_ind = 0;
-  for (int i = 1; i < total; ++i) {
-    const int y = key_y(keys[i]);
-    if (key_y(keys[miny_ind]) > y) miny_ind = i;
-    if (key_y(keys[maxy_ind]) < y) maxy_ind = i;
+  // first sorted position with the minimum y / with the maximum y (strict comparisons in OpenCV's loop)
+  if (warp == 0) {
+    int miny = 0x7fffffff, mini = 0x7fffffff, maxy = -0x7fffffff, maxi = 0x7fffffff;
+    for (int i = lane; i < total; i += 32) {
+      const int y = key_y(keys[i]);
+      if (y < miny) miny = y, mini = i;
+      if (y > maxy) maxy = y, maxi = i;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int oy = __shfl_xor_sync(0xffffffffu, miny, o), oi = __shfl_xor_sync(0xffffffffu, mini, o);
+      if (oy < miny || (oy == miny && oi < mini)) miny = oy, mini = oi;
+      const int py = __shfl_xor_sync(0xffffffffu, maxy, o), pi = __shfl_xor_sync(0xffffffffu, maxi, o);
+      if (py > maxy || (py == maxy && pi < maxi)) maxy = py, maxi = pi;
+    }
+    if (lane == 0) s_ind[0] = mini, s_ind[1] = maxi;
   }
-  if (key_x(keys[0]) == key_x(keys[total - 1]) && key_y(keys[0]) == key_y(keys[total - 1])) {
+  __syncthreads();
+  const int miny_ind = s_ind[0], maxy_ind = s_ind[1];
+  const bool single = key_x(keys[0]) == key_x(keys[total - 1]) && key_y(keys[0]) == key_y(keys[total - 1]);
+  const int SS = npad + 4;  // stack stride: one region per scan
+  if (!single && lane == 0 && warp < 4) {
+    int* st = S.stack + warp * SS;
+    int c;
+    if (warp == 0) c = sklansky(keys, 0, maxy_ind, st, -1, 1);               // tl
+    else if (warp == 1) c = sklansky(keys, total - 1, maxy_ind, st, -1, -1);  // tr
+    else if (warp == 2) c = sklansky(keys, 0, miny_ind, st, 1, -1);           // bl
+    else c = sklansky(keys, total - 1, miny_ind, st, 1, 1);                   // br
+    s_count[warp] = c;
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  int nout = 0;
+  if (single) {
     hullbuf[nout++] = 0;  // sorted position; converted below
   } else {
-    int* stack = S.stack;
-    int* tl_stack = stack;
-    int tl_count = sklansky(keys, 0, maxy_ind, tl_stack, -1, 1);
-    int* tr_stack = stack + tl_count;
-    int tr_count = sklansky(keys, total - 1, maxy_ind, tr_stack, -1, -1);
+    int* tl_stack = S.stack;
+    int tl_count = s_count[0];
+    int* tr_stack = S.stack + SS;
+    int tr_count = s_count[1];
     {  // !clockwise: swap
       int* t = tl_stack; tl_stack = tr_stack; tr_stack = t;
       int c = tl_count; tl_count = tr_count; tr_count = c;
@@ -146,13 +176,10 @@ __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npa
     for (int i = 0; i < tl_count - 1; ++i) hullbuf[nout++] = tl_stack[i];
     for (int i = tr_count - 1; i > 0; --i) hullbuf[nout++] = tr_stack[i];
     const int stop_idx = tr_count > 2 ? tr_stack[1] : (tl_count > 2 ? tl_stack[tl_count - 2] : -1);
-    // lower half reuses a second stack area (the upper stacks are no longer needed,
-    // but stop_idx was already captured)
-    int* stack2 = S.stack + (npad + 4) * 2;
-    int* bl_stack = stack2;
-    int bl_count = sklansky(keys, 0, miny_ind, bl_stack, 1, -1);
-    int* br_stack = stack2 + bl_count;
-    int br_count = sklansky(keys, total - 1, miny_ind, br_stack, 1, 1);
+    int* bl_stack = S.stack + 2 * SS;
+    int bl_count = s_count[2];
+    int* br_stack = S.stack + 3 * SS;
+    int br_count = s_count[3];
     if (stop_idx >= 0) {
       const int check_idx = bl_count > 2 ? bl_stack[1] : (bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1);
       if (check_idx == stop_idx ||
@@ -181,7 +208,7 @@ __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npa
         const int i0 = ascending ? min_idx : max_idx;
         int j = i0;
         if (i0 > 0) {
-          int* tmp = S.stack;  // free again
+          int* tmp = S.stack;  // the scan stacks are dead now
           int i;
           for (i = 0; i < nout; ++i) {
             const int curr_idx = IDX(j);

@@ -168,7 +168,7 @@ def ohnm_batch_raw(scores, pos_mask, neg_mask, variant=_lib.VARIANT_MODEL, ratio
     _require_gpu(dev)
     sel = torch.empty((B, N), dtype=torch.float32, device=dev)
     thr = torch.empty((B,), dtype=torch.float32, device=dev)
-    ws = torch.empty(max(B * N * 4, 16), dtype=torch.uint8, device=dev) if N * 4 > 200 * 1024 else None
+    ws = torch.empty(((B * 16 + 255) // 256) * 256 + B * N * 4, dtype=torch.uint8, device=dev)  # ImageInfo[B] | keys
     with torch.cuda.device(dev):
         rc = lib.plh_ohnm_batch(_p(scores), _p(pos_mask), _p(neg_mask), _p(n_pos), B, N, variant, ratio, _p(sel),
                                 _p(thr), _p(ws), 0 if ws is None else ws.numel(), _stream(dev))

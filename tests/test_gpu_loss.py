@@ -33,7 +33,8 @@ def _compare(out, ref, B, check_mask=True):
         thr = st[_lib.ST_THR:_lib.ST_THR + B]
         assert np.array_equal(np.isnan(thr), np.isnan(ref["thr"]))
         ok = ~np.isnan(thr)
-        assert np.array_equal(thr[ok], ref["thr"][ok]), "OHEM thresholds differ"
+        # the threshold VALUE may differ in the last bits (CUDA expf vs numpy exp); the mask is what is bit-exact
+        assert np.allclose(thr[ok], ref["thr"][ok], rtol=1e-6, atol=0), "OHEM thresholds differ"
 
 
 def test_model_loss_golden(golden_dir, cuda_dev):
