@@ -220,6 +220,14 @@ PLH_API int plh_east_loss(const float* score_gt, const float* score_pred, const 
 PLH_API size_t plh_workspace_bytes(int op, int B, int H, int W, int K);
 PLH_API int plh_version(void);
 PLH_API const char* plh_strerror(int code);
+/*
+ * Measurement hooks (bench.py roofline): between begin and end, every plh_pixellink_loss call
+ * records CUDA events around its dominant kernel (loss_main) on the launching stream;
+ * end() returns the summed device time and the number of launches.  Not for use under
+ * CUDA-graph capture.  This is the only state the library keeps, and only while enabled.
+ */
+PLH_API int plh_profile_begin(int max_launches);
+PLH_API int plh_profile_end(float* total_ms, int* n_launches);
 /* number of kernels the library has launched in this process (for bench.py's gpu_launches) */
 PLH_API long long plh_launch_count(void);
 

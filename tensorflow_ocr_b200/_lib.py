@@ -51,6 +51,8 @@ SIGNATURES = {
     "plh_version": (_i, []),
     "plh_strerror": (C.c_char_p, [_i]),
     "plh_launch_count": (_ll, []),
+    "plh_profile_begin": (_i, [_i]),
+    "plh_profile_end": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
 
 _lib = None

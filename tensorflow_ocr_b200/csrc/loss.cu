@@ -27,6 +27,14 @@ namespace plh {
 
 std::atomic<long long> g_launch_count{0};
 
+// Optional instrumentation for bench.py's roofline: CUDA events around the dominant
+// kernel (K3 loss_main) on the launching stream.  Off unless plh_profile_begin() was
+// called; not used under CUDA-graph capture.
+constexpr int kProfMax = 8192;
+static cudaEvent_t g_prof_ev[2 * kProfMax];
+static int g_prof_created = 0;
+static int g_prof_n = -1;  // -1: disabled
+
 // ------------------------------------------------------------------ workspace layout
 struct LossHeader {  // 128 B, zeroed by cudaMemsetAsync at the start of every call
   int n_seg_pos;
@@ -647,6 +655,8 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
     const long long Q = (long long)total_px * 4;
     const int grid = (int)std::min<long long>((Q + kMainThreads * 2 - 1) / (kMainThreads * 2), kMainMaxCTAs);
     const bool g = grad_pix != nullptr, f = decode_flags != nullptr;
+    const bool prof = g_prof_n >= 0 && g_prof_n < g_prof_created / 2;
+    if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], s);
 #define PLH_DISPATCH(V, T) launch_main<V, T>(g, f, grid, s, a, B, N)
     if (p->term == PLH_TERM_CE) {
       if (p->variant == PLH_VARIANT_MODEL) PLH_DISPATCH(PLH_VARIANT_MODEL, PLH_TERM_CE);
@@ -659,7 +669,38 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
     }
 #undef PLH_DISPATCH
     if ((rc = launch_status())) return rc;
+    if (prof) {
+      cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], s);
+      ++g_prof_n;
+    }
   }
+  return PLH_OK;
+}
+
+extern "C" int plh_profile_begin(int max_launches) {
+  if (max_launches <= 0 || max_launches > kProfMax) return PLH_E_PARAM;
+  for (; g_prof_created < 2 * max_launches; ++g_prof_created) {
+    cudaError_t e = cudaEventCreate(&g_prof_ev[g_prof_created]);
+    if (e != cudaSuccess) return (int)e;
+  }
+  g_prof_n = 0;
+  return PLH_OK;
+}
+
+extern "C" int plh_profile_end(float* total_ms, int* n_launches) {
+  if (!total_ms || !n_launches) return PLH_E_NULL;
+  if (g_prof_n < 0) return PLH_E_PARAM;
+  double tot = 0.0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    cudaError_t e = cudaEventSynchronize(g_prof_ev[2 * i + 1]);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]);
+    if (e != cudaSuccess) { g_prof_n = -1; return (int)e; }
+    tot += ms;
+  }
+  *total_ms = (float)tot;
+  *n_launches = g_prof_n;
+  g_prof_n = -1;
   return PLH_OK;
 }
 

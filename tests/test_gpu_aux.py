@@ -1,0 +1,90 @@
+"""Parity of the dice head, EAST loss and restore_rectangle kernels (through the C ABI)."""
+import numpy as np
+import pytest
+
+from util import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dice_coefficient(golden_dir, cuda_dev):
+    import torch
+    from tensorflow_ocr_b200.nets import model
+    g = np.load(golden_dir + "/dice_coefficient.npz")
+    assert rel_err(model.dice_coefficient(g["t"], g["p"], g["m"]), g["loss"]) <= TOL
+    p = torch.tensor(g["p"], device=cuda_dev, requires_grad=True)
+    l = model.dice_coefficient(torch.tensor(g["t"], device=cuda_dev), p, torch.tensor(g["m"], device=cuda_dev))
+    l.backward()
+    assert rel_err(l.item(), g["loss"]) <= TOL
+    assert rel_err(p.grad.cpu().numpy(), g["grad"]) <= TOL
+
+
+def test_dice_head_golden_and_oracle(golden_dir, cuda_dev):
+    import torch
+    from oracle import pixellink_loss as O
+    from tensorflow_ocr_b200.nets import model_vgg_16
+    g = np.load(golden_dir + "/vgg16_dice_loss.npz")
+    pp = torch.tensor(g["pix_prob"], device=cuda_dev, requires_grad=True)
+    lp = torch.tensor(g["link_prob"], device=cuda_dev, requires_grad=True)
+    l = model_vgg_16.loss(torch.tensor(g["pix_lab"], device=cuda_dev), pp, torch.tensor(g["link_lab"], device=cuda_dev),
+                          lp, torch.tensor(g["training_mask"], device=cuda_dev))
+    l.backward()
+    assert rel_err(l.item(), g["loss"]) <= TOL
+    assert rel_err(pp.grad.cpu().numpy(), g["grad_pixel"]) <= TOL
+    assert rel_err(lp.grad.cpu().numpy(), g["grad_link"]) <= TOL
+    # BASELINE config 5 map size, against the oracle
+    rng = np.random.default_rng(1)
+    B, H, W = 4, 192, 192
+    t_p = (rng.uniform(size=(B, H, W, 1)) > 0.8).astype(np.float32)
+    t_l = (rng.uniform(size=(B, H, W, 8)) > 0.7).astype(np.float32)
+    p_p = rng.uniform(size=(B, H, W, 1)).astype(np.float32)
+    p_l = rng.uniform(size=(B, H, W, 8)).astype(np.float32)
+    m = (rng.uniform(size=(B, H, W, 1)) > 0.1).astype(np.float32)
+    ref = O.loss_vgg16_dice(t_p, p_p, t_l, p_l, m)
+    assert rel_err(model_vgg_16.loss(t_p, p_p, t_l, p_l, m), ref["loss"]) <= TOL
+
+
+def test_cal_link_loss(cuda_dev):
+    from oracle import pixellink_loss as O
+    from tensorflow_ocr_b200 import synth
+    from tensorflow_ocr_b200.nets import model_vgg_16
+    inp = synth.make_batch(41, 2, 24, 24, "G")
+    W = (inp["pix_lab"].reshape(-1) == 1).astype(np.float32)
+    gt, pred = inp["link_lab"][..., 3:4], inp["link_logits"][..., 6:8]
+    assert rel_err(model_vgg_16.cal_link_loss(gt, pred, W), O.cal_link_loss(gt, pred, W)) <= TOL
+
+
+def test_east_loss_vs_oracle(cuda_dev):
+    """E2 — parity unpinned (not in the reference; restated from upstream EAST)."""
+    import torch
+    from oracle import east as E
+    from tensorflow_ocr_b200 import head, synth
+    inp = synth.make_east_batch(4, 3, 64, 64)
+    ref = E.east_loss(inp["score_gt"], inp["score_pred"], inp["geo_gt"], inp["geo_pred"], inp["training_mask"])
+    t = {k: torch.as_tensor(v).to(cuda_dev) for k, v in inp.items()}
+    outv, gs, gg = head.east_loss_raw(t["score_gt"], t["score_pred"], t["geo_gt"], t["geo_pred"], t["training_mask"])
+    torch.cuda.synchronize()
+    assert rel_err(outv[0].item(), ref["loss"]) <= TOL
+    assert rel_err(gs.cpu().numpy(), ref["grad_score"]) <= TOL
+    assert rel_err(gg.cpu().numpy(), ref["grad_geo"]) <= 5e-5   # cosf/sinf/logf vs numpy: a few ulp on tiny terms
+
+
+def test_restore_rectangle(golden_dir, cuda_dev):
+    from oracle import east as E
+    from tensorflow_ocr_b200.datasets import icdar
+    g = np.load(golden_dir + "/restore_rectangle.npz")
+    out = icdar.restore_rectangle(g["origin"], g["geometry"])
+    assert out.dtype == np.float64 and out.shape == g["out"].shape
+    assert np.allclose(out, g["out"], rtol=1e-6, atol=1e-4)     # fp32 cos/sin differ by an ulp between libms
+    out, idx = icdar.restore_rectangle_rbox(g["origin"], g["geometry"], return_index=True)
+    a = g["geometry"][:, 4]
+    expect = np.concatenate([np.nonzero(a >= 0)[0], np.nonzero(a < 0)[0]])
+    assert np.array_equal(idx, expect)                           # stable partition, icdar.py:479
+    assert icdar.restore_rectangle(g["origin"][:0], g["geometry"][:0]).shape == (0, 4, 2)
+    # large ragged N across many scan blocks
+    rng = np.random.default_rng(2)
+    N = 70001
+    origin = rng.uniform(0, 512, (N, 2)).astype(np.float32)
+    geom = np.concatenate([rng.uniform(1, 80, (N, 4)), rng.uniform(-0.7, 0.7, (N, 1))], 1).astype(np.float32)
+    ref = E.restore_rectangle_rbox(origin, geom)
+    assert np.allclose(icdar.restore_rectangle(origin, geom), ref, rtol=1e-6, atol=1e-4)

@@ -1,0 +1,130 @@
+"""CPU: the oracle against the golden vectors produced by executing the reference's own
+source (tests/golden/make_golden.py) — this is what pins the oracle."""
+import numpy as np
+
+from util import TOL, rel_err
+
+
+def test_example_softmax_known_answer(golden_dir):
+    """example.py:5,12 — the only known answer in the reference: softmax([a, a+1])."""
+    from oracle import pixellink_loss as O
+    g = np.load(golden_dir + "/example_softmax.npz")
+    y = O.softmax2(g["x"])
+    assert np.allclose(y, g["y"], rtol=1e-6)
+    assert np.allclose(y[..., 0], 0.26894142, atol=1e-7) and np.allclose(y[..., 1], 0.73105858, atol=1e-7)
+
+
+def test_model_loss_golden(golden_dir):
+    from oracle import pixellink_loss as O
+    g = np.load(golden_dir + "/model_loss_b14.npz")
+    r = O.loss_model(g["pix_lab"], g["pix_logits"], g["link_lab"], g["link_logits"])
+    assert rel_err(r["loss"], g["loss"]) <= TOL
+    assert np.array_equal(r["ohem_mask"], g["ohem_mask"])
+    assert rel_err(r["grad_pixel"], g["grad_pixel"]) <= TOL
+    assert rel_err(r["grad_link"], g["grad_link"]) <= TOL
+
+
+def test_model_loss_golden_nan(golden_dir):
+    from oracle import pixellink_loss as O
+    g = np.load(golden_dir + "/model_loss_b14_nopos.npz")
+    r = O.loss_model(g["pix_lab"], g["pix_logits"], g["link_lab"], g["link_logits"])
+    assert np.isnan(r["loss"]) and np.isnan(g["loss"])
+    assert rel_err(r["grad_pixel"], g["grad_pixel"]) == 0.0
+    assert np.isnan(r["grad_link"]).all() and np.isnan(g["grad_link"]).all()
+
+
+def test_vgg16_goldens(golden_dir):
+    from oracle import pixellink_loss as O
+    g = np.load(golden_dir + "/vgg16_ohem_loss.npz")
+    r = O.ohem_loss_vgg16(g["pix_lab"], g["pix_logits"], g["link_lab"], g["link_logits"])
+    assert rel_err(r["loss"], g["loss"]) <= TOL
+    assert rel_err(r["grad_pixel"], g["grad_pixel"]) <= TOL
+    assert rel_err(r["grad_link"], g["grad_link"]) <= TOL
+    g = np.load(golden_dir + "/vgg16_dice_loss.npz")
+    r = O.loss_vgg16_dice(g["pix_lab"], g["pix_prob"], g["link_lab"], g["link_prob"], g["training_mask"])
+    assert rel_err(r["loss"], g["loss"]) <= TOL
+    assert rel_err(r["grad_pixel"], g["grad_pixel"]) <= TOL
+    assert rel_err(r["grad_link"], g["grad_link"]) <= TOL
+    g = np.load(golden_dir + "/dice_coefficient.npz")
+    l, gr, _, _ = O.dice_coefficient(g["t"], g["p"], g["m"], True)
+    assert rel_err(l, g["loss"]) <= TOL and rel_err(gr, g["grad"]) <= TOL
+
+
+def test_pixellink_build_loss_golden(golden_dir):
+    from oracle import pixellink_loss as O
+    g = np.load(golden_dir + "/pixellink_build_loss.npz")
+    r = O.build_loss_pixellink(g["pix_logits"], g["link_logits"], g["pix_lab"], g["link_lab"])
+    assert rel_err(r["losses"][0], g["losses"][0]) <= TOL
+    assert rel_err(r["losses"][1], g["losses"][1]) <= TOL
+    assert np.array_equal(r["ohem_mask"], g["ohem_mask"])
+    assert rel_err(r["grad_pixel"], g["grad_pixel"]) <= TOL
+    assert rel_err(r["grad_link"], g["grad_link"]) <= TOL
+
+
+def test_pixel_detect_golden(golden_dir):
+    from oracle import decode as D
+    g = np.load(golden_dir + "/pixel_detect.npz")
+    assert np.array_equal(D.pixel_detect(g["score"], g["geo"]), g["res"])
+    assert np.array_equal(D.pixel_detect(g["score"], g["geo"], 0.75, 0.7), g["res_075_07"])
+
+
+def test_restore_rectangle_golden(golden_dir):
+    from oracle import east as E
+    g = np.load(golden_dir + "/restore_rectangle.npz")
+    out = E.restore_rectangle_rbox(g["origin"], g["geometry"])
+    assert out.dtype == np.float64 and np.allclose(out, g["out"], rtol=1e-12, atol=1e-9)
+    m = g["geometry"][:, 4] >= 0
+    assert np.allclose(E.restore_rectangle_rbox(g["origin"][m], g["geometry"][m]), g["out_pos_only"], rtol=1e-12, atol=1e-9)
+    assert tuple(E.restore_rectangle_rbox(g["origin"][:0], g["geometry"][:0]).shape) == tuple(g["out_empty_shape"])
+
+
+def test_order_points_golden(golden_dir):
+    from oracle import decode as D
+    from tensorflow_ocr_b200 import decode as P
+    g = np.load(golden_dir + "/order_points.npz")
+    for b, o, s in zip(g["boxes"], g["ordered"], g["sorted_poly"]):
+        assert np.array_equal(D.order_points(b), o) and np.array_equal(P.order_points(b), o)
+        assert np.array_equal(D.sort_poly(b), s) and np.array_equal(P.sort_poly(b), s)
+
+
+def _loss_fp64(inp, M):
+    """fp64 evaluation of nets/model.py:204-261 with the OHEM mask M held fixed."""
+    def ce(logits, lab):
+        x = logits.astype(np.float64)
+        m = x.max(-1, keepdims=True)
+        lse = np.log(np.exp(x - m).sum(-1)) + m[..., 0]
+        return lse - np.take_along_axis(x, lab[..., None], -1)[..., 0]
+    B = inp["pix_logits"].shape[0]
+    M = M.reshape(B, -1).astype(np.float64)
+    pl = inp["pix_lab"].reshape(B, -1).astype(np.int64)
+    L_pix = (ce(inp["pix_logits"].reshape(B, -1, 2), pl) * M).sum() / (pl == 1).sum()
+    ll = inp["link_lab"].reshape(B, -1, 8).astype(np.int64)
+    lg = inp["link_logits"].reshape(B, -1, 8, 2)
+    total = 0.0
+    for d in range(8):
+        c = ce(lg[:, :, d], ll[:, :, d])
+        wp, wn = (ll[:, :, d] == 1) * M, (ll[:, :, d] == 0) * M
+        total += (c * wp).sum() / wp.sum() + (c * wn).sum() / wn.sum()
+    return total + 2 * L_pix
+
+
+def test_gradients_match_finite_differences():
+    """Analytic gradients of the oracle vs fp64 central differences (mask and counts held
+    fixed, as TF autodiff does: they carry no gradient)."""
+    from oracle import pixellink_loss as O
+    from tensorflow_ocr_b200 import synth
+    inp = synth.make_batch(21, 2, 8, 10, "C")
+    base = O.loss_model(inp["pix_lab"], inp["pix_logits"], inp["link_lab"], inp["link_logits"])
+    assert abs(_loss_fp64(inp, base["ohem_mask"]) - float(base["loss"])) < 1e-5
+    rng = np.random.default_rng(0)
+    for name, key in (("pix_logits", "grad_pixel"), ("link_logits", "grad_link")):
+        for idx in rng.choice(inp[name].size, 24, replace=False):
+            eps = 1e-3
+            vals = []
+            for sgn in (+1, -1):
+                x = {k: v.astype(np.float64) for k, v in inp.items()}
+                x[name].reshape(-1)[idx] += sgn * eps
+                vals.append(_loss_fp64(x, base["ohem_mask"]))
+            fd = (vals[0] - vals[1]) / (2 * eps)
+            an = float(base[key].reshape(-1)[idx])
+            assert abs(fd - an) <= 1e-4 * abs(an) + 1e-7, (name, idx, fd, an)
