@@ -169,7 +169,7 @@ typedef struct plh_decode_params {
  *          then only K are written)
  *  rects   [B,K,5] float optional: cx, cy, w, h, angle of cv2.minAreaRect
  *  comp    [B,K,2] int32 optional: label (min pixel index) and pixel count per box
- * Limits: H <= 2048 rows, W*scale_x < 65536, H*scale_y < 65536.
+ * Limits: H <= 1024 rows, W*scale_x < 32768, H*scale_y < 32768.
  */
 PLH_API int plh_decode(const float* pix_logits, const float* link_logits, int B, int H, int W,
                const plh_decode_params* p, int32_t* labels, int32_t* boxes, int32_t* n_boxes, float* rects,
@@ -184,7 +184,7 @@ PLH_API int plh_decode_from_flags(const uint16_t* flags, int B, int H, int W, co
  * cv2.minAreaRect -> cv2.boxPoints -> np.int0 for explicit point lists
  * (test_pixellink_fast.py:199-200, test.py:190-191), one CTA per list.
  *  pts [total,2] int32 (x,y) in the caller's order; offsets [n_sets+1] int32
- *  boxes [n_sets,8] int32; rects [n_sets,5] float optional.  Each set <= 4096 points.
+ *  boxes [n_sets,8] int32; rects [n_sets,5] float optional.  Each set <= 2048 points.
  */
 PLH_API int plh_min_area_boxes(const int32_t* pts, const int32_t* offsets, int n_sets, int32_t* boxes, float* rects,
                        void* stream);

@@ -57,9 +57,10 @@ __device__ __forceinline__ float neg_class_score(float x0, float x1) {
 }
 
 // Deterministic block-wide sum of per-CTA partial vectors.  Thread t owns value t % NV and
-// CTAs g, g+G, ... (g = t / NV, G = T / NV groups): one fp64 accumulator per thread,
-// independent loads, then a fixed-order sum over the groups.  Result in s_out[NV]
-// (shared, valid after the trailing __syncthreads).  s_tmp holds (T / NV) * NV doubles.
+// CTAs g, g+G, ... (g = t / NV, G = T / NV groups).  Loads are issued in independent batches of
+// 8 (the L2 latency would otherwise serialise into a long single-CTA tail), added in a fixed
+// order into one fp64 accumulator per thread, then summed over the groups in a fixed order.
+// Result in s_out[NV] (shared, valid after the trailing __syncthreads).  s_tmp: (T / NV) * NV doubles.
 template <int NV, int T>
 __device__ __forceinline__ void block_final_reduce(const float* partials, int stride, unsigned ncta, double* s_out,
                                                    double* s_tmp) {
@@ -67,7 +68,16 @@ __device__ __forceinline__ void block_final_reduce(const float* partials, int st
   const int g = threadIdx.x / NV, i = threadIdx.x - g * NV;
   if (g < G) {
     double acc = 0.0;
-    for (unsigned c = g; c < ncta; c += G) acc += (double)__ldcg(partials + (size_t)c * stride + i);
+    for (unsigned c0 = g; c0 < ncta; c0 += G * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const unsigned c = c0 + u * G;
+        v[u] = c < ncta ? __ldcg(partials + (size_t)c * stride + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += (double)v[u];
+    }
     s_tmp[g * NV + i] = acc;
   }
   __syncthreads();

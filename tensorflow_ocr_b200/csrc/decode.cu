@@ -11,8 +11,11 @@
 //                 parent[v] = v / -1, size[v] = 0.       reads 72 B/px, writes 10 B/px
 //                 (or, in the fused path, flags come from the loss kernel and D0'
 //                 only initialises parent/size)
-//   D1 union      lock-free union-find over the reference's edge set, hooking the
-//                 larger root under the smaller (atomicMin) -> root = min pixel index
+//   D1a tile cc   one CTA per 32x16 tile: union-find in SHARED memory over the tile's
+//                 intra-tile edges (flags staged with a 1-pixel halo), hooking the larger
+//                 index under the smaller (atomicMin) -> tile root = min pixel index
+//   D1b cross     only tile-border pixels: lock-free global union of the tile roots
+//                 across tile boundaries (atomic pointer jumping in L2)
 //   D2 flatten    parent[v] = root, component sizes (warp-aggregated atomics),
 //                 border pixels that no edge reaches are dropped (not graph nodes)
 //   D3 roots      roots with size > min_size take a box slot (ascending-label order is
@@ -59,9 +62,10 @@ size_t decode_workspace_bytes(int B, int H, int W, int K) { return decode_ws_lay
 // ------------------------------------------------------------------ D0: flags from logits (+ init)
 __global__ void __launch_bounds__(256)
 decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restrict__ link_logits, long long total_px,
-                    float tp_logit, float tl_logit, uint16_t* __restrict__ flags, int* __restrict__ parent,
-                    int* __restrict__ size) {
+                    float tp_logit, float tl_logit, uint16_t* __restrict__ flags, int* __restrict__ n_boxes, int B) {
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < B; i += blockDim.x) n_boxes[i] = 0;
   const int j = threadIdx.x & 3;
   const long long Q = total_px * 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -83,20 +87,7 @@ decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restric
     if (valid && j == 0) {
       const bool p = (P.y - P.x) > tp_logit;
       flags[px] = (uint16_t)(bits | (p ? kFlagP : 0));
-      parent[px] = p ? (int)px : -1;
-      size[px] = 0;
     }
-  }
-}
-
-// D0': init only (flags already produced by the fused loss kernel)
-__global__ void __launch_bounds__(256)
-decode_init_kernel(const uint16_t* __restrict__ flags, long long total_px, int* __restrict__ parent,
-                   int* __restrict__ size) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < total_px; px += stride) {
-    parent[px] = (flags[px] & kFlagP) ? (int)px : -1;
-    size[px] = 0;
   }
 }
 
@@ -141,22 +132,112 @@ __device__ __forceinline__ void unite(int* parent, int a, int b) {
 // (1 <= x <= W-2, 1 <= y <= H-2) that pass the pixel threshold emit edges, to the
 // neighbour in direction d iff link_d passes AND the neighbour passes the pixel
 // threshold.  Connectivity is taken undirected (weakly-connected components).
-__global__ void __launch_bounds__(256)
-decode_union_kernel(const uint16_t* __restrict__ flags, int H, int W, long long total_px, int* __restrict__ parent) {
-  const int N = H * W;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
-    const unsigned f = flags[g];
-    if (!(f & kFlagP) || !(f & 0xffu)) continue;
-    const int v = (int)(g % N);
-    const int y = v / W, x = v - y * W;
-    if (x < 1 || x > W - 2 || y < 1 || y > H - 2) continue;
+constexpr int kTW = 32, kTH = 16;  // tile: 512 pixels, one thread each
+
+// Each undirected neighbour pair is visited once, from its first pixel in row-major order, through the
+// four "forward" directions; the pair is connected if either endpoint emits the edge:
+//   v -> u via direction d (v interior, link_d[v])   or   u -> v via opp(d) (u interior, link_opp(d)[u]).
+__constant__ int c_fwd[4] = {3, 1, 7, 4};   // right, left_down, down, right_down
+__constant__ int c_opp[4] = {0, 5, 6, 2};   // left,  right_up,  up,   left_up
+
+__device__ __forceinline__ int find_root_s(volatile int* lab, int v) {
+  int p = lab[v];
+  while (p != v) {
+    const int gp = lab[p];
+    if (gp != p) lab[v] = gp;
+    v = p;
+    p = gp;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void unite_s(int* lab, int a, int b) {
+  while (true) {
+    a = find_root_s(lab, a);
+    b = find_root_s(lab, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&lab[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(kTW * kTH)
+decode_tile_cc_kernel(const uint16_t* __restrict__ flags, int H, int W, int* __restrict__ parent,
+                      int* __restrict__ size, int* __restrict__ n_boxes) {
+  __shared__ uint16_t sf[kTH + 2][kTW + 2];
+  __shared__ int slab[kTW * kTH];
+  const int tid = threadIdx.x;
+  const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH, b = blockIdx.z;
+  const size_t base = (size_t)b * H * W;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) n_boxes[b] = 0;
+  for (int i = tid; i < (kTH + 2) * (kTW + 2); i += kTW * kTH) {
+    const int r = i / (kTW + 2), c = i - r * (kTW + 2);
+    const int gy = ty0 - 1 + r, gx = tx0 - 1 + c;
+    sf[r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? flags[base + (size_t)gy * W + gx] : (uint16_t)0;
+  }
+  const int ly = tid / kTW, lx = tid - ly * kTW;
+  const int gy = ty0 + ly, gx = tx0 + lx;
+  const bool inimg = gy < H && gx < W;
+  __syncthreads();
+  const unsigned f = sf[ly + 1][lx + 1];
+  const bool P = inimg && (f & kFlagP);
+  slab[tid] = P ? tid : -1;
+  __syncthreads();
+  if (P) {
+    const bool vin = gx >= 1 && gx <= W - 2 && gy >= 1 && gy <= H - 2;
 #pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      if (f & (1u << d)) {
-        const long long u = g + c_dy[d] * W + c_dx[d];
-        if (flags[u] & kFlagP) unite(parent, (int)g, (int)u);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const int d = c_fwd[k];
+      const int uy = ly + c_dy[d], ux = lx + c_dx[d];
+      if (uy < 0 || uy >= kTH || ux < 0 || ux >= kTW) continue;  // cross-tile: decode_cross_kernel
+      const unsigned fu = sf[uy + 1][ux + 1];
+      if (!(fu & kFlagP)) continue;
+      const int ugx = gx + c_dx[d], ugy = gy + c_dy[d];
+      const bool uin = ugx >= 1 && ugx <= W - 2 && ugy >= 1 && ugy <= H - 2;
+      if ((vin && (f & (1u << d))) || (uin && (fu & (1u << c_opp[k])))) unite_s(slab, tid, uy * kTW + ux);
+    }
+  }
+  __syncthreads();
+  if (inimg) {
+    const size_t g = base + (size_t)gy * W + gx;
+    int root = -1;
+    if (P) {
+      const int r = find_root_s(slab, tid);
+      const int ry = r / kTW, rx = r - ry * kTW;
+      root = (int)(base + (size_t)(ty0 + ry) * W + tx0 + rx);
+    }
+    parent[g] = root;
+    size[g] = 0;
+  }
+}
+
+// Cross-tile pairs: only pixels on the right / bottom / left border of a tile have a forward
+// neighbour in another tile.
+__global__ void __launch_bounds__(256)
+decode_cross_kernel(const uint16_t* __restrict__ flags, int H, int W, int total_px, int* __restrict__ parent) {
+  const int N = H * W;
+  const int stride = gridDim.x * blockDim.x;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
+    const int v = g % N;
+    const int y = v / W, x = v - y * W;
+    const int lx = x % kTW, ly = y % kTH;
+    if (lx != 0 && lx != kTW - 1 && ly != kTH - 1) continue;
+    const unsigned f = flags[g];
+    if (!(f & kFlagP)) continue;
+    const bool vin = x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int d = c_fwd[k];
+      const int ux = x + c_dx[d], uy = y + c_dy[d];
+      if (ux < 0 || ux >= W || uy >= H) continue;
+      if (ux / kTW == x / kTW && uy / kTH == y / kTH) continue;  // intra-tile: done in shared memory
+      const int u = g + c_dy[d] * W + c_dx[d];
+      const unsigned fu = flags[u];
+      if (!(fu & kFlagP)) continue;
+      const bool uin = ux >= 1 && ux <= W - 2 && uy >= 1 && uy <= H - 2;
+      if ((vin && (f & (1u << d))) || (uin && (fu & (1u << c_opp[k])))) unite(parent, g, u);
     }
   }
 }
@@ -210,7 +291,8 @@ decode_flatten_kernel(const uint16_t* __restrict__ flags, int H, int W, long lon
 // kept component (may be >= K: kept in the label map, but no box row) or -1 for a filtered one.
 __global__ void __launch_bounds__(256)
 decode_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int N, int total_px, int min_size, int K,
-                    int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes) {
+                    int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes,
+                    int* __restrict__ rowmin, int* __restrict__ rowmax, int H) {
   const int stride = gridDim.x * blockDim.x;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
     if (parent[g] != g) continue;
@@ -222,6 +304,10 @@ decode_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int 
       if (slot < K) {
         comp_root[(size_t)b * K + slot] = g - b * N;
         comp_size[(size_t)b * K + slot] = sz;
+        // this slot's row-extreme table (only used slots are initialised: no memset of the whole table)
+        int* rmin = rowmin + ((size_t)b * K + slot) * H;
+        int* rmax = rowmax + ((size_t)b * K + slot) * H;
+        for (int y = (g - b * N) / (N / H); y < H; ++y) rmin[y] = 0x7fffffff, rmax[y] = -1;
       }
     } else {
       size[g] = -1;
@@ -362,7 +448,7 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
                          int W, const plh_decode_params* p, int32_t* labels, int32_t* boxes, int32_t* n_boxes,
                          float* rects, int32_t* comp, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   if (!p || !labels || !boxes || !n_boxes) return PLH_E_NULL;
-  if (B <= 0 || H <= 0 || W <= 0 || H > 2048 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || H > 1024 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
   if (p->max_boxes <= 0 || p->min_size < 0 || !(p->scale_x >= 1.0) || !(p->scale_y >= 1.0) ||
       W * p->scale_x >= 32768.0 || H * p->scale_y >= 32768.0)
     return PLH_E_PARAM;
@@ -384,26 +470,22 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   const int grid_px = (int)std::min<long long>((total_px + 255) / 256, kNumSMs * 16);
   if (flags_in) {
     flags = const_cast<uint16_t*>(flags_in);
-    decode_init_kernel<<<grid_px, 256, 0, s>>>(flags, total_px, parent, size);
   } else {
     const int grid = (int)std::min<long long>((total_px * 4 + 255) / 256, kNumSMs * 16);
     decode_flags_kernel<<<grid, 256, 0, s>>>(pix_logits, link_logits, total_px,
                                              prob_to_logit_threshold(p->pixel_thresh),
-                                             prob_to_logit_threshold(p->link_thresh), flags, parent, size);
+                                             prob_to_logit_threshold(p->link_thresh), flags, n_boxes, B);
+    if ((rc = launch_status())) return rc;
   }
+  decode_tile_cc_kernel<<<dim3((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, B), kTW * kTH, 0, s>>>(flags, H, W, parent, size,
+                                                                                                n_boxes);
   if ((rc = launch_status())) return rc;
-  decode_union_kernel<<<grid_px, 256, 0, s>>>(flags, H, W, total_px, parent);
+  decode_cross_kernel<<<grid_px, 256, 0, s>>>(flags, H, W, (int)total_px, parent);
   if ((rc = launch_status())) return rc;
   decode_flatten_kernel<<<grid_px, 256, 0, s>>>(flags, H, W, total_px, parent, size);
   if ((rc = launch_status())) return rc;
-  {
-    cudaError_t e = cudaMemsetAsync(n_boxes, 0, sizeof(int) * (size_t)B, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(rowmin, 0x7f, sizeof(int) * (size_t)B * K * H, s);  // 0x7f7f7f7f = +big
-    if (e == cudaSuccess) e = cudaMemsetAsync(rowmax, 0xff, sizeof(int) * (size_t)B * K * H, s);  // -1
-    if (e != cudaSuccess) return (int)e;
-  }
   decode_roots_kernel<<<grid_px, 256, 0, s>>>(parent, size, N, (int)total_px, p->min_size, K, comp_root, comp_size,
-                                              n_boxes);
+                                              n_boxes, rowmin, rowmax, H);
   if ((rc = launch_status())) return rc;
   decode_labels_kernel<<<grid_px, 256, 0, s>>>(parent, size, H, W, total_px, K, labels, rowmin, rowmax);
   if ((rc = launch_status())) return rc;
@@ -448,7 +530,7 @@ extern "C" int plh_min_area_boxes(const int32_t* pts, const int32_t* offsets, in
                                   void* stream) {
   if (!pts || !offsets || !boxes) return PLH_E_NULL;
   if (n_sets <= 0) return PLH_E_SHAPE;
-  const int npad = 4096;
+  const int npad = 2048;  // max points per set
   const size_t smem = rect_smem_bytes(npad);
   static bool attr_set = false;
   if (!attr_set) {

@@ -41,35 +41,42 @@ struct LossHeader {  // 128 B, zeroed by cudaMemsetAsync at the start of every c
   int cntP[8];
   int cntN[8];
   int n_selected;
-  unsigned ticket;
-  int pad[13];
+  unsigned ticket;    // K3 last-CTA election
+  unsigned ticket2;   // K2 last-CTA election
+  int pad[12];
 };
 static_assert(sizeof(LossHeader) == 128, "header size");
 
-struct ImageInfo {  // per image; n_pos / n_neg accumulate in K0 (zeroed with the header), rest from K1
+struct ImageInfo {  // per image, written by K1
   int n_pos;
   int n_neg;
   unsigned thr_key;  // bit pattern of the threshold score
   int valid;         // 0: select no negatives
 };
+constexpr int kKeysMaxCTAsPerImage = 64;  // K0 writes one (n_pos, n_neg) pair per CTA; K1 sums them (no atomics, no memset)
 
-constexpr int kMainThreads = 256;
-constexpr int kMainMaxCTAs = kNumSMs * 4;
+constexpr int kMainThreads = 512;
+constexpr int kMainMaxCTAs = kNumSMs * 2;
 constexpr int kPartialFloats = 20;                 // 17 used
 constexpr int kSelectThreads = 1024;
 constexpr size_t kSmemKeysMaxBytes = 200 * 1024;   // keys of one image fit in shared memory up to 51200 px
 
 struct LossWsLayout {
-  size_t header, info, partials, mask, keys, total;
+  size_t header, info, counts, cparts, partials, mask, keys, total;
 };
+constexpr int kCountsMaxCTAs = kNumSMs * 4;
 
 static LossWsLayout loss_ws_layout(int B, long long N) {
   LossWsLayout l;
   size_t off = 0;
   l.header = off;
   off += sizeof(LossHeader);
-  l.info = off;                                   // contiguous with the header: one memset clears both
+  l.info = off;
   off = align_up(off + sizeof(ImageInfo) * (size_t)B, 256);
+  l.counts = off;
+  off = align_up(off + sizeof(int2) * (size_t)B * kKeysMaxCTAsPerImage, 256);
+  l.cparts = off;
+  off = align_up(off + sizeof(int) * 18 * kCountsMaxCTAs, 256);
   l.partials = off;
   off = align_up(off + sizeof(float) * kPartialFloats * kMainMaxCTAs, 256);
   l.mask = off;
@@ -85,10 +92,10 @@ size_t loss_workspace_bytes(int B, int H, int W) { return loss_ws_layout(B, (lon
 // ------------------------------------------------------------------ K0: scores -> keys
 // Key of a pixel: the fp32 bit pattern of its score (scores are >= 0, so the
 // unsigned order of the bits is the numeric order).
-//   KEYS_MODEL     (nets/model.py:175-176)     non-negatives are excluded (key 0xFFFFFFFF)
+//   KEYS_MODEL     (nets/model.py:175-176)     non-negatives are excluded (key 0x7FFFFFFF)
 //   KEYS_PIXELLINK (nets/pixellink.py:124-125) non-negatives become score 0 (key 0)
 enum { KEYS_MODEL = 0, KEYS_PIXELLINK = 1 };
-constexpr uint32_t kExcluded = 0xFFFFFFFFu;
+constexpr uint32_t kExcluded = 0x7FFFFFFFu;  // > every real key, and (t - key) stays negative in int32
 constexpr int kKeysThreads = 256;
 
 template <int KEYMODE, bool FROM_SCORES>
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(kKeysThreads)
 score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
                   const float* __restrict__ scores, const uint8_t* __restrict__ pos_mask,
                   const uint8_t* __restrict__ neg_mask, int N, uint32_t* __restrict__ keys,
-                  ImageInfo* __restrict__ info) {
+                  int2* __restrict__ counts) {
   __shared__ int s_np, s_nn;
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -133,22 +140,20 @@ score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict_
     if (nneg) atomicAdd(&s_nn, nneg);
   }
   __syncthreads();
-  if (tid == 0) {
-    if (s_np) atomicAdd(&info[b].n_pos, s_np);
-    if (s_nn) atomicAdd(&info[b].n_neg, s_nn);
-  }
+  if (tid == 0) counts[(size_t)b * gridDim.x + blockIdx.x] = make_int2(s_np, s_nn);
 }
 
 // ------------------------------------------------------------------ K1: per-image OHEM threshold
 // Exact k-th smallest key, built MSB first: bit b of the answer is 1 iff fewer than k
 // keys are <= (prefix | all lower bits set).  Keys of real scores are <= bits(1.0f) =
-// 0x3F800000 < 2^30, so 30 rounds; excluded keys (0xFFFFFFFF) never count.
+// 0x3F800000 < 2^30, so 30 rounds; excluded keys (0x7FFFFFFF) never count.
 // KPT > 0: the image's keys live in registers (KPT per thread); KPT == 0: they are read
 // from `keys` (shared memory copy if it fits, else global/L2) every round.
 template <int KPT>
 __global__ void __launch_bounds__(kSelectThreads, 1)
-ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int* __restrict__ n_pos_override, int N, int ratio,
-                   int keymode, int use_smem, ImageInfo* __restrict__ info, float* __restrict__ thr_out) {
+ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict__ counts, int ncounts,
+                   const int* __restrict__ n_pos_override, int N, int ratio, int keymode, int use_smem,
+                   ImageInfo* __restrict__ info, float* __restrict__ thr_out, LossHeader* __restrict__ hdr) {
   extern __shared__ __align__(16) uint32_t skeys[];
   __shared__ int s_w[2][32];
   const int b = blockIdx.x;
@@ -156,8 +161,21 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int* __restrict_
   const int lane = tid & 31, warp = tid >> 5;
   const uint32_t* gkeys = keys_all + (size_t)b * N;
 
-  int npos = info[b].n_pos;
-  const int nneg = info[b].n_neg;
+  // the counters K2/K3 accumulate into are cleared here (K1 precedes them on the stream)
+  if (hdr && b == 0 && tid < (int)(sizeof(LossHeader) / sizeof(int))) reinterpret_cast<int*>(hdr)[tid] = 0;
+  int npos = 0, nneg = 0;
+  if (warp == 0) {
+    for (int i = lane; i < ncounts; i += 32) {
+      const int2 c = counts[(size_t)b * ncounts + i];
+      npos += c.x, nneg += c.y;
+    }
+    npos = __reduce_add_sync(0xffffffffu, npos);
+    nneg = __reduce_add_sync(0xffffffffu, nneg);
+    if (lane == 0) s_w[0][0] = npos, s_w[0][1] = nneg;
+  }
+  __syncthreads();
+  npos = s_w[0][0], nneg = s_w[0][1];
+  __syncthreads();
   if (n_pos_override) npos = n_pos_override[b];  // OHNM_single_image(scores, n_pos, neg_mask): n_pos is an argument
   // ---- k (model.py:170-173 / pixellink.py:116-120)
   const long long kk = (long long)npos * ratio;
@@ -184,8 +202,17 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int* __restrict_
       const uint32_t t = ans | ((1u << bit) - 1u);
       int c = 0;
       if (KPT > 0) {
+        // count(key > t) from the sign of (t - key): keys and t are < 2^31, so the subtraction
+        // cannot wrap; two instructions per key (IADD3 + LEA.HI) in four independent chains
+        unsigned g0 = 0, g1 = 0, g2 = 0, g3 = 0;
 #pragma unroll
-        for (int j = 0; j < KPT; ++j) c += (rk[j] <= t);
+        for (int j = 0; j < KPT; j += 4) {
+          g0 += (t - rk[j]) >> 31;
+          g1 += (t - rk[j + 1]) >> 31;
+          g2 += (t - rk[j + 2]) >> 31;
+          g3 += (t - rk[j + 3]) >> 31;
+        }
+        c = KPT - (int)(g0 + g1 + g2 + g3);
       } else {
         for (int i = tid; i < N; i += kSelectThreads) c += (keys[i] <= t);
       }
@@ -198,6 +225,7 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int* __restrict_
     }
   }
   if (tid == 0) {
+    info[b].n_pos = npos, info[b].n_neg = nneg;
     info[b].thr_key = ans;
     info[b].valid = none ? 0 : 1;
     // NaN when nothing is selected: `score <= NaN` is false for every pixel
@@ -206,32 +234,40 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int* __restrict_
 }
 
 // ------------------------------------------------------------------ K2: mask + integer normalisers
+constexpr int kCountsThreads = 512;
 template <int VARIANT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCountsThreads)
 ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ pix_lab,
-                   const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N, int total_px,
-                   uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr) {
+                   const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N,
+                   uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr, int* __restrict__ cparts) {
   __shared__ int s_c[18];
+  __shared__ bool s_last;
   const int tid = threadIdx.x;
+  const int b = blockIdx.y;
   if (tid < 18) s_c[tid] = 0;
   __syncthreads();
   int cP[8], cN[8], nsp = 0, nsel = 0;
 #pragma unroll
   for (int d = 0; d < 8; ++d) cP[d] = 0, cN[d] = 0;
-
-  const int stride = gridDim.x * blockDim.x;
-  for (int px = blockIdx.x * blockDim.x + tid; px < total_px; px += stride) {
-    const float4 la = __ldg(reinterpret_cast<const float4*>(link_lab) + (size_t)px * 2);
-    const float4 lb = __ldg(reinterpret_cast<const float4*>(link_lab) + (size_t)px * 2 + 1);
+  unsigned thr_key = 0;
+  bool valid = false;
+  if (VARIANT != PLH_VARIANT_POS_ONLY) {
+    const ImageInfo ii = info[b];
+    thr_key = ii.thr_key, valid = ii.valid != 0;
+  }
+  const size_t base = (size_t)b * N;
+  for (int i = blockIdx.x * kCountsThreads + tid; i < N; i += gridDim.x * kCountsThreads) {
+    const size_t px = base + i;
+    const float4 la = __ldg(reinterpret_cast<const float4*>(link_lab) + px * 2);
+    const float4 lb = __ldg(reinterpret_cast<const float4*>(link_lab) + px * 2 + 1);
     const float l = __ldg(pix_lab + px);
+    const unsigned key = (VARIANT != PLH_VARIANT_POS_ONLY) ? __ldg(keys + px) : 0u;
     bool pos, neg;
     if (VARIANT == PLH_VARIANT_PIXELLINK) pos = l > 0.f, neg = !pos;
     else { const int li = (int)l; pos = li == 1, neg = li == 0; }
     bool M = pos;
-    if (VARIANT != PLH_VARIANT_POS_ONLY && neg) {
-      const ImageInfo ii = info[px / N];
-      M = ii.valid && (__ldg(keys + px) <= ii.thr_key);  // model.py:178 ties at the threshold are all selected
-    }
+    if (VARIANT != PLH_VARIANT_POS_ONLY && neg)
+      M = valid && key <= thr_key;  // model.py:178 ties at the threshold are all selected
     mask[px] = M ? 1 : 0;
     nsel += M;
     if (VARIANT == PLH_VARIANT_PIXELLINK) nsp += M;  // pixellink.py:155 n_seg_pos = sum(selected mask)
@@ -263,7 +299,30 @@ ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ 
     if (nsel) atomicAdd(&s_c[17], nsel);
   }
   __syncthreads();
-  if (tid < 18 && s_c[tid]) atomicAdd(reinterpret_cast<int*>(hdr) + tid, s_c[tid]);  // header ints 0..17
+  // per-CTA partial counts, summed by the last CTA (18 hot atomics per CTA would serialise in L2)
+  const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+  if (tid < 18) cparts[(size_t)cta * 18 + tid] = s_c[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&hdr->ticket2, 1u) == ncta - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // thread t: value t % 18, CTAs t / 18, t / 18 + G, ...
+  constexpr int G = kCountsThreads / 18;
+  __shared__ int s_part[G * 18];
+  const int g = tid / 18, i = tid - g * 18;
+  if (g < G) {
+    int acc = 0;
+    for (unsigned c = g; c < ncta; c += G) acc += __ldcg(cparts + (size_t)c * 18 + i);
+    s_part[g * 18 + i] = acc;
+  }
+  __syncthreads();
+  if (tid < 18) {
+    int sum = 0;
+    for (int gg = 0; gg < G; ++gg) sum += s_part[gg * 18 + tid];
+    reinterpret_cast<int*>(hdr)[tid] = sum;  // header ints 0..17
+  }
 }
 
 // ------------------------------------------------------------------ K3: main fused pass
@@ -321,7 +380,7 @@ __device__ __forceinline__ void classify(float l, bool& p, bool& n) {
 }
 
 template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
-__global__ void __launch_bounds__(kMainThreads)
+__global__ void __launch_bounds__(kMainThreads, 2)
 loss_main_kernel(const MainArgs a, const int B, const int N) {
   __shared__ float s_red[kMainThreads / 32][4][5];
   __shared__ double s_fin[17];
@@ -557,20 +616,23 @@ static void launch_main(bool grad, bool flags, int grid, cudaStream_t s, const M
 template <int KEYMODE, bool FROM_SCORES>
 static int launch_keys_and_select(const float* pix_logits, const float* pix_lab, const float* scores,
                                   const uint8_t* pos, const uint8_t* neg, const int* n_pos_override, int B, int N,
-                                  int ratio, uint32_t* keys, ImageInfo* info, float* thr_out, cudaStream_t s) {
-  {
-    const int per_image = std::max(1, std::min((N + kKeysThreads - 1) / kKeysThreads, (kNumSMs * 8 + B - 1) / B));
-    score_keys_kernel<KEYMODE, FROM_SCORES><<<dim3(per_image, B), kKeysThreads, 0, s>>>(pix_logits, pix_lab, scores,
-                                                                                        pos, neg, N, keys, info);
-    const int rc = launch_status();
-    if (rc) return rc;
-  }
+                                  int ratio, uint32_t* keys, int2* counts, ImageInfo* info, float* thr_out,
+                                  LossHeader* hdr, cudaStream_t s) {
+  const int per_image = std::max(1, std::min({(N + kKeysThreads - 1) / kKeysThreads, (kNumSMs * 8 + B - 1) / B,
+                                              kKeysMaxCTAsPerImage}));
+  score_keys_kernel<KEYMODE, FROM_SCORES><<<dim3(per_image, B), kKeysThreads, 0, s>>>(pix_logits, pix_lab, scores, pos,
+                                                                                      neg, N, keys, counts);
+  int rc = launch_status();
+  if (rc) return rc;
+#define PLH_SELECT(KPT, SMEM, USE)                                                                                   \
+  ohem_select_kernel<KPT><<<B, kSelectThreads, SMEM, s>>>(keys, counts, per_image, n_pos_override, N, ratio, KEYMODE, \
+                                                         USE, info, thr_out, hdr)
   if (N <= kSelectThreads * 4) {
-    ohem_select_kernel<4><<<B, kSelectThreads, 0, s>>>(keys, n_pos_override, N, ratio, KEYMODE, 0, info, thr_out);
+    PLH_SELECT(4, 0, 0);
   } else if (N <= kSelectThreads * 16) {
-    ohem_select_kernel<16><<<B, kSelectThreads, 0, s>>>(keys, n_pos_override, N, ratio, KEYMODE, 0, info, thr_out);
+    PLH_SELECT(16, 0, 0);
   } else if (N <= kSelectThreads * 36) {
-    ohem_select_kernel<36><<<B, kSelectThreads, 0, s>>>(keys, n_pos_override, N, ratio, KEYMODE, 0, info, thr_out);
+    PLH_SELECT(36, 0, 0);
   } else {
     const bool use_smem = (size_t)N * 4 <= kSmemKeysMaxBytes;
     static bool attr_set = false;  // idempotent; benign if raced
@@ -580,10 +642,9 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
-    ohem_select_kernel<0><<<B, kSelectThreads, use_smem ? (size_t)N * 4 : 0, s>>>(keys, n_pos_override, N, ratio,
-                                                                                  KEYMODE, use_smem ? 1 : 0, info,
-                                                                                  thr_out);
+    PLH_SELECT(0, use_smem ? (size_t)N * 4 : 0, use_smem ? 1 : 0);
   }
+#undef PLH_SELECT
   return launch_status();
 }
 
@@ -615,32 +676,37 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   float* partials = (float*)(ws + l.partials);
   uint8_t* mask = ohem_mask ? ohem_mask : (uint8_t*)(ws + l.mask);
   uint32_t* keys = (uint32_t*)(ws + l.keys);
+  int2* counts = (int2*)(ws + l.counts);
+  int* cparts = (int*)(ws + l.cparts);
   const int total_px = B * N;
-
-  cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(LossHeader) + sizeof(ImageInfo) * (size_t)B, s);
-  if (e != cudaSuccess) return (int)e;
+  cudaError_t e;
   int rc;
   // K0 + K1 (not needed for the positives-only variant: there is no mining, vgg16 :265)
   if (p->variant == PLH_VARIANT_MODEL)
     rc = launch_keys_and_select<KEYS_MODEL, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
-                                                   p->neg_pos_ratio, keys, info, stats + PLH_ST_THR, s);
+                                                   p->neg_pos_ratio, keys, counts, info, stats + PLH_ST_THR, hdr, s);
   else if (p->variant == PLH_VARIANT_PIXELLINK)
     rc = launch_keys_and_select<KEYS_PIXELLINK, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
-                                                       p->neg_pos_ratio, keys, info, stats + PLH_ST_THR, s);
+                                                       p->neg_pos_ratio, keys, counts, info, stats + PLH_ST_THR, hdr,
+                                                       s);
   else {
     e = cudaMemsetAsync(stats + PLH_ST_THR, 0xff, sizeof(float) * B, s);  // thr[b] = NaN
+    if (e == cudaSuccess) e = cudaMemsetAsync(hdr, 0, sizeof(LossHeader), s);
     rc = e == cudaSuccess ? PLH_OK : (int)e;
   }
   if (rc) return rc;
   // K2
   {
-    const int grid = std::min((total_px + 255) / 256, kNumSMs * 4);
+    int per_image = std::max(1, std::min((N + kCountsThreads - 1) / kCountsThreads, (kNumSMs * 2 + B - 1) / B));
+    while (per_image > 1 && (long long)per_image * B > kCountsMaxCTAs) --per_image;
+    if ((long long)per_image * B > kCountsMaxCTAs) return PLH_E_SHAPE;  // B > 592 images per call
+    const dim3 grid(per_image, B);
     if (p->variant == PLH_VARIANT_MODEL)
-      ohem_counts_kernel<PLH_VARIANT_MODEL><<<grid, 256, 0, s>>>(keys, pix_lab, link_lab, info, N, total_px, mask, hdr);
+      ohem_counts_kernel<PLH_VARIANT_MODEL><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr, cparts);
     else if (p->variant == PLH_VARIANT_POS_ONLY)
-      ohem_counts_kernel<PLH_VARIANT_POS_ONLY><<<grid, 256, 0, s>>>(keys, pix_lab, link_lab, info, N, total_px, mask, hdr);
+      ohem_counts_kernel<PLH_VARIANT_POS_ONLY><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr, cparts);
     else
-      ohem_counts_kernel<PLH_VARIANT_PIXELLINK><<<grid, 256, 0, s>>>(keys, pix_lab, link_lab, info, N, total_px, mask, hdr);
+      ohem_counts_kernel<PLH_VARIANT_PIXELLINK><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr, cparts);
     if ((rc = launch_status())) return rc;
   }
   // K3
@@ -711,19 +777,20 @@ extern "C" int plh_ohnm_batch(const float* scores, const uint8_t* pos_mask, cons
   if (!scores || !pos_mask || !neg_mask || !selected_mask || !thr) return PLH_E_NULL;
   if (B <= 0 || N <= 0 || (long long)B * N > (1ll << 29)) return PLH_E_SHAPE;
   if (variant != PLH_VARIANT_MODEL && variant != PLH_VARIANT_PIXELLINK) return PLH_E_PARAM;
-  // workspace: ImageInfo[B] | keys[B*N]
+  // workspace: ImageInfo[B] | counts[B * kKeysMaxCTAsPerImage] | keys[B*N]
   const size_t info_bytes = align_up(sizeof(ImageInfo) * (size_t)B, 256);
-  if (!workspace || !aligned16(workspace) || workspace_bytes < info_bytes + (size_t)B * N * 4) return PLH_E_WORKSPACE;
+  const size_t cnt_bytes = align_up(sizeof(int2) * (size_t)B * kKeysMaxCTAsPerImage, 256);
+  if (!workspace || !aligned16(workspace) || workspace_bytes < info_bytes + cnt_bytes + (size_t)B * N * 4)
+    return PLH_E_WORKSPACE;
   ImageInfo* info = (ImageInfo*)workspace;
-  uint32_t* keys = (uint32_t*)((char*)workspace + info_bytes);
+  int2* counts = (int2*)((char*)workspace + info_bytes);
+  uint32_t* keys = (uint32_t*)((char*)workspace + info_bytes + cnt_bytes);
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(ImageInfo) * (size_t)B, s);
-  if (e != cudaSuccess) return (int)e;
   int rc = variant == PLH_VARIANT_MODEL
                ? launch_keys_and_select<KEYS_MODEL, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B, N,
-                                                          neg_pos_ratio, keys, info, thr, s)
+                                                          neg_pos_ratio, keys, counts, info, thr, nullptr, s)
                : launch_keys_and_select<KEYS_PIXELLINK, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B,
-                                                              N, neg_pos_ratio, keys, info, thr, s);
+                                                              N, neg_pos_ratio, keys, counts, info, thr, nullptr, s);
   if (rc) return rc;
   const long long total = (long long)B * N;
   const int grid = (int)std::min<long long>((total + 255) / 256, kNumSMs * 8);

@@ -6,33 +6,47 @@
 //
 // Every fp32 operation uses the _rn intrinsics so that nvcc never contracts a
 // multiply-add: the rounding sequence is OpenCV's.
+//
+// Work split inside the CTA: bitonic sort (all threads) -> coordinates decoded to int
+// arrays (all threads) -> the four Sklansky scans on four warps concurrently, each
+// carrying the current/previous point in registers -> hull assembly (thread 0) -> edge
+// vectors / inverse lengths / unit leads (all threads) -> calipers loop (thread 0).
 #pragma once
 #include "common.cuh"
 
 namespace plh {
 
 struct RectSmem {
-  unsigned long long* keys;  // [npad] sort keys: x<<32 | y<<16... see make_key
-  int* stack;                // [n + 2] x 2 (upper/lower scans reuse)
-  int* hullbuf;              // [n]
-  float* hx;                 // [n] hull points / edge vectors / inverse lengths
+  unsigned long long* keys;  // [npad] sort keys (x, y, input index)
+  int* X;                    // [npad] sorted coordinates / input indices
+  int* Y;
+  int* I;
+  int* stack;                // 4 regions of (npad + 4): one per Sklansky scan
+  int* hullbuf;              // [npad] hull as sorted positions
+  float* hx;                 // [npad] hull points, edge vectors, inverse lengths, unit leads
   float* hy;
   float* vx;
   float* vy;
   float* inv;
+  float* lx;
+  float* ly;
 };
 
 __host__ __device__ inline size_t rect_smem_bytes(int npad) {
-  // keys 8 + stack 2*4 (two stacks of npad+2 -> rounded) + hullbuf 4 + 5 floats 20
-  return (size_t)npad * 8 + (size_t)(npad + 4) * 4 * 4 + (size_t)npad * 4 + (size_t)npad * 20 + 64;
+  return (size_t)npad * 8 + (size_t)npad * 4 * 3 + (size_t)(npad + 4) * 4 * 4 + (size_t)npad * 4 +
+         (size_t)npad * 4 * 7 + 64;
 }
 
 __device__ inline RectSmem rect_carve(unsigned char* base, int npad) {
   RectSmem s;
   s.keys = reinterpret_cast<unsigned long long*>(base);
   base += (size_t)npad * 8;
+  s.X = reinterpret_cast<int*>(base);
+  s.Y = s.X + npad;
+  s.I = s.Y + npad;
+  base += (size_t)npad * 12;
   s.stack = reinterpret_cast<int*>(base);
-  base += (size_t)(npad + 4) * 4 * 4;
+  base += (size_t)(npad + 4) * 16;
   s.hullbuf = reinterpret_cast<int*>(base);
   base += (size_t)npad * 4;
   s.hx = reinterpret_cast<float*>(base);
@@ -40,10 +54,12 @@ __device__ inline RectSmem rect_carve(unsigned char* base, int npad) {
   s.vx = s.hy + npad;
   s.vy = s.vx + npad;
   s.inv = s.vy + npad;
+  s.lx = s.inv + npad;
+  s.ly = s.lx + npad;
   return s;
 }
 
-// key orders by (x, y, index); x,y in [0, 65535] after +bias, index < 2^20
+// key orders by (x, y, index); x,y biased by 32768 into 24/20-bit fields, index < 2^20
 __device__ __forceinline__ unsigned long long make_key(int x, int y, int idx) {
   return ((unsigned long long)(unsigned)(x + 32768) << 40) | ((unsigned long long)(unsigned)(y + 32768) << 20) |
          (unsigned long long)(unsigned)idx;
@@ -52,11 +68,11 @@ __device__ __forceinline__ int key_x(unsigned long long k) { return (int)(k >> 4
 __device__ __forceinline__ int key_y(unsigned long long k) { return (int)((k >> 20) & 0xFFFFFu) - 32768; }
 __device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(k & 0xFFFFFu); }
 
-// In-place bitonic sort of keys[0..npad) by the whole CTA (npad a power of two; pad = ~0).
-__device__ inline void bitonic_sort(unsigned long long* keys, int npad) {
-  for (int k = 2; k <= npad; k <<= 1) {
+// In-place bitonic sort of keys[0..n) by the whole CTA (n a power of two; pad = ~0).
+__device__ inline void bitonic_sort(unsigned long long* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const unsigned long long a = keys[i], b = keys[ixj];
@@ -71,42 +87,46 @@ __device__ inline void bitonic_sort(unsigned long long* keys, int npad) {
 
 __device__ __forceinline__ int sgn(long long v) { return (v > 0) - (v < 0); }
 
-// OpenCV convhull.cpp Sklansky_ over the sorted keys; returns the stack size.
-__device__ inline int sklansky(const unsigned long long* keys, int start, int end, int* stack, int nsign, int sign2) {
+// OpenCV convhull.cpp Sklansky_ over the sorted points; returns the stack size.
+// The coordinates of pprev / pcur are carried in registers: one shared-memory round trip
+// per step instead of five.
+__device__ inline int sklansky(const int* __restrict__ X, const int* __restrict__ Y, int start, int end, int* stack,
+                               int nsign, int sign2) {
   const int incr = end > start ? 1 : -1;
   int pprev = start, pcur = pprev + incr, pnext = pcur + incr;
   int stacksize = 3;
-  if (start == end || (key_x(keys[start]) == key_x(keys[end]) && key_y(keys[start]) == key_y(keys[end]))) {
+  if (start == end || (X[start] == X[end] && Y[start] == Y[end])) {
     stack[0] = start;
     return 1;
   }
   stack[0] = pprev, stack[1] = pcur, stack[2] = pnext;
   end += incr;
+  int xprev = X[pprev], yprev = Y[pprev], xcur = X[pcur], ycur = Y[pcur];
   while (pnext != end) {
-    const int cury = key_y(keys[pcur]);
-    const int nexty = key_y(keys[pnext]);
-    const int by = nexty - cury;
+    const int xnext = X[pnext], ynext = Y[pnext];
+    const int by = ynext - ycur;
     if (sgn(by) != nsign) {
-      const int ax = key_x(keys[pcur]) - key_x(keys[pprev]);
-      const int bx = key_x(keys[pnext]) - key_x(keys[pcur]);
-      const int ay = cury - key_y(keys[pprev]);
+      const int ax = xcur - xprev;
+      const int bx = xnext - xcur;
+      const int ay = ycur - yprev;
       const long long convexity = (long long)ay * bx - (long long)ax * by;
       if (sgn(convexity) == sign2 && (ax != 0 || ay != 0)) {
-        pprev = pcur;
-        pcur = pnext;
+        pprev = pcur, xprev = xcur, yprev = ycur;
+        pcur = pnext, xcur = xnext, ycur = ynext;
         pnext += incr;
         stack[stacksize] = pnext;
         stacksize++;
       } else {
         if (pprev == start) {
-          pcur = pnext;
+          pcur = pnext, xcur = xnext, ycur = ynext;
           stack[1] = pcur;
           pnext += incr;
           stack[2] = pnext;
         } else {
           stack[stacksize - 2] = pnext;
-          pcur = pprev;
+          pcur = pprev, xcur = xprev, ycur = yprev;
           pprev = stack[stacksize - 4];
+          xprev = X[pprev], yprev = Y[pprev];
           stacksize--;
         }
       }
@@ -119,21 +139,27 @@ __device__ inline int sklansky(const unsigned long long* keys, int start, int en
 }
 
 // Called by the WHOLE CTA (>= 128 threads) after the keys are sorted.  total = number of
-// real points.  The four Sklansky scans run concurrently on four warps; the short
-// sequential tail (assembly, calipers over the hull) runs on thread 0.
-// out_box: 8 ints (x0,y0..x3,y3), out_rect: 5 floats or nullptr — written by thread 0 only.
+// real points (> 0).  out_box: 8 ints (x0,y0..x3,y3), out_rect: 5 floats or nullptr — valid
+// in thread 0 only.
 __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npad, int* out_box, float* out_rect) {
   __shared__ int s_ind[2];     // miny_ind, maxy_ind
   __shared__ int s_count[4];   // tl, tr, bl, br stack sizes
-  const unsigned long long* keys = S.keys;
+  __shared__ int s_nout;
   int* hullbuf = S.hullbuf;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < total; i += blockDim.x) {
+    const unsigned long long k = S.keys[i];
+    S.X[i] = key_x(k), S.Y[i] = key_y(k), S.I[i] = key_idx(k);
+  }
+  __syncthreads();
+  const int* X = S.X;
+  const int* Y = S.Y;
   // ---- cv::convexHull(points, clockwise=false, returnPoints=true)
   // first sorted position with the minimum y / with the maximum y (strict comparisons in OpenCV's loop)
   if (warp == 0) {
     int miny = 0x7fffffff, mini = 0x7fffffff, maxy = -0x7fffffff, maxi = 0x7fffffff;
     for (int i = lane; i < total; i += 32) {
-      const int y = key_y(keys[i]);
+      const int y = Y[i];
       if (y < miny) miny = y, mini = i;
       if (y > maxy) maxy = y, maxi = i;
     }
@@ -148,111 +174,116 @@ __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npa
   }
   __syncthreads();
   const int miny_ind = s_ind[0], maxy_ind = s_ind[1];
-  const bool single = key_x(keys[0]) == key_x(keys[total - 1]) && key_y(keys[0]) == key_y(keys[total - 1]);
+  const bool single = X[0] == X[total - 1] && Y[0] == Y[total - 1];
   const int SS = npad + 4;  // stack stride: one region per scan
   if (!single && lane == 0 && warp < 4) {
     int* st = S.stack + warp * SS;
     int c;
-    if (warp == 0) c = sklansky(keys, 0, maxy_ind, st, -1, 1);               // tl
-    else if (warp == 1) c = sklansky(keys, total - 1, maxy_ind, st, -1, -1);  // tr
-    else if (warp == 2) c = sklansky(keys, 0, miny_ind, st, 1, -1);           // bl
-    else c = sklansky(keys, total - 1, miny_ind, st, 1, 1);                   // br
+    if (warp == 0) c = sklansky(X, Y, 0, maxy_ind, st, -1, 1);               // tl
+    else if (warp == 1) c = sklansky(X, Y, total - 1, maxy_ind, st, -1, -1);  // tr
+    else if (warp == 2) c = sklansky(X, Y, 0, miny_ind, st, 1, -1);           // bl
+    else c = sklansky(X, Y, total - 1, miny_ind, st, 1, 1);                   // br
     s_count[warp] = c;
   }
   __syncthreads();
-  if (tid != 0) return;
-  int nout = 0;
-  if (single) {
-    hullbuf[nout++] = 0;  // sorted position; converted below
-  } else {
-    int* tl_stack = S.stack;
-    int tl_count = s_count[0];
-    int* tr_stack = S.stack + SS;
-    int tr_count = s_count[1];
-    {  // !clockwise: swap
-      int* t = tl_stack; tl_stack = tr_stack; tr_stack = t;
-      int c = tl_count; tl_count = tr_count; tr_count = c;
-    }
-    for (int i = 0; i < tl_count - 1; ++i) hullbuf[nout++] = tl_stack[i];
-    for (int i = tr_count - 1; i > 0; --i) hullbuf[nout++] = tr_stack[i];
-    const int stop_idx = tr_count > 2 ? tr_stack[1] : (tl_count > 2 ? tl_stack[tl_count - 2] : -1);
-    int* bl_stack = S.stack + 2 * SS;
-    int bl_count = s_count[2];
-    int* br_stack = S.stack + 3 * SS;
-    int br_count = s_count[3];
-    if (stop_idx >= 0) {
-      const int check_idx = bl_count > 2 ? bl_stack[1] : (bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1);
-      if (check_idx == stop_idx ||
-          (check_idx >= 0 && key_x(keys[check_idx]) == key_x(keys[stop_idx]) &&
-           key_y(keys[check_idx]) == key_y(keys[stop_idx]))) {
-        bl_count = min(bl_count, 2);
-        br_count = min(br_count, 2);
+  if (tid == 0) {
+    int nout = 0;
+    if (single) {
+      hullbuf[nout++] = 0;
+    } else {
+      int* tl_stack = S.stack;
+      int tl_count = s_count[0];
+      int* tr_stack = S.stack + SS;
+      int tr_count = s_count[1];
+      {  // !clockwise: swap
+        int* t = tl_stack; tl_stack = tr_stack; tr_stack = t;
+        int c = tl_count; tl_count = tr_count; tr_count = c;
       }
-    }
-    for (int i = 0; i < bl_count - 1; ++i) hullbuf[nout++] = bl_stack[i];
-    for (int i = br_count - 1; i > 0; --i) hullbuf[nout++] = br_stack[i];
-    // cyclic shift towards a monotone sequence of INPUT indices
-    if (nout >= 3) {
-      int min_idx = 0, max_idx = 0, lt = 0;
-      auto IDX = [&](int i) { return key_idx(keys[hullbuf[i]]); };
-      for (int i = 1; i < nout; ++i) {
-        const int idx = IDX(i);
-        lt += IDX(i - 1) < idx;
-        if (lt > 1 && lt <= i - 2) break;
-        if (idx < IDX(min_idx)) min_idx = i;
-        if (idx > IDX(max_idx)) max_idx = i;
+      for (int i = 0; i < tl_count - 1; ++i) hullbuf[nout++] = tl_stack[i];
+      for (int i = tr_count - 1; i > 0; --i) hullbuf[nout++] = tr_stack[i];
+      const int stop_idx = tr_count > 2 ? tr_stack[1] : (tl_count > 2 ? tl_stack[tl_count - 2] : -1);
+      int* bl_stack = S.stack + 2 * SS;
+      int bl_count = s_count[2];
+      int* br_stack = S.stack + 3 * SS;
+      int br_count = s_count[3];
+      if (stop_idx >= 0) {
+        const int check_idx = bl_count > 2 ? bl_stack[1] : (bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1);
+        if (check_idx == stop_idx ||
+            (check_idx >= 0 && X[check_idx] == X[stop_idx] && Y[check_idx] == Y[stop_idx])) {
+          bl_count = min(bl_count, 2);
+          br_count = min(br_count, 2);
+        }
       }
-      const int mmdist = abs(max_idx - min_idx);
-      if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
-        const int ascending = (max_idx + 1) % nout == min_idx;
-        const int i0 = ascending ? min_idx : max_idx;
-        int j = i0;
-        if (i0 > 0) {
-          int* tmp = S.stack;  // the scan stacks are dead now
-          int i;
-          for (i = 0; i < nout; ++i) {
-            const int curr_idx = IDX(j);
-            tmp[i] = hullbuf[j];
-            const int next_j = j + 1 < nout ? j + 1 : 0;
-            const int next_idx = IDX(next_j);
-            if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
-            j = next_j;
+      for (int i = 0; i < bl_count - 1; ++i) hullbuf[nout++] = bl_stack[i];
+      for (int i = br_count - 1; i > 0; --i) hullbuf[nout++] = br_stack[i];
+      // cyclic shift towards a monotone sequence of INPUT indices
+      if (nout >= 3) {
+        int min_idx = 0, max_idx = 0, lt = 0;
+        const int* I = S.I;
+        for (int i = 1; i < nout; ++i) {
+          const int idx = I[hullbuf[i]];
+          lt += I[hullbuf[i - 1]] < idx;
+          if (lt > 1 && lt <= i - 2) break;
+          if (idx < I[hullbuf[min_idx]]) min_idx = i;
+          if (idx > I[hullbuf[max_idx]]) max_idx = i;
+        }
+        const int mmdist = abs(max_idx - min_idx);
+        if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
+          const int ascending = (max_idx + 1) % nout == min_idx;
+          const int i0 = ascending ? min_idx : max_idx;
+          int j = i0;
+          if (i0 > 0) {
+            int* tmp = S.stack;  // the scan stacks are dead now
+            int i;
+            for (i = 0; i < nout; ++i) {
+              const int curr_idx = I[hullbuf[j]];
+              tmp[i] = hullbuf[j];
+              const int next_j = j + 1 < nout ? j + 1 : 0;
+              const int next_idx = I[hullbuf[next_j]];
+              if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
+              j = next_j;
+            }
+            if (i == nout)
+              for (i = 0; i < nout; ++i) hullbuf[i] = tmp[i];
           }
-          if (i == nout)
-            for (i = 0; i < nout; ++i) hullbuf[i] = tmp[i];
         }
       }
     }
+    s_nout = nout;
   }
-  const int n = nout;
+  __syncthreads();
+  const int n = s_nout;
   float* hx = S.hx; float* hy = S.hy; float* vx = S.vx; float* vy = S.vy; float* inv = S.inv;
-  for (int i = 0; i < n; ++i) {
-    hx[i] = (float)key_x(keys[hullbuf[i]]);
-    hy[i] = (float)key_y(keys[hullbuf[i]]);
+  float* ldx = S.lx; float* ldy = S.ly;
+  for (int i = tid; i < n; i += blockDim.x) hx[i] = (float)X[hullbuf[i]], hy[i] = (float)Y[hullbuf[i]];
+  __syncthreads();
+  // edge vectors (rotcalipers.cpp: differences in double, stored as float; 1/length via double)
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int nx = i + 1 < n ? i + 1 : 0;
+    const double dx = (double)hx[nx] - (double)hx[i];
+    const double dy = (double)hy[nx] - (double)hy[i];
+    const float fx = (float)dx, fy = (float)dy;
+    const float iv = (float)__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+    vx[i] = fx, vy[i] = fy, inv[i] = iv;
+    ldx[i] = __fmul_rn(fx, iv), ldy[i] = __fmul_rn(fy, iv);
   }
+  __syncthreads();
+  if (tid != 0) return;
   // ---- cv::minAreaRect
   float cx = 0.f, cy = 0.f, w = 0.f, h = 0.f;
   double angle = 0.0;
   if (n > 2) {
-    // rotatingCalipers(CALIPERS_MINAREARECT)
+    // rotatingCalipers(CALIPERS_MINAREARECT): extreme points with strict comparisons
     int left = 0, bottom = 0, right = 0, top = 0;
     float left_x, right_x, top_y, bottom_y;
-    float pt0x = hx[0], pt0y = hy[0];
-    left_x = right_x = pt0x;
-    top_y = bottom_y = pt0y;
-    for (int i = 0; i < n; ++i) {
-      if (pt0x < left_x) left_x = pt0x, left = i;
-      if (pt0x > right_x) right_x = pt0x, right = i;
-      if (pt0y > top_y) top_y = pt0y, top = i;
-      if (pt0y < bottom_y) bottom_y = pt0y, bottom = i;
-      const float nx = (i + 1 < n) ? hx[i + 1] : hx[0];
-      const float ny = (i + 1 < n) ? hy[i + 1] : hy[0];
-      const double dx = (double)nx - (double)pt0x;
-      const double dy = (double)ny - (double)pt0y;
-      vx[i] = (float)dx;
-      vy[i] = (float)dy;
-      inv[i] = (float)__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
-      pt0x = nx, pt0y = ny;
+    left_x = right_x = hx[0];
+    top_y = bottom_y = hy[0];
+    for (int i = 1; i < n; ++i) {
+      const float px = hx[i], py = hy[i];
+      if (px < left_x) left_x = px, left = i;
+      if (px > right_x) right_x = px, right = i;
+      if (py > top_y) top_y = py, top = i;
+      if (py < bottom_y) bottom_y = py, bottom = i;
     }
     float orientation = 0.f;
     {
@@ -287,8 +318,7 @@ __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npa
       }
       {
         const int pindex = seq[main_element];
-        const float lead_x = __fmul_rn(vx[pindex], inv[pindex]);
-        const float lead_y = __fmul_rn(vy[pindex], inv[pindex]);
+        const float lead_x = ldx[pindex], lead_y = ldy[pindex];
         switch (main_element) {
           case 0: base_a = lead_x, base_b = lead_y; break;
           case 1: base_a = lead_y, base_b = -lead_x; break;

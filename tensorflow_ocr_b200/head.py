@@ -168,7 +168,9 @@ def ohnm_batch_raw(scores, pos_mask, neg_mask, variant=_lib.VARIANT_MODEL, ratio
     _require_gpu(dev)
     sel = torch.empty((B, N), dtype=torch.float32, device=dev)
     thr = torch.empty((B,), dtype=torch.float32, device=dev)
-    ws = torch.empty(((B * 16 + 255) // 256) * 256 + B * N * 4, dtype=torch.uint8, device=dev)  # ImageInfo[B] | keys
+    # ImageInfo[B] | per-CTA counts [B*64] | keys [B*N]
+    ws = torch.empty(((B * 16 + 255) // 256) * 256 + ((B * 64 * 8 + 255) // 256) * 256 + B * N * 4,
+                     dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.plh_ohnm_batch(_p(scores), _p(pos_mask), _p(neg_mask), _p(n_pos), B, N, variant, ratio, _p(sel),
                                 _p(thr), _p(ws), 0 if ws is None else ws.numel(), _stream(dev))
@@ -230,13 +232,42 @@ def decode_from_flags_raw(flags, cfg: DecodeConfig = DecodeConfig(), out: Option
     return out
 
 
+_aux_streams = {}
+
+
+def _aux_stream(dev: torch.device) -> torch.cuda.Stream:
+    st = _aux_streams.get(dev.index)
+    if st is None:
+        st = torch.cuda.Stream(dev)
+        _aux_streams[dev.index] = st
+    return st
+
+
 def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossConfig = LossConfig(),
                         dcfg: DecodeConfig = DecodeConfig(), out: Optional[dict] = None,
-                        want_rects: bool = False) -> dict:
-    """The fused head step: loss fwd+bwd and decode sharing ONE read of the logits
-    (the loss kernel emits the 2 B/px threshold flags the decode starts from)."""
-    out = pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg, True, False, dcfg, out)
-    return decode_from_flags_raw(out["flags"], dcfg, out, want_rects)
+                        want_rects: bool = False, parallel: bool = True) -> dict:
+    """The head step: loss fwd+bwd and decode of the same logits.
+
+    parallel=True (default): the two pipelines are independent chains of small kernels, so the
+    decode runs on a second stream concurrently with the loss (fork/join with events; under
+    CUDA-graph capture this becomes two parallel branches).  The per-image radix select of the
+    loss occupies one SM per image; the decode fills the rest of the chip meanwhile.
+    parallel=False: one stream; the loss kernel emits the 2 B/px threshold flags and the decode
+    starts from them (one read of the logits instead of two).
+    """
+    dev = pix_logits.device
+    if not parallel:
+        out = pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg, True, False, dcfg, out)
+        return decode_from_flags_raw(out["flags"], dcfg, out, want_rects)
+    out = {} if out is None else out
+    cur = torch.cuda.current_stream(dev)
+    aux = _aux_stream(dev)
+    aux.wait_stream(cur)
+    with torch.cuda.stream(aux):
+        decode_raw(pix_logits, link_logits, dcfg, out, want_rects)
+    pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg, True, False, None, out)
+    cur.wait_stream(aux)
+    return out
 
 
 def min_area_boxes_raw(pts: torch.Tensor, offsets: torch.Tensor, want_rects=True):

@@ -28,7 +28,7 @@ def run(mode, d):
     elif mode == "fused":
         head.loss_and_decode_raw(d["pix_logits"], d["link_logits"], d["pix_lab"], d["link_lab"], lcfg, dcfg, d["out"])
 
-for mode in ("loss", "decode", "fused"):
+for mode in os.environ.get("MODES", "loss,decode,fused").split(","):
     for i in range(10):
         run(mode, sets[i % NSETS])
     torch.cuda.synchronize()
