@@ -36,16 +36,20 @@ static int g_prof_created = 0;
 static int g_prof_n = -1;  // -1: disabled
 
 // ------------------------------------------------------------------ workspace layout
-struct LossHeader {  // 128 B, zeroed by cudaMemsetAsync at the start of every call
+struct LossHeader {  // 384 B, zeroed by K1 (or a memset when there is no K1) at the start of every call
   int n_seg_pos;
   int cntP[8];
   int cntN[8];
   int n_selected;
   unsigned ticket;    // K3 last-CTA election
-  unsigned ticket2;   // K2 last-CTA election
-  int pad[12];
+  int pad[13];
+  // 17 loss sums (s_pos[8], s_neg[8], s_pix): fp64 atomic adds of fp32 per-CTA partials.  The
+  // partials carry 24 significant bits and similar exponents, so the fp64 additions are exact
+  // and the result does not depend on the order in which the CTAs arrive (deterministic).
+  double sums[17];
+  double pad2[15];
 };
-static_assert(sizeof(LossHeader) == 128, "header size");
+static_assert(sizeof(LossHeader) == 384, "header size");
 
 struct ImageInfo {  // per image, written by K1
   int n_pos;
@@ -57,14 +61,12 @@ constexpr int kKeysMaxCTAsPerImage = 64;  // K0 writes one (n_pos, n_neg) pair p
 
 constexpr int kMainThreads = 512;
 constexpr int kMainMaxCTAs = kNumSMs * 2;
-constexpr int kPartialFloats = 20;                 // 17 used
 constexpr int kSelectThreads = 1024;
 constexpr size_t kSmemKeysMaxBytes = 200 * 1024;   // keys of one image fit in shared memory up to 51200 px
 
 struct LossWsLayout {
-  size_t header, info, counts, cparts, partials, mask, keys, total;
+  size_t header, info, counts, mask, keys, total;
 };
-constexpr int kCountsMaxCTAs = kNumSMs * 4;
 
 static LossWsLayout loss_ws_layout(int B, long long N) {
   LossWsLayout l;
@@ -75,10 +77,6 @@ static LossWsLayout loss_ws_layout(int B, long long N) {
   off = align_up(off + sizeof(ImageInfo) * (size_t)B, 256);
   l.counts = off;
   off = align_up(off + sizeof(int2) * (size_t)B * kKeysMaxCTAsPerImage, 256);
-  l.cparts = off;
-  off = align_up(off + sizeof(int) * 18 * kCountsMaxCTAs, 256);
-  l.partials = off;
-  off = align_up(off + sizeof(float) * kPartialFloats * kMainMaxCTAs, 256);
   l.mask = off;
   off = align_up(off + (size_t)B * N, 256);
   l.keys = off;
@@ -163,6 +161,7 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict
 
   // the counters K2/K3 accumulate into are cleared here (K1 precedes them on the stream)
   if (hdr && b == 0 && tid < (int)(sizeof(LossHeader) / sizeof(int))) reinterpret_cast<int*>(hdr)[tid] = 0;
+  static_assert(sizeof(LossHeader) / sizeof(int) <= kSelectThreads, "header is cleared by one CTA");
   int npos = 0, nneg = 0;
   if (warp == 0) {
     for (int i = lane; i < ncounts; i += 32) {
@@ -239,9 +238,8 @@ template <int VARIANT>
 __global__ void __launch_bounds__(kCountsThreads)
 ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ pix_lab,
                    const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N,
-                   uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr, int* __restrict__ cparts) {
+                   uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr) {
   __shared__ int s_c[18];
-  __shared__ bool s_last;
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   if (tid < 18) s_c[tid] = 0;
@@ -299,30 +297,8 @@ ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ 
     if (nsel) atomicAdd(&s_c[17], nsel);
   }
   __syncthreads();
-  // per-CTA partial counts, summed by the last CTA (18 hot atomics per CTA would serialise in L2)
-  const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
-  if (tid < 18) cparts[(size_t)cta * 18 + tid] = s_c[tid];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&hdr->ticket2, 1u) == ncta - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // thread t: value t % 18, CTAs t / 18, t / 18 + G, ...
-  constexpr int G = kCountsThreads / 18;
-  __shared__ int s_part[G * 18];
-  const int g = tid / 18, i = tid - g * 18;
-  if (g < G) {
-    int acc = 0;
-    for (unsigned c = g; c < ncta; c += G) acc += __ldcg(cparts + (size_t)c * 18 + i);
-    s_part[g * 18 + i] = acc;
-  }
-  __syncthreads();
-  if (tid < 18) {
-    int sum = 0;
-    for (int gg = 0; gg < G; ++gg) sum += s_part[gg * 18 + tid];
-    reinterpret_cast<int*>(hdr)[tid] = sum;  // header ints 0..17
-  }
+  // integer atomics: exact and order independent
+  if (tid < 18 && s_c[tid]) atomicAdd(reinterpret_cast<int*>(hdr) + tid, s_c[tid]);  // header ints 0..17
 }
 
 // ------------------------------------------------------------------ K3: main fused pass
@@ -333,7 +309,6 @@ struct MainArgs {
   const float* link_lab;
   const uint8_t* mask;
   LossHeader* hdr;
-  float* partials;
   float* stats;
   float* grad_pix;
   float* grad_link;
@@ -383,7 +358,6 @@ template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
 __global__ void __launch_bounds__(kMainThreads, 2)
 loss_main_kernel(const MainArgs a, const int B, const int N) {
   __shared__ float s_red[kMainThreads / 32][4][5];
-  __shared__ double s_fin[17];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -503,14 +477,14 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
   }
   __syncthreads();
   if (tid < 17) {
-    // partial index: 0..7 s_pos[d], 8..15 s_neg[d], 16 s_pix ; d = 2*jj + c
+    // sum index: 0..7 s_pos[d], 8..15 s_neg[d], 16 s_pix ; d = 2*jj + c
     int jj, slot;
     if (tid < 16) { const int d = tid & 7; jj = d >> 1; slot = (tid < 8 ? 0 : 2) + (d & 1); }
     else { jj = 0; slot = 4; }
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kMainThreads / 32; ++w) s += s_red[w][jj][slot];
-    a.partials[(size_t)blockIdx.x * kPartialFloats + tid] = s;
+    atomicAdd(&a.hdr->sums[tid], (double)s);  // exact in fp64: order independent (see LossHeader)
   }
   __threadfence();
   __syncthreads();
@@ -518,41 +492,47 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
   __syncthreads();
   if (!s_last) return;
 
-  // ---- last CTA: deterministic final reduction + scalars
+  // ---- last CTA: the scalars.  One warp: lane d owns link direction d, so the header loads and the
+  // IEEE divisions run side by side instead of as one thread's chain of dependent L2 round trips.
   __threadfence();
-  __shared__ double s_tmp[(kMainThreads / 17) * 17];
-  block_final_reduce<17, kMainThreads>(a.partials, kPartialFloats, gridDim.x, s_fin, s_tmp);
-  if (tid == 0) {
+  if (warp == 0) {
     float* st = a.stats;
-    const float nsp = (float)hdr->n_seg_pos;
-    const float s_pix = (float)s_fin[16];
+    const int* hi = reinterpret_cast<const int*>(a.hdr);
+    const float nsp = (float)__ldcg(hi + 0);                     // n_seg_pos
+    const float nsel = (float)__ldcg(hi + 17);                   // n_selected
+    const int dd = lane & 7;
+    const float cp = (float)__ldcg(hi + 1 + dd), cn = (float)__ldcg(hi + 9 + dd);
+    const float s_pos = (float)__ldcg(&a.hdr->sums[dd]), s_neg = (float)__ldcg(&a.hdr->sums[8 + dd]);
+    const double s_pix_d = __ldcg(&a.hdr->sums[16]);
+    const float s_pix = (float)s_pix_d;
+    float Ld;
+    if (VARIANT == PLH_VARIANT_PIXELLINK)
+      Ld = (cp != 0.f ? s_pos * __fdiv_rn(1.f, cp) : 0.f) + (cn != 0.f ? s_neg * __fdiv_rn(1.f, cn) : 0.f);
+    else
+      Ld = __fdiv_rn(s_pos, cp) + __fdiv_rn(s_neg, cn);
+    if (lane < 8) {
+      st[PLH_ST_L_LINK + dd] = Ld;
+      st[PLH_ST_SUM_WP + dd] = cp;
+      st[PLH_ST_SUM_WN + dd] = cn;
+      st[PLH_ST_S_POS + dd] = s_pos;
+      st[PLH_ST_S_NEG + dd] = s_neg;
+    }
+    double link_total = 0.0;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) link_total += (double)__shfl_sync(0xffffffffu, Ld, d);  // fixed order
     float L_pix;
     if (VARIANT == PLH_VARIANT_MODEL) L_pix = nsp > 0.f ? __fdiv_rn(s_pix, nsp) : 0.f;
     else if (VARIANT == PLH_VARIANT_POS_ONLY) L_pix = __fdiv_rn(s_pix, nsp);
-    else L_pix = (float)(s_fin[16] / (double)((long long)B * N));
-    double link_total = 0.0;
-    for (int d = 0; d < 8; ++d) {
-      const float cp = (float)hdr->cntP[d], cn = (float)hdr->cntN[d];
-      const float s_pos = (float)s_fin[d], s_neg = (float)s_fin[8 + d];
-      float Ld;
-      if (VARIANT == PLH_VARIANT_PIXELLINK)
-        Ld = (cp != 0.f ? s_pos * __fdiv_rn(1.f, cp) : 0.f) + (cn != 0.f ? s_neg * __fdiv_rn(1.f, cn) : 0.f);
-      else
-        Ld = __fdiv_rn(s_pos, cp) + __fdiv_rn(s_neg, cn);
-      st[PLH_ST_L_LINK + d] = Ld;
-      st[PLH_ST_SUM_WP + d] = cp;
-      st[PLH_ST_SUM_WN + d] = cn;
-      st[PLH_ST_S_POS + d] = s_pos;
-      st[PLH_ST_S_NEG + d] = s_neg;
-      link_total += (double)Ld;
+    else L_pix = (float)(s_pix_d / (double)((long long)B * N));
+    if (lane == 0) {
+      st[PLH_ST_L_PIX] = L_pix;
+      st[PLH_ST_N_SEG_POS] = nsp;
+      st[PLH_ST_S_PIX] = s_pix;
+      st[PLH_ST_LINK_TOTAL] = (float)link_total;
+      st[PLH_ST_N_SELECTED] = nsel;
+      st[PLH_ST_TOTAL] = (float)link_total + 2.f * L_pix;  // model.py:261 / pixellink.py:170,254
     }
-    st[PLH_ST_L_PIX] = L_pix;
-    st[PLH_ST_N_SEG_POS] = nsp;
-    st[PLH_ST_S_PIX] = s_pix;
-    st[PLH_ST_LINK_TOTAL] = (float)link_total;
-    st[PLH_ST_N_SELECTED] = (float)hdr->n_selected;
-    st[PLH_ST_TOTAL] = (float)link_total + 2.f * L_pix;  // model.py:261 / pixellink.py:170,254
-    for (int i = 46; i < PLH_STATS_FLOATS; ++i) st[i] = 0.f;
+    if (lane >= 14) st[32 + lane] = 0.f;  // stats[46..63] reserved
   }
 }
 
@@ -673,11 +653,9 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   char* ws = (char*)workspace;
   LossHeader* hdr = (LossHeader*)(ws + l.header);
   ImageInfo* info = (ImageInfo*)(ws + l.info);
-  float* partials = (float*)(ws + l.partials);
   uint8_t* mask = ohem_mask ? ohem_mask : (uint8_t*)(ws + l.mask);
   uint32_t* keys = (uint32_t*)(ws + l.keys);
   int2* counts = (int2*)(ws + l.counts);
-  int* cparts = (int*)(ws + l.cparts);
   const int total_px = B * N;
   cudaError_t e;
   int rc;
@@ -697,23 +675,21 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   if (rc) return rc;
   // K2
   {
-    int per_image = std::max(1, std::min((N + kCountsThreads - 1) / kCountsThreads, (kNumSMs * 2 + B - 1) / B));
-    while (per_image > 1 && (long long)per_image * B > kCountsMaxCTAs) --per_image;
-    if ((long long)per_image * B > kCountsMaxCTAs) return PLH_E_SHAPE;  // B > 592 images per call
+    const int per_image = std::max(1, std::min((N + kCountsThreads - 1) / kCountsThreads, (kNumSMs * 2 + B - 1) / B));
     const dim3 grid(per_image, B);
     if (p->variant == PLH_VARIANT_MODEL)
-      ohem_counts_kernel<PLH_VARIANT_MODEL><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr, cparts);
+      ohem_counts_kernel<PLH_VARIANT_MODEL><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr);
     else if (p->variant == PLH_VARIANT_POS_ONLY)
-      ohem_counts_kernel<PLH_VARIANT_POS_ONLY><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr, cparts);
+      ohem_counts_kernel<PLH_VARIANT_POS_ONLY><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr);
     else
-      ohem_counts_kernel<PLH_VARIANT_PIXELLINK><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr, cparts);
+      ohem_counts_kernel<PLH_VARIANT_PIXELLINK><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr);
     if ((rc = launch_status())) return rc;
   }
   // K3
   {
     MainArgs a;
     a.pix_logits = pix_logits, a.link_logits = link_logits, a.pix_lab = pix_lab, a.link_lab = link_lab;
-    a.mask = mask, a.hdr = hdr, a.partials = partials, a.stats = stats;
+    a.mask = mask, a.hdr = hdr, a.stats = stats;
     a.grad_pix = grad_pix, a.grad_link = grad_link, a.flags = decode_flags;
     a.total_px = total_px, a.alpha = p->focal_alpha, a.gamma = p->focal_gamma;
     a.tp_logit = dp ? prob_to_logit_threshold(dp->pixel_thresh) : 0.f;
