@@ -172,6 +172,8 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     lcfg, dcfg = head.LossConfig(), head.DecodeConfig(max_boxes=128)
@@ -217,14 +219,20 @@ def run_gpu(args):
         torch.cuda.set_stream(main_stream)
 
     launches_per_step = [0]
+    # training mode, N > 1: one tiny NCCL all-reduce of the loss scalars per step on a side stream
+    # (SURVEY.md §8e); the compute stream only waits for the all-reduce that last read the stats
+    # buffer it is about to overwrite (NSETS steps ago).
+    reducers = [pdist.LossStatsReducer(dev) for _ in range(NSETS)] if world > 1 else None
 
     def run_step(i):
+        if reducers is not None and reducers[i % NSETS].pending:
+            main_stream.wait_event(reducers[i % NSETS].event)
         if graphs is not None:
             graphs[i % NSETS].replay()
         else:
             step(i)
-        if world > 1:  # training mode: one tiny all-reduce of the loss scalars, off the critical path
-            pdist.allreduce_loss_stats(outs[i % NSETS]["stats"])
+        if reducers is not None:
+            reducers[i % NSETS].submit(outs[i % NSETS]["stats"])
 
     def barrier():
         if world > 1:

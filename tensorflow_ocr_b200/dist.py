@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 from . import _lib
 
-__all__ = ["shard_bounds", "shard_batch", "allreduce_loss_stats"]
+__all__ = ["shard_bounds", "shard_batch", "allreduce_loss_stats", "LossStatsReducer"]
 
 
 def shard_bounds(B: int, world_size: int, rank: int):
@@ -42,3 +42,41 @@ def allreduce_loss_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
         mean_idx = [_lib.ST_TOTAL, _lib.ST_L_PIX, _lib.ST_LINK_TOTAL] + list(range(_lib.ST_L_LINK, _lib.ST_L_LINK + 8))
         v[mean_idx] = v[mean_idx] / w
     return v
+
+
+_MEAN_IDX = [_lib.ST_TOTAL, _lib.ST_L_PIX, _lib.ST_LINK_TOTAL] + list(range(_lib.ST_L_LINK, _lib.ST_L_LINK + 8))
+
+
+class LossStatsReducer(object):
+    """The per-step NCCL all-reduce of the loss scalars, kept OFF the critical path.
+
+    `submit(stats)` snapshots the 64 scalars and launches the all-reduce on a private side
+    stream that waits for the producing stream; the producing stream never waits for the
+    collective.  `result()` blocks the host and returns the tower-mean loss terms and the
+    summed counts (what multigpu_train.py would print if it reported every tower, quirk Q18).
+    `event` can be waited on by a stream that is about to overwrite `stats`.
+    """
+
+    def __init__(self, device, group=None):
+        self.group = group
+        self.stream = torch.cuda.Stream(device)
+        self.buf = torch.zeros(_lib.STATS_FLOATS, dtype=torch.float32, device=device)
+        self.event = torch.cuda.Event()
+        self.pending = False
+
+    def submit(self, stats: torch.Tensor):
+        cur = torch.cuda.current_stream(stats.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.buf.copy_(stats[:_lib.STATS_FLOATS], non_blocking=True)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+            self.event.record(self.stream)
+        self.pending = True
+
+    def result(self) -> torch.Tensor:
+        self.event.synchronize()
+        v = self.buf.clone()
+        w = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        v[_MEAN_IDX] = v[_MEAN_IDX] / w
+        return v
