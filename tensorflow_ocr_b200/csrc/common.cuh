@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
+#include <utility>
 
 #include "../../include/plhead.h"
 
@@ -17,6 +19,40 @@ inline int launch_status() {
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   return e == cudaSuccess ? PLH_OK : (int)e;
+}
+
+// Every kernel of the hot chains is launched with programmatic dependent launch (PDL): the next
+// kernel's CTAs are scheduled while the previous kernel drains, and wait at
+// cudaGridDependencySynchronize() (the first statement of each kernel) until the predecessor has
+// completed and flushed.  This removes most of the launch latency between the ~10 small dependent
+// kernels of a head step; PLH_NO_PDL=1 in the environment disables it (A/B measurements).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("PLH_NO_PDL") ? 0 : 1;
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  return e == cudaSuccess ? PLH_OK : (int)e;
+}
+
+// first statement of every PDL-launched kernel
+__device__ __forceinline__ void pdl_wait_and_release() {
+  cudaGridDependencySynchronize();             // predecessor complete, its writes visible
+  cudaTriggerProgrammaticLaunchCompletion();   // let the successor start scheduling
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

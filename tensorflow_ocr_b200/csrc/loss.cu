@@ -102,6 +102,7 @@ score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict_
                   const float* __restrict__ scores, const uint8_t* __restrict__ pos_mask,
                   const uint8_t* __restrict__ neg_mask, int N, uint32_t* __restrict__ keys,
                   int2* __restrict__ counts) {
+  pdl_wait_and_release();
   __shared__ int s_np, s_nn;
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(kSelectThreads, 1)
 ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict__ counts, int ncounts,
                    const int* __restrict__ n_pos_override, int N, int ratio, int keymode, int use_smem,
                    ImageInfo* __restrict__ info, float* __restrict__ thr_out, LossHeader* __restrict__ hdr) {
+  pdl_wait_and_release();
   extern __shared__ __align__(16) uint32_t skeys[];
   __shared__ int s_w[2][32];
   const int b = blockIdx.x;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kCountsThreads)
 ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ pix_lab,
                    const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N,
                    uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr) {
+  pdl_wait_and_release();
   __shared__ int s_c[18];
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -357,6 +360,7 @@ __device__ __forceinline__ void classify(float l, bool& p, bool& n) {
 template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
 __global__ void __launch_bounds__(kMainThreads, 2)
 loss_main_kernel(const MainArgs a, const int B, const int N) {
+  pdl_wait_and_release();
   __shared__ float s_red[kMainThreads / 32][4][5];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
@@ -585,11 +589,13 @@ float prob_to_logit_threshold(float t) {
 }
 
 template <int VARIANT, int TERM>
-static void launch_main(bool grad, bool flags, int grid, cudaStream_t s, const MainArgs& a, int B, int N) {
-  if (grad && flags) loss_main_kernel<VARIANT, TERM, true, true><<<grid, kMainThreads, 0, s>>>(a, B, N);
-  else if (grad) loss_main_kernel<VARIANT, TERM, true, false><<<grid, kMainThreads, 0, s>>>(a, B, N);
-  else if (flags) loss_main_kernel<VARIANT, TERM, false, true><<<grid, kMainThreads, 0, s>>>(a, B, N);
-  else loss_main_kernel<VARIANT, TERM, false, false><<<grid, kMainThreads, 0, s>>>(a, B, N);
+static int launch_main(bool grad, bool flags, int grid, cudaStream_t s, const MainArgs& a, int B, int N) {
+  int rc;
+  if (grad && flags) rc = launch(loss_main_kernel<VARIANT, TERM, true, true>, grid, kMainThreads, 0, s, a, B, N);
+  else if (grad) rc = launch(loss_main_kernel<VARIANT, TERM, true, false>, grid, kMainThreads, 0, s, a, B, N);
+  else if (flags) rc = launch(loss_main_kernel<VARIANT, TERM, false, true>, grid, kMainThreads, 0, s, a, B, N);
+  else rc = launch(loss_main_kernel<VARIANT, TERM, false, false>, grid, kMainThreads, 0, s, a, B, N);
+  return rc;
 }
 
 // K0 + K1
@@ -600,12 +606,11 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
                                   LossHeader* hdr, cudaStream_t s) {
   const int per_image = std::max(1, std::min({(N + kKeysThreads - 1) / kKeysThreads, (kNumSMs * 8 + B - 1) / B,
                                               kKeysMaxCTAsPerImage}));
-  score_keys_kernel<KEYMODE, FROM_SCORES><<<dim3(per_image, B), kKeysThreads, 0, s>>>(pix_logits, pix_lab, scores, pos,
+  int rc = launch(score_keys_kernel<KEYMODE, FROM_SCORES>, dim3(per_image, B), kKeysThreads, 0, s, pix_logits, pix_lab, scores, pos,
                                                                                       neg, N, keys, counts);
-  int rc = launch_status();
   if (rc) return rc;
 #define PLH_SELECT(KPT, SMEM, USE)                                                                                   \
-  ohem_select_kernel<KPT><<<B, kSelectThreads, SMEM, s>>>(keys, counts, per_image, n_pos_override, N, ratio, KEYMODE, \
+  rc = launch(ohem_select_kernel<KPT>, B, kSelectThreads, SMEM, s, keys, counts, per_image, n_pos_override, N, ratio, KEYMODE, \
                                                          USE, info, thr_out, hdr)
   if (N <= kSelectThreads * 4) {
     PLH_SELECT(4, 0, 0);
@@ -625,7 +630,7 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
     PLH_SELECT(0, use_smem ? (size_t)N * 4 : 0, use_smem ? 1 : 0);
   }
 #undef PLH_SELECT
-  return launch_status();
+  return rc;
 }
 
 }  // namespace plh
@@ -678,12 +683,12 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
     const int per_image = std::max(1, std::min((N + kCountsThreads - 1) / kCountsThreads, (kNumSMs * 2 + B - 1) / B));
     const dim3 grid(per_image, B);
     if (p->variant == PLH_VARIANT_MODEL)
-      ohem_counts_kernel<PLH_VARIANT_MODEL><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr);
+      rc = launch(ohem_counts_kernel<PLH_VARIANT_MODEL>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask, hdr);
     else if (p->variant == PLH_VARIANT_POS_ONLY)
-      ohem_counts_kernel<PLH_VARIANT_POS_ONLY><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr);
+      rc = launch(ohem_counts_kernel<PLH_VARIANT_POS_ONLY>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask, hdr);
     else
-      ohem_counts_kernel<PLH_VARIANT_PIXELLINK><<<grid, kCountsThreads, 0, s>>>(keys, pix_lab, link_lab, info, N, mask, hdr);
-    if ((rc = launch_status())) return rc;
+      rc = launch(ohem_counts_kernel<PLH_VARIANT_PIXELLINK>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask, hdr);
+    if (rc) return rc;
   }
   // K3
   {
@@ -699,7 +704,7 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
     const bool g = grad_pix != nullptr, f = decode_flags != nullptr;
     const bool prof = g_prof_n >= 0 && g_prof_n < g_prof_created / 2;
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], s);
-#define PLH_DISPATCH(V, T) launch_main<V, T>(g, f, grid, s, a, B, N)
+#define PLH_DISPATCH(V, T) rc = launch_main<V, T>(g, f, grid, s, a, B, N)
     if (p->term == PLH_TERM_CE) {
       if (p->variant == PLH_VARIANT_MODEL) PLH_DISPATCH(PLH_VARIANT_MODEL, PLH_TERM_CE);
       else if (p->variant == PLH_VARIANT_POS_ONLY) PLH_DISPATCH(PLH_VARIANT_POS_ONLY, PLH_TERM_CE);
@@ -710,7 +715,7 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
       else PLH_DISPATCH(PLH_VARIANT_PIXELLINK, PLH_TERM_FOCAL);
     }
 #undef PLH_DISPATCH
-    if ((rc = launch_status())) return rc;
+    if (rc) return rc;
     if (prof) {
       cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], s);
       ++g_prof_n;
