@@ -63,6 +63,7 @@ size_t decode_workspace_bytes(int B, int H, int W, int K) { return decode_ws_lay
 __global__ void __launch_bounds__(256)
 decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restrict__ link_logits, long long total_px,
                     float tp_logit, float tl_logit, uint16_t* __restrict__ flags, int* __restrict__ n_boxes, int B) {
+  pdl_wait_and_release();
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < B; i += blockDim.x) n_boxes[i] = 0;
@@ -166,6 +167,7 @@ __device__ __forceinline__ void unite_s(int* lab, int a, int b) {
 __global__ void __launch_bounds__(kTW * kTH)
 decode_tile_cc_kernel(const uint16_t* __restrict__ flags, int H, int W, int* __restrict__ parent,
                       int* __restrict__ size, int* __restrict__ n_boxes) {
+  pdl_wait_and_release();
   __shared__ uint16_t sf[kTH + 2][kTW + 2];
   __shared__ int slab[kTW * kTH];
   const int tid = threadIdx.x;
@@ -217,6 +219,7 @@ decode_tile_cc_kernel(const uint16_t* __restrict__ flags, int H, int W, int* __r
 // neighbour in another tile.
 __global__ void __launch_bounds__(256)
 decode_cross_kernel(const uint16_t* __restrict__ flags, int H, int W, int total_px, int* __restrict__ parent) {
+  pdl_wait_and_release();
   const int N = H * W;
   const int stride = gridDim.x * blockDim.x;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
@@ -246,6 +249,7 @@ decode_cross_kernel(const uint16_t* __restrict__ flags, int H, int W, int total_
 __global__ void __launch_bounds__(256)
 decode_flatten_kernel(const uint16_t* __restrict__ flags, int H, int W, long long total_px, int* __restrict__ parent,
                       int* __restrict__ size) {
+  pdl_wait_and_release();
   const int N = H * W;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long start = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(256)
 decode_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int N, int total_px, int min_size, int K,
                     int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes,
                     int* __restrict__ rowmin, int* __restrict__ rowmax, int H) {
+  pdl_wait_and_release();
   const int stride = gridDim.x * blockDim.x;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
     if (parent[g] != g) continue;
@@ -319,6 +324,7 @@ decode_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int 
 __global__ void __launch_bounds__(256)
 decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ size, int H, int W, long long total_px,
                      int K, int32_t* __restrict__ labels, int* __restrict__ rowmin, int* __restrict__ rowmax) {
+  pdl_wait_and_release();
   const int N = H * W;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
@@ -346,6 +352,7 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
                     const int* __restrict__ comp_size, const int* __restrict__ rowmin, const int* __restrict__ rowmax,
                     int H, int W, int K, double sx, double sy, int npad, int32_t* __restrict__ boxes,
                     float* __restrict__ rects, int32_t* __restrict__ comp) {
+  pdl_wait_and_release();
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_n, s_rank;
   const int b = blockIdx.y, slot = blockIdx.x;
@@ -472,23 +479,23 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
     flags = const_cast<uint16_t*>(flags_in);
   } else {
     const int grid = (int)std::min<long long>((total_px * 4 + 255) / 256, kNumSMs * 16);
-    decode_flags_kernel<<<grid, 256, 0, s>>>(pix_logits, link_logits, total_px,
+    rc = launch(decode_flags_kernel, grid, 256, 0, s, pix_logits, link_logits, total_px,
                                              prob_to_logit_threshold(p->pixel_thresh),
                                              prob_to_logit_threshold(p->link_thresh), flags, n_boxes, B);
-    if ((rc = launch_status())) return rc;
+    if (rc) return rc;
   }
-  decode_tile_cc_kernel<<<dim3((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, B), kTW * kTH, 0, s>>>(flags, H, W, parent, size,
+  rc = launch(decode_tile_cc_kernel, dim3((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, B), kTW * kTH, 0, s, flags, H, W, parent, size,
                                                                                                 n_boxes);
-  if ((rc = launch_status())) return rc;
-  decode_cross_kernel<<<grid_px, 256, 0, s>>>(flags, H, W, (int)total_px, parent);
-  if ((rc = launch_status())) return rc;
-  decode_flatten_kernel<<<grid_px, 256, 0, s>>>(flags, H, W, total_px, parent, size);
-  if ((rc = launch_status())) return rc;
-  decode_roots_kernel<<<grid_px, 256, 0, s>>>(parent, size, N, (int)total_px, p->min_size, K, comp_root, comp_size,
+  if (rc) return rc;
+  rc = launch(decode_cross_kernel, grid_px, 256, 0, s, flags, H, W, (int)total_px, parent);
+  if (rc) return rc;
+  rc = launch(decode_flatten_kernel, grid_px, 256, 0, s, flags, H, W, total_px, parent, size);
+  if (rc) return rc;
+  rc = launch(decode_roots_kernel, grid_px, 256, 0, s, parent, size, N, (int)total_px, p->min_size, K, comp_root, comp_size,
                                               n_boxes, rowmin, rowmax, H);
-  if ((rc = launch_status())) return rc;
-  decode_labels_kernel<<<grid_px, 256, 0, s>>>(parent, size, H, W, total_px, K, labels, rowmin, rowmax);
-  if ((rc = launch_status())) return rc;
+  if (rc) return rc;
+  rc = launch(decode_labels_kernel, grid_px, 256, 0, s, parent, size, H, W, total_px, K, labels, rowmin, rowmax);
+  if (rc) return rc;
   {
     const int npad = next_pow2(std::max(2 * H, 32));
     const size_t smem = rect_smem_bytes(npad);
@@ -498,9 +505,9 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
       if (e != cudaSuccess) return (int)e;
       attr_bytes = smem;
     }
-    decode_rects_kernel<<<dim3(K, B), 256, smem, s>>>(n_boxes, comp_root, comp_size, rowmin, rowmax, H, W, K,
+    rc = launch(decode_rects_kernel, dim3(K, B), 256, smem, s, n_boxes, comp_root, comp_size, rowmin, rowmax, H, W, K,
                                                       p->scale_x, p->scale_y, npad, boxes, rects, comp);
-    if ((rc = launch_status())) return rc;
+    if (rc) return rc;
   }
   return PLH_OK;
 }
