@@ -260,23 +260,71 @@ def run_gpu(args):
     ms_total = float(ms.item())
     value = world * B * args.steps / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (loss_main): same loop, direct launches, events around the kernel
+    # ---- roofline of the dominant kernel (loss_main_kernel)
+    # (1) the kernel alone: every input set's workspace is prepared by one full loss call, then the main
+    #     pass is relaunched back to back over the rotating sets (> L2), CUDA events around the whole
+    #     sequence on the launching stream, duration = elapsed / launches;
+    # (2) the same kernel inside the step: events recorded by the library around that launch
+    #     (plh_profile_begin/end); this one also contains the launch latency of an event-bracketed kernel.
     roofline = None
     if rank == 0:
-        nprof = min(args.steps, 4096)
-        _lib.check(lib.plh_profile_begin(nprof), "plh_profile_begin")
-        for i in range(nprof):
+        nbytes = lib.plh_workspace_bytes(_lib.OP_LOSS, B, H, W, 0)
+        wss = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(NSETS)]
+        routs = [{} for _ in range(NSETS)]
+        only = head.LossConfig(main_only=True)
+
+        def loss_call(i, cfg):
+            d = dev_sets[i % NSETS]
+            head.pixellink_loss_raw(d["pix_logits"], d["link_logits"], d["pix_lab"], d["link_lab"], cfg,
+                                    not os.environ.get("BENCH_RF_NOGRAD"), False, None, routs[i % NSETS],
+                                    wss[i % NSETS])
+
+        for i in range(NSETS):
+            loss_call(i, lcfg)
+        for i in range(2 * NSETS):
+            loss_call(i, only)
+        torch.cuda.synchronize()
+        # one graph holding the NSETS relaunches (a Python call per launch would be host-bound at ~20 us)
+        rg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(rg, stream=main_stream):
+            for i in range(NSETS):
+                loss_call(i, only)
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(main_stream)
+        reps = max(1, min(args.steps, 4096) // NSETS)
+        nprof = reps * NSETS
+        for _ in range(3):
+            rg.replay()
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(reps):
+            rg.replay()
+        r1.record()
+        torch.cuda.synchronize()
+        per_launch_s = r0.elapsed_time(r1) * 1e-3 / nprof
+        ref_loss = routs[0]["stats"][0].item()
+
+        _lib.check(lib.plh_profile_begin(min(nprof, 4096)), "plh_profile_begin")
+        for i in range(min(nprof, 4096)):
             step(i)
         tot, n = ctypes.c_float(0), ctypes.c_int(0)
         _lib.check(lib.plh_profile_end(ctypes.byref(tot), ctypes.byref(n)), "plh_profile_end")
+        in_step_us = tot.value * 1e3 / max(1, n.value)
+        assert abs(outs[0]["stats"][0].item() - ref_loss) <= 1e-6 * abs(ref_loss)   # main-only reruns compute the same loss
+
         peak, peak_src = _peaks()
-        per_launch_s = tot.value * 1e-3 / max(1, n.value)
         alg = BYTES_LOSS * PX
         ach = alg / per_launch_s / 1e9
         roofline = {"bound": "hbm", "kernel": "loss_main_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / peak, "traffic": 62.3e6, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": per_launch_s * 1e6,
-                    "launches_timed": int(n.value),
+                    "launches_timed": nprof,
+                    "method": "kernel relaunched alone back to back (CUDA graph of %d launches over the rotating "
+                              "input sets, replayed), CUDA events around the sequence / launches" % NSETS,
+                    "us_per_launch_inside_step_event_bracketed": in_step_us,
+                    "traffic_note": "ncu dram__bytes_read+write per launch (profiles/): 57.2 MB read + 5.2 MB written "
+                                    "to DRAM; the 37.7 MB of gradients are still dirty in the 126 MB L2 at kernel end",
                     "frac_of_nominal_8TBs": ach / 8000.0,
                     "whole_step_GBs": (BYTES_LOSS + BYTES_DECODE_EXTRA) * PX / (ms_total * 1e-3 / args.steps) / 1e9}
     if world > 1:
@@ -286,26 +334,47 @@ def run_gpu(args):
     hres = [{"stats": torch.empty(_lib.STATS_FLOATS + B, dtype=torch.float32).pin_memory(),
              "n_boxes": torch.empty(B, dtype=torch.int32).pin_memory(),
              "boxes": torch.empty((B, dcfg.max_boxes, 4, 2), dtype=torch.int32).pin_memory()} for _ in range(2)]
-    stage = {k: torch.empty_like(dev_sets[0][k]) for k in keys}
-    eout = {}
+    # double-buffered staging: the H2D copy of step i+1 (copy stream) overlaps the head of step i
+    stages = [{k: torch.empty_like(dev_sets[0][k]) for k in keys} for _ in range(2)]
+    eouts = [{}, {}]
+    copy_stream = torch.cuda.Stream(dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step(i):
-        hs = host_sets[i % NSETS]
-        for k in keys:
-            stage[k].copy_(hs[k], non_blocking=True)
-        head.loss_and_decode_raw(stage["pix_logits"], stage["link_logits"], stage["pix_lab"], stage["link_lab"], lcfg,
-                                 dcfg, eout, want_rects=False)
-        hr = hres[i % 2]
+    def e2e_copy(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])          # the head of step i-2 has finished reading this buffer
+            hs = host_sets[i % NSETS]
+            for k in keys:
+                stages[j][k].copy_(hs[k], non_blocking=True)
+            copied[j].record(copy_stream)
+
+    def e2e_step(i, last):
+        j = i % 2
+        if not last:
+            e2e_copy(i + 1)
+        main_stream.wait_event(copied[j])
+        st = stages[j]
+        head.loss_and_decode_raw(st["pix_logits"], st["link_logits"], st["pix_lab"], st["link_lab"], lcfg, dcfg,
+                                 eouts[j], want_rects=False)
+        consumed[j].record(main_stream)
+        hr = hres[j]
         for k in ("stats", "n_boxes", "boxes"):
-            hr[k].copy_(eout[k], non_blocking=True)
+            hr[k].copy_(eouts[j][k], non_blocking=True)
 
     e2e_steps = max(3, min(args.steps, 200))
+    for j in range(2):
+        consumed[j].record(main_stream)
+    e2e_copy(0)
     for i in range(3):
-        e2e_step(i)
+        e2e_step(i, i == 2)
     barrier()
+    # timed: the copy of step 0 is issued inside the region
     e0.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
+    e2e_copy(3)
+    for i in range(3, 3 + e2e_steps):
+        e2e_step(i, i == 2 + e2e_steps)
     e1.record()
     barrier()
     ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -314,7 +383,7 @@ def run_gpu(args):
     e2e_value = world * B * e2e_steps / (float(ems.item()) * 1e-3)
     h2d = sum(host_sets[0][k].numel() * host_sets[0][k].element_size() for k in keys)
     d2h = sum(v.numel() * v.element_size() for v in hres[0].values())
-    assert np.isfinite(hres[(e2e_steps - 1) % 2]["stats"][0].item())
+    assert np.isfinite(hres[(2 + e2e_steps) % 2]["stats"][0].item())
 
     clocks = sampler.result()
     launches = torch.tensor([launches_per_step[0] * args.steps], device=dev, dtype=torch.int64)
@@ -335,7 +404,7 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "note": "pinned host logits+labels -> device, fused head, loss stats + boxes -> pinned host"},
+                    "note": "pinned host logits+labels -> device (double-buffered, copy stream overlaps the previous step), head step, loss stats + boxes -> pinned host"},
             "gpu_launches": int(launches.item()),
             "roofline": roofline,
         }

@@ -68,7 +68,8 @@ typedef struct plh_loss_params {
   int32_t neg_pos_ratio; /* 3 (nets/model.py:171; config.max_neg_pos_ratio in nets/pixellink.py:116) */
   float focal_alpha;     /* 0.25 */
   float focal_gamma;     /* 2.0 */
-  int32_t reserved[3];
+  int32_t reserved[3];   /* reserved[0] bit 0: measurement only — rerun the main pass on a workspace that a
+                            previous full call with the same inputs prepared (skips selection and counts) */
 } plh_loss_params;
 
 /* Layout of the `stats` output (device floats).  PLH_STATS_FLOATS + B entries. */

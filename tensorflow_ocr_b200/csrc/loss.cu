@@ -537,6 +537,11 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
       st[PLH_ST_TOTAL] = (float)link_total + 2.f * L_pix;  // model.py:261 / pixellink.py:170,254
     }
     if (lane >= 14) st[32 + lane] = 0.f;  // stats[46..63] reserved
+    // leave the accumulators clean, so that this kernel can be relaunched on the same prepared
+    // workspace (plh_loss_params.reserved[0] = 1: measurement of the main pass alone)
+    __syncwarp();
+    if (lane < 17) a.hdr->sums[lane] = 0.0;
+    if (lane == 0) a.hdr->ticket = 0u;
   }
 }
 
@@ -663,9 +668,11 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   int2* counts = (int2*)(ws + l.counts);
   const int total_px = B * N;
   cudaError_t e;
-  int rc;
+  int rc = PLH_OK;
+  const bool main_only = (p->reserved[0] & 1) != 0;  // K0-K2 already ran on this workspace
   // K0 + K1 (not needed for the positives-only variant: there is no mining, vgg16 :265)
-  if (p->variant == PLH_VARIANT_MODEL)
+  if (main_only) {
+  } else if (p->variant == PLH_VARIANT_MODEL)
     rc = launch_keys_and_select<KEYS_MODEL, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
                                                    p->neg_pos_ratio, keys, counts, info, stats + PLH_ST_THR, hdr, s);
   else if (p->variant == PLH_VARIANT_PIXELLINK)
@@ -679,7 +686,7 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   }
   if (rc) return rc;
   // K2
-  {
+  if (!main_only) {
     const int per_image = std::max(1, std::min((N + kCountsThreads - 1) / kCountsThreads, (kNumSMs * 2 + B - 1) / B));
     const dim3 grid(per_image, B);
     if (p->variant == PLH_VARIANT_MODEL)

@@ -32,9 +32,12 @@ class LossConfig:
     neg_pos_ratio: int = 3        # nets/model.py:171
     focal_alpha: float = 0.25     # Lin et al. 2017 (not in the reference)
     focal_gamma: float = 2.0
+    main_only: bool = False       # measurement hook: rerun the main pass on an already prepared workspace
 
     def c_struct(self):
-        return _lib.LossParams(self.variant, self.term, self.neg_pos_ratio, self.focal_alpha, self.focal_gamma)
+        p = _lib.LossParams(self.variant, self.term, self.neg_pos_ratio, self.focal_alpha, self.focal_gamma)
+        p.reserved[0] = 1 if self.main_only else 0
+        return p
 
 
 @dataclass(frozen=True)
@@ -124,7 +127,8 @@ def _check_head_shapes(pix_logits, link_logits, pix_lab, link_lab):
 
 def pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, cfg: LossConfig = LossConfig(),
                        want_grad: bool = True, want_mask: bool = False,
-                       decode: Optional[DecodeConfig] = None, out: Optional[dict] = None) -> dict:
+                       decode: Optional[DecodeConfig] = None, out: Optional[dict] = None,
+                       workspace: Optional[torch.Tensor] = None) -> dict:
     """Fused PixelLink loss fwd+bwd on CUDA tensors (plh_pixellink_loss).
 
     Returns device tensors: stats [64+B], grad_pixel, grad_link (if want_grad),
@@ -149,7 +153,7 @@ def pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, cfg: LossConf
     gl = buf("grad_link", (B, H, W, 16), torch.float32) if want_grad else None
     mask = buf("ohem_mask", (B, H, W), torch.uint8) if want_mask else None
     flags = buf("flags", (B, H, W), torch.int16) if decode is not None else None
-    ws = _workspace(_lib.OP_LOSS, B, H, W, 0, dev)
+    ws = workspace if workspace is not None else _workspace(_lib.OP_LOSS, B, H, W, 0, dev)
     lp = cfg.c_struct()
     dp = decode.c_struct() if decode is not None else None
     with torch.cuda.device(dev):
