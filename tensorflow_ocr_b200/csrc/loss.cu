@@ -323,30 +323,29 @@ struct MainArgs {
 
 // One 2-way softmax term.  Returns the per-element loss term and d(term)/d(logit 1);
 // d/d(logit 0) is its negative.  Fast intrinsics: nothing here feeds a mask decision.
+//   z = x_other - x_label;  CE = softplus(z) = max(z,0) + log(1 + exp(-|z|));
+//   d CE / d logit1 = +sigmoid(z) for label 0, -sigmoid(z) for label 1.
 template <int TERM>
 __device__ __forceinline__ void term_and_grad(float x0, float x1, bool lab1, float alpha, float gamma,
                                               float& term, float& g1) {
   const float d = x1 - x0;
-  const float ad = fabsf(d);
-  const float e = __expf(-ad);
+  const float z = lab1 ? -d : d;
+  const float e = __expf(-fabsf(z));
   const float den = 1.f + e;
   const float r = __fdividef(1.f, den);
-  const float qbig = r, qsmall = e * r;
-  const bool one_is_max = d >= 0.f;
-  const float q1 = one_is_max ? qbig : qsmall;
-  // CE = log(sum exp(x - max)) - (x_label - max)
-  const float ce = __logf(den) + ((lab1 == one_is_max) ? 0.f : ad);
+  const float sig = z >= 0.f ? r : e * r;         // sigmoid(z) = 1 - p_label
+  const float ce = fmaxf(z, 0.f) + __logf(den);
   if (TERM == PLH_TERM_CE) {
     term = ce;
-    g1 = q1 - (lab1 ? 1.f : 0.f);
+    g1 = lab1 ? -sig : sig;
   } else {
-    const float pt = lab1 ? q1 : (one_is_max ? qsmall : qbig);
+    const float pt = z >= 0.f ? e * r : r;        // p_label = sigmoid(-z)
     const float logpt = -ce;
     const float at = lab1 ? alpha : 1.f - alpha;
-    const float om = 1.f - pt;
+    const float om = sig;                          // 1 - p_label
     const float mod = (gamma == 2.f) ? om * om : __powf(om, gamma);
     term = -(at * mod * logpt);
-    const float gt = at * mod * (gamma * pt * logpt - om);
+    const float gt = at * mod * (gamma * pt * logpt - om);   // d/d x_label
     g1 = lab1 ? gt : -gt;
   }
 }
@@ -357,6 +356,13 @@ __device__ __forceinline__ void classify(float l, bool& p, bool& n) {
   else { const int li = (int)l; p = li == 1, n = li == 0; }
 }
 
+// Work unit = 16 consecutive pixels, handled by one warp:
+//   link phase : 2 iterations x 32 lanes, lane = (pixel-in-iteration, quarter j): 128-bit loads of the
+//                two link directions 2j, 2j+1 of that pixel (logits) + 64-bit load of their labels;
+//   pixel phase: lanes 0..15 own one pixel each (lanes 16..31 shadow them; same addresses, no extra
+//                traffic) — the pixel term is computed once per pixel instead of once per quarter.
+// Units are dealt round-robin to the warps of the persistent grid (16-pixel granularity keeps the
+// per-warp imbalance at ~1%); two units are in flight per trip for memory-level parallelism.
 template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
 __global__ void __launch_bounds__(kMainThreads, 2)
 loss_main_kernel(const MainArgs a, const int B, const int N) {
@@ -389,83 +395,105 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
   }
 
   float sp[2] = {0.f, 0.f}, sn[2] = {0.f, 0.f}, spx = 0.f;
-  const long long Q = a.total_px * 4;
-  const long long stride = (long long)gridDim.x * kMainThreads;
+  const int total_px = (int)a.total_px;
+  const int nunits = (total_px + 15) >> 4;
+  const int nwarps = gridDim.x * (kMainThreads / 32);
   const float4* ll4 = reinterpret_cast<const float4*>(a.link_logits);
   const float2* lab2 = reinterpret_cast<const float2*>(a.link_lab);
   const float2* pl2 = reinterpret_cast<const float2*>(a.pix_logits);
+  const int pl_lane = lane & 15;        // pixel-phase lane -> pixel of the unit
+  const int q_pix = lane >> 2;          // link-phase lane -> pixel of the iteration (0..7)
 
   constexpr int U = 2;
-  // warp-uniform trip count (the quad shuffles below need every lane in the loop)
-  for (long long w0 = (long long)blockIdx.x * kMainThreads + (tid & ~31); w0 < Q; w0 += stride * U) {
-    const long long q0 = w0 + lane;
-    float4 L[U];
-    float2 LB[U], P[U];
-    float PLB[U];
-    uint8_t MK[U];
+  for (int u0 = blockIdx.x * (kMainThreads / 32) + warp; u0 < nunits; u0 += nwarps * U) {
+    float4 L[U][2];
+    float2 LB[U][2], P[U];
+    float PLB[U], MF[U];
+    // ---- all loads of the trip first
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long q = q0 + u * stride;
-      L[u] = make_float4(0.f, 0.f, 0.f, 0.f), LB[u] = make_float2(0.f, 0.f), P[u] = make_float2(0.f, 0.f);
-      PLB[u] = 0.f, MK[u] = 0;
-      if (q < Q) {
-        const long long px = q >> 2;
-        L[u] = ldg_stream4(ll4 + q);
-        LB[u] = ldg_stream2(lab2 + q);
-        P[u] = __ldg(pl2 + px);
-        PLB[u] = __ldg(a.pix_lab + px);
-        MK[u] = (VARIANT == PLH_VARIANT_PIXELLINK) ? (uint8_t)1 : __ldg(a.mask + px);
+    for (int uu = 0; uu < U; ++uu) {
+      const int u = u0 + uu * nwarps;
+      const int px0 = u << 4;  // first pixel of the unit (may be >= total_px for the shadow unit of the last trip)
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int px = px0 + it * 8 + q_pix;
+        L[uu][it] = make_float4(0.f, 0.f, 0.f, 0.f), LB[uu][it] = make_float2(0.f, 0.f);
+        if (px < total_px) {
+          const size_t q = (size_t)px * 4 + j;
+          L[uu][it] = ldg_stream4(ll4 + q);
+          LB[uu][it] = ldg_stream2(lab2 + q);
+        }
+      }
+      const int pp = px0 + pl_lane;
+      P[uu] = make_float2(0.f, 0.f), PLB[uu] = 0.f, MF[uu] = 0.f;
+      if (pp < total_px) {
+        P[uu] = __ldg(pl2 + pp);
+        PLB[uu] = __ldg(a.pix_lab + pp);
+        MF[uu] = (VARIANT == PLH_VARIANT_PIXELLINK) ? 1.f : (float)__ldg(a.mask + pp);
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long q = q0 + u * stride;
-      const bool valid = q < Q;  // Q % 4 == 0 and strides are multiples of 4: a quad is valid as a whole
-      const long long px = q >> 2;
-      const float Mf = (float)MK[u];
-      // ---- two link directions
+    for (int uu = 0; uu < U; ++uu) {
+      const int px0 = (u0 + uu * nwarps) << 4;
+      // ---- pixel phase: one pixel per lane (0..15)
+      const int pp = px0 + pl_lane;
       {
-        bool p0, n0, p1, n1;
-        classify<VARIANT>(LB[u].x, p0, n0);
-        classify<VARIANT>(LB[u].y, p1, n1);
-        float t0, g0, t1, g1;
-        term_and_grad<TERM>(L[u].x, L[u].y, p0, a.alpha, a.gamma, t0, g0);
-        term_and_grad<TERM>(L[u].z, L[u].w, p1, a.alpha, a.gamma, t1, g1);
-        if (valid) {
-          const float w0 = Mf * (p0 ? invP[0] : (n0 ? invN[0] : 0.f));
-          const float w1 = Mf * (p1 ? invP[1] : (n1 ? invN[1] : 0.f));
-          sp[0] += p0 ? t0 * Mf : 0.f, sn[0] += n0 ? t0 * Mf : 0.f;
-          sp[1] += p1 ? t1 * Mf : 0.f, sn[1] += n1 ? t1 * Mf : 0.f;
-          const float a0 = w0 * g0, a1 = w1 * g1;
-          if (GRAD) stg_stream4(reinterpret_cast<float4*>(a.grad_link) + q, make_float4(-a0, a0, -a1, a1));
-        }
-      }
-      // ---- pixel term (quad-redundant; lane j == 0 owns the store and the sum)
-      {
-        bool pp, pn;
-        classify<VARIANT>(PLB[u], pp, pn);
+        bool ppos, pneg;
+        classify<VARIANT>(PLB[uu], ppos, pneg);
         float t, g1;
-        term_and_grad<TERM>(P[u].x, P[u].y, pp, a.alpha, a.gamma, t, g1);
-        if (valid && j == 0) {
-          spx += t * Mf;
+        term_and_grad<TERM>(P[uu].x, P[uu].y, ppos, a.alpha, a.gamma, t, g1);
+        if (lane < 16 && pp < total_px) {
+          spx += t * MF[uu];
           if (GRAD) {
-            const float gp = (Mf * pix_scale) * g1;
-            stg_stream2(reinterpret_cast<float2*>(a.grad_pix) + px, make_float2(-gp, gp));
+            const float gp = (MF[uu] * pix_scale) * g1;
+            stg_stream2(reinterpret_cast<float2*>(a.grad_pix) + pp, make_float2(-gp, gp));
           }
         }
       }
+      unsigned lbits[2] = {0u, 0u};
+      // ---- link phase: two iterations of 8 pixels x 4 quarters
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int px = px0 + it * 8 + q_pix;
+        const float Mf = __shfl_sync(0xffffffffu, MF[uu], it * 8 + q_pix);  // the pixel's selected-mask weight
+        bool p0, n0, p1, n1;
+        classify<VARIANT>(LB[uu][it].x, p0, n0);
+        classify<VARIANT>(LB[uu][it].y, p1, n1);
+        float t0, g0, t1, g1;
+        term_and_grad<TERM>(L[uu][it].x, L[uu][it].y, p0, a.alpha, a.gamma, t0, g0);
+        term_and_grad<TERM>(L[uu][it].z, L[uu][it].w, p1, a.alpha, a.gamma, t1, g1);
+        if (px < total_px) {
+          const float tm0 = t0 * Mf, tm1 = t1 * Mf;
+          sp[0] += p0 ? tm0 : 0.f, sn[0] += n0 ? tm0 : 0.f;
+          sp[1] += p1 ? tm1 : 0.f, sn[1] += n1 ? tm1 : 0.f;
+          if (GRAD) {
+            const float a0 = (Mf * (p0 ? invP[0] : (n0 ? invN[0] : 0.f))) * g0;
+            const float a1 = (Mf * (p1 ? invP[1] : (n1 ? invN[1] : 0.f))) * g1;
+            stg_stream4(reinterpret_cast<float4*>(a.grad_link) + ((size_t)px * 4 + j), make_float4(-a0, a0, -a1, a1));
+          }
+        }
+        if (FLAGS) {
+          unsigned bits = ((L[uu][it].y - L[uu][it].x) > a.tl_logit ? 1u : 0u) << (2 * j) |
+                          ((L[uu][it].w - L[uu][it].z) > a.tl_logit ? 1u : 0u) << (2 * j + 1);
+          bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+          bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+          lbits[it] = bits;  // all four lanes of the quad hold the pixel's 8 link bits
+        }
+      }
       if (FLAGS) {
-        unsigned bits = ((L[u].y - L[u].x) > a.tl_logit ? 1u : 0u) << (2 * j) |
-                        ((L[u].w - L[u].z) > a.tl_logit ? 1u : 0u) << (2 * j + 1);
-        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-        if (valid && j == 0)
-          a.flags[px] = (uint16_t)(bits | (((P[u].y - P[u].x) > a.tp_logit ? 1u : 0u) << 8));
+        // pixel-phase lane t (< 16) owns pixel t = it * 8 + quad: fetch that quad's bits of iteration it
+        const unsigned b0 = __shfl_sync(0xffffffffu, lbits[0], (lane & 7) << 2);
+        const unsigned b1 = __shfl_sync(0xffffffffu, lbits[1], (lane & 7) << 2);
+        if (lane < 16 && pp < total_px)
+          a.flags[pp] = (uint16_t)(((lane & 8) ? b1 : b0) | (((P[uu].y - P[uu].x) > a.tp_logit ? 1u : 0u) << 8));
       }
     }
   }
 
-  // ---- block reduction of the 17 sums (lanes with equal j hold the same directions)
+  // ---- block reduction of the 17 sums (lanes with equal j hold the same directions; the pixel sum is
+  // spread over all lanes, so it is first folded across the quad)
+  spx += __shfl_xor_sync(0xffffffffu, spx, 1);
+  spx += __shfl_xor_sync(0xffffffffu, spx, 2);
 #pragma unroll
   for (int o = 4; o <= 16; o <<= 1) {
     sp[0] += __shfl_xor_sync(0xffffffffu, sp[0], o);
