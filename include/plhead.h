@@ -216,6 +216,17 @@ PLH_API int plh_east_loss(const float* score_gt, const float* score_pred, const 
                   const float* mask, long long M, float* out, float* grad_score, float* grad_geo,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Locality-aware NMS — NOT in the reference; restated from upstream argman/EAST
+ * locality_aware_nms.nms_locality: row-major fold merging consecutive overlapping boxes by
+ * score-weighted averaging, then standard NMS.  Parity unpinned (checked against oracle/east.py).
+ *  polys [total,9] fp64 (8 coords + score) — the boxes of image b are rows offsets[b]..offsets[b+1]
+ *  out   [total,9] fp64: survivors of image b start at row offsets[b], n_out[b] of them, by descending score
+ *  workspace >= align256(total*72) + total*4 + 256 bytes
+ */
+PLH_API int plh_lanms(const double* polys, const int32_t* offsets, int B, int total, double thres, double* out,
+                      int32_t* n_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- housekeeping ---- */
 /* `K` = plh_decode_params.max_boxes for the decode ops, ignored otherwise */
 PLH_API size_t plh_workspace_bytes(int op, int B, int H, int W, int K);

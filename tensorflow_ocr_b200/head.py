@@ -20,7 +20,7 @@ from . import _lib
 
 __all__ = ["DecodeConfig", "LossConfig", "pixellink_loss_raw", "decode_raw", "loss_and_decode_raw",
            "ohnm_batch_raw", "dice_raw", "dice_head_raw", "east_loss_raw", "restore_rectangle_raw",
-           "pixel_detect_raw", "min_area_boxes_raw", "to_device", "launch_count"]
+           "pixel_detect_raw", "min_area_boxes_raw", "lanms_raw", "to_device", "launch_count"]
 
 
 # ----------------------------------------------------------------------------- configuration
@@ -350,6 +350,23 @@ def east_loss_raw(score_gt, score_pred, geo_gt, geo_pred, mask, want_grad=True):
                                _p(gs), _p(gg), _p(ws), ws.numel(), _stream(dev))
     _lib.check(rc, "plh_east_loss")
     return outv, gs, gg
+
+
+def lanms_raw(polys: torch.Tensor, offsets: torch.Tensor, thres: float = 0.3):
+    """plh_lanms: polys fp64 [total,9], offsets int32 [B+1] -> (out fp64 [total,9], n_out int32 [B])."""
+    lib = _lib.load()
+    dev = polys.device
+    _require_gpu(dev)
+    total = polys.shape[0]
+    Bn = offsets.numel() - 1
+    out = torch.empty_like(polys)
+    n_out = torch.zeros((Bn,), dtype=torch.int32, device=dev)
+    ws = torch.empty(((total * 72 + 255) // 256) * 256 + total * 4 + 256, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_lanms(_p(polys), _p(offsets), Bn, total, float(thres), _p(out), _p(n_out), _p(ws), ws.numel(),
+                           _stream(dev))
+    _lib.check(rc, "plh_lanms")
+    return out, n_out
 
 
 def restore_rectangle_raw(origin, geometry, want_index=False):

@@ -88,3 +88,39 @@ def test_restore_rectangle(golden_dir, cuda_dev):
     geom = np.concatenate([rng.uniform(1, 80, (N, 4)), rng.uniform(-0.7, 0.7, (N, 1))], 1).astype(np.float32)
     ref = E.restore_rectangle_rbox(origin, geom)
     assert np.allclose(icdar.restore_rectangle(origin, geom), ref, rtol=1e-6, atol=1e-4)
+
+
+def _east_boxes(rng, n_groups, per_group):
+    """Row-major-like stream of slightly jittered boxes: consecutive boxes of a group overlap."""
+    polys = []
+    for g in range(n_groups):
+        c = rng.uniform(50, 450, 2)
+        w, h = rng.uniform(30, 120), rng.uniform(10, 30)
+        a = rng.uniform(-0.5, 0.5)
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        base = (np.array([[-w, -h], [w, -h], [w, h], [-w, h]]) / 2) @ R.T + c
+        for _ in range(per_group):
+            q = base + rng.normal(0, 1.0, (4, 2))
+            polys.append(np.concatenate([q.reshape(-1), [rng.uniform(0.8, 1.0)]]))
+    return np.asarray(polys, np.float64)
+
+
+def test_lanms_vs_oracle(cuda_dev):
+    """E3 — parity unpinned (not in the reference; restated from upstream EAST)."""
+    from oracle import east as E
+    from tensorflow_ocr_b200 import locality_aware_nms as L
+    rng = np.random.default_rng(6)
+    for trial in range(4):
+        polys = _east_boxes(rng, int(rng.integers(1, 12)), int(rng.integers(1, 30)))
+        ref = E.nms_locality(polys, 0.3)
+        got = L.nms_locality(polys, 0.3)
+        assert got.shape == ref.shape
+        assert np.allclose(got, ref, rtol=1e-9, atol=1e-9)
+    assert L.nms_locality(np.zeros((0, 9))).shape == (0, 9)
+    # batched, ragged (one empty image)
+    sets = [_east_boxes(rng, 3, 10), np.zeros((0, 9)), _east_boxes(rng, 5, 4)]
+    offs = np.cumsum([0] + [len(s) for s in sets]).astype(np.int32)
+    res = L.nms_locality_batch(np.concatenate(sets), offs, 0.3)
+    for s, r in zip(sets, res):
+        ref = E.nms_locality(s, 0.3) if len(s) else np.zeros((0, 9))
+        assert r.shape == ref.shape and np.allclose(r, ref, rtol=1e-9, atol=1e-9)

@@ -44,6 +44,28 @@ def test_decode_vs_oracle(family, B, H, W, cuda_dev):
     assert nb > 0 or H < 40
 
 
+def test_decode_icdar_shaped_2s_map(cuda_dev):
+    """BASELINE config 3a map size: 768x1280 network input at 2s -> 384x640 maps, box scale (2.0, 1.875)."""
+    from tensorflow_ocr_b200 import synth
+    inp = synth.make_batch(15, 2, 384, 640, "G")
+    out = _decode(inp, scale=(2.0, 1.875), max_boxes=512)
+    assert _check(inp, out, scale=(2.0, 1.875)) > 0
+
+
+def test_decode_pixellink_api(cuda_dev):
+    """The named drop-in: numpy in -> (labels, boxes, counts)."""
+    from oracle import decode as D
+    from tensorflow_ocr_b200 import synth
+    from tensorflow_ocr_b200.decode import decode_pixellink
+    inp = synth.make_batch(16, 3, 64, 80, "G")
+    labels, boxes, counts = decode_pixellink(inp["pix_logits"], inp["link_logits"])
+    for b in range(3):
+        lab, bx, sizes, _ = D.decode_pixellink(inp["pix_logits"][b], inp["link_logits"][b])
+        assert np.array_equal(labels[b], lab) and np.array_equal(boxes[b], bx) and np.array_equal(counts[b], sizes)
+    l1, b1, c1 = decode_pixellink(inp["pix_logits"][0], inp["link_logits"][0])
+    assert np.array_equal(l1, labels[0]) and np.array_equal(b1, boxes[0])
+
+
 def test_decode_variants(cuda_dev):
     """full-res script constants (test_pixellink.py:177,209-215): min_size 200, no scaling;
     and a 2s configuration (scale 2.0, 1.875)."""

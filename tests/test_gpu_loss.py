@@ -57,7 +57,7 @@ def test_model_loss_golden_nan(golden_dir, cuda_dev):
 
 
 @pytest.mark.parametrize("B,H,W,edge", [(1, 128, 128, False), (5, 24, 40, True), (8, 64, 64, True), (3, 37, 53, True),
-                                        (2, 240, 240, False)])
+                                        (2, 240, 240, False), (4, 192, 192, True), (2, 96, 200, False)])
 def test_model_loss_vs_oracle(B, H, W, edge, cuda_dev):
     from oracle import pixellink_loss as O
     from tensorflow_ocr_b200 import synth
