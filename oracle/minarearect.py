@@ -70,7 +70,7 @@ def _sklansky(pts, order, start, end, nsign, sign2):
     return stack[:stacksize]
 
 
-def convex_hull_cv(points, clockwise=False):
+def convex_hull_cv(points, clockwise=False, index_shift=True):
     """cv::convexHull(points, clockwise, returnPoints=true) on int points.
 
     ``points`` [n,2] integer (x,y).  Returns hull indices into ``points`` in
@@ -121,7 +121,7 @@ def convex_hull_cv(points, clockwise=False):
         hull.append(order[br[i]])
     nout = len(hull)
     # cyclic shift towards a monotone index sequence
-    if nout >= 3:
+    if nout >= 3 and index_shift:
         min_idx = max_idx = 0
         lt = 0
         broke = False
@@ -154,6 +154,43 @@ def convex_hull_cv(points, clockwise=False):
                     j = nj
                 if ok:
                     hull = tmp
+    return hull
+
+
+def convex_hull_giftwrap(points):
+    """The same hull as ``convex_hull_cv(points, clockwise=False, index_shift=False)`` for DISTINCT
+    points, computed without the sequential Sklansky scans (this is what the CUDA decode uses,
+    csrc/rect.cuh): start at the lexicographic maximum (x, then y); the successor of p is the point q
+    with every other point on the clockwise side of p->q in (x, y-down) coordinates, the farthest
+    one among collinear candidates."""
+    pts = [(int(p[0]), int(p[1])) for p in points]
+    n = len(pts)
+    if n == 1:
+        return [0]
+    start = max(range(n), key=lambda i: (pts[i][0], pts[i][1]))
+
+    def succ(i):
+        best = -1
+        for j in range(n):
+            if j == i:
+                continue
+            if best < 0:
+                best = j
+                continue
+            ax, ay = pts[best][0] - pts[i][0], pts[best][1] - pts[i][1]
+            bx, by = pts[j][0] - pts[i][0], pts[j][1] - pts[i][1]
+            c = ax * by - ay * bx
+            if c < 0 or (c == 0 and (ax * bx + ay * by) > 0 and bx * bx + by * by > ax * ax + ay * ay):
+                best = j
+        return best
+
+    hull, cur = [start], start
+    while True:
+        nx = succ(cur)
+        if nx == start or len(hull) > n:
+            break
+        hull.append(nx)
+        cur = nx
     return hull
 
 

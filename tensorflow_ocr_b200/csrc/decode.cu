@@ -347,65 +347,79 @@ decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ siz
 }
 
 // ------------------------------------------------------------------ D5: one CTA per component
+// Persistent grid: the components of the whole batch form one work list (image-major); CTA c takes
+// items c, c + gridDim.x, ...  (a grid of B x K CTAs would be ~95% empty CTAs that still have to be
+// scheduled ahead of the real ones).
 __global__ void __launch_bounds__(256)
 decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ comp_root,
                     const int* __restrict__ comp_size, const int* __restrict__ rowmin, const int* __restrict__ rowmax,
-                    int H, int W, int K, double sx, double sy, int npad, int32_t* __restrict__ boxes,
+                    int B, int H, int W, int K, double sx, double sy, int npad, int32_t* __restrict__ boxes,
                     float* __restrict__ rects, int32_t* __restrict__ comp) {
   pdl_wait_and_release();
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int s_n, s_rank;
-  const int b = blockIdx.y, slot = blockIdx.x;
-  const int nb = min(n_boxes[b], K);
-  if (slot >= nb) return;
+  __shared__ int s_n, s_rank, s_b, s_slot;
   RectSmem S = rect_carve(smem, npad);
-  const size_t rowbase = ((size_t)b * K + slot) * H;
-  if (threadIdx.x == 0) s_n = 0, s_rank = 0;
-  for (int i = threadIdx.x; i < npad; i += blockDim.x) S.keys[i] = ~0ull;
-  __syncthreads();
-  const int root = comp_root[(size_t)b * K + slot];
-  // output position = rank of this component's label among the image's kept components
-  {
-    int r = 0;
-    for (int j = threadIdx.x; j < nb; j += blockDim.x) r += comp_root[(size_t)b * K + j] < root;
-    r = __reduce_add_sync(0xffffffffu, r);
-    if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_rank, r);
-  }
-  // candidates: (minx, y) and (maxx, y) of every occupied row; input index = row-major order
-  // (test_pixellink_fast.py:194-197: x*scale_x, y*scale_y assigned into an int64 array -> trunc)
-  const int y0 = root / W;  // the component's first row: its minimum pixel index lives there
-  for (int y = y0 + threadIdx.x; y < H; y += blockDim.x) {
-    const int mn = rowmin[rowbase + y], mx = rowmax[rowbase + y];
-    if (mx >= 0) {
-      const int py = (int)((double)y * sy);
-      const int pos = atomicAdd(&s_n, mn == mx ? 1 : 2);
-      S.keys[pos] = make_key((int)((double)mn * sx), py, 2 * y);
-      if (mn != mx) S.keys[pos + 1] = make_key((int)((double)mx * sx), py, 2 * y + 1);
+  for (int item = blockIdx.x;; item += gridDim.x) {
+    // locate item in the image-major list (B is small: one thread walks the counts)
+    if (threadIdx.x == 0) {
+      int acc = 0, bb = -1, sl = 0;
+      for (int i = 0; i < B; ++i) {
+        const int nb = min(n_boxes[i], K);
+        if (item < acc + nb) {
+          bb = i, sl = item - acc;
+          break;
+        }
+        acc += nb;
+      }
+      s_b = bb, s_slot = sl, s_n = 0, s_rank = 0;
     }
-  }
-  __syncthreads();
-  const int total = s_n;
-  const int rank = s_rank;
-  // sort only as many as needed (power of two >= total)
-  int nsort = 32;
-  while (nsort < total) nsort <<= 1;
-  bitonic_sort(S.keys, nsort);
-  int box[8];
-  float rect[5];
-  min_area_box_sorted(S, total, npad, box, rect);
-  if (threadIdx.x == 0) {
-    int32_t* ob = boxes + ((size_t)b * K + rank) * 8;
+    __syncthreads();
+    const int b = s_b, slot = s_slot;
+    if (b < 0) return;
+    const int nb = min(n_boxes[b], K);
+    const size_t rowbase = ((size_t)b * K + slot) * H;
+    const int root = comp_root[(size_t)b * K + slot];
+    // output position = rank of this component's label among the image's kept components
+    {
+      int r = 0;
+      for (int j = threadIdx.x; j < nb; j += blockDim.x) r += comp_root[(size_t)b * K + j] < root;
+      r = __reduce_add_sync(0xffffffffu, r);
+      if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_rank, r);
+    }
+    // candidates: (minx, y) and (maxx, y) of every occupied row; input index = row-major order
+    // (test_pixellink_fast.py:194-197: x*scale_x, y*scale_y assigned into an int64 array -> trunc).
+    // Scales >= 1 keep the candidates distinct, so the sort-free hull applies.
+    const int y0 = root / W;  // the component's first row: its minimum pixel index lives there
+    for (int y = y0 + threadIdx.x; y < H; y += blockDim.x) {
+      const int mn = rowmin[rowbase + y], mx = rowmax[rowbase + y];
+      if (mx >= 0) {
+        const int py = (int)((double)y * sy);
+        const int pos = atomicAdd(&s_n, mn == mx ? 1 : 2);
+        S.X[pos] = (int)((double)mn * sx), S.Y[pos] = py, S.I[pos] = 2 * y;
+        if (mn != mx) S.X[pos + 1] = (int)((double)mx * sx), S.Y[pos + 1] = py, S.I[pos + 1] = 2 * y + 1;
+      }
+    }
+    __syncthreads();
+    const int total = s_n;
+    const int rank = s_rank;
+    int box[8];
+    float rect[5];
+    min_area_box_distinct(S, total, box, rect);
+    if (threadIdx.x == 0) {
+      int32_t* ob = boxes + ((size_t)b * K + rank) * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ob[i] = box[i];
-    if (rects) {
-      float* orc = rects + ((size_t)b * K + rank) * 5;
+      for (int i = 0; i < 8; ++i) ob[i] = box[i];
+      if (rects) {
+        float* orc = rects + ((size_t)b * K + rank) * 5;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) orc[i] = rect[i];
+        for (int i = 0; i < 5; ++i) orc[i] = rect[i];
+      }
+      if (comp) {
+        comp[((size_t)b * K + rank) * 2] = root;
+        comp[((size_t)b * K + rank) * 2 + 1] = comp_size[(size_t)b * K + slot];
+      }
     }
-    if (comp) {
-      comp[((size_t)b * K + rank) * 2] = root;
-      comp[((size_t)b * K + rank) * 2 + 1] = comp_size[(size_t)b * K + slot];
-    }
+    __syncthreads();  // shared state is reused by the next item
   }
 }
 
@@ -505,7 +519,8 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
       if (e != cudaSuccess) return (int)e;
       attr_bytes = smem;
     }
-    rc = launch(decode_rects_kernel, dim3(K, B), 256, smem, s, n_boxes, comp_root, comp_size, rowmin, rowmax, H, W, K,
+    const int rect_grid = (int)std::min<long long>((long long)B * K, kNumSMs * 8);
+    rc = launch(decode_rects_kernel, rect_grid, 256, smem, s, n_boxes, comp_root, comp_size, rowmin, rowmax, B, H, W, K,
                                                       p->scale_x, p->scale_y, npad, boxes, rects, comp);
     if (rc) return rc;
   }

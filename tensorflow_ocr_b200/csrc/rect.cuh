@@ -138,9 +138,114 @@ __device__ inline int sklansky(const int* __restrict__ X, const int* __restrict_
   return --stacksize;
 }
 
-// Called by the WHOLE CTA (>= 128 threads) after the keys are sorted.  total = number of
-// real points (> 0).  out_box: 8 ints (x0,y0..x3,y3), out_rect: 5 floats or nullptr — valid
-// in thread 0 only.
+// Cyclic shift of the hull towards a monotone sequence of INPUT indices (convhull.cpp, the block after
+// the four scans).  Thread 0 only.  hullbuf holds positions into X/Y/I; tmp is scratch of >= nout ints.
+__device__ inline void hull_index_shift(int* hullbuf, int nout, const int* I, int* tmp) {
+  if (nout < 3) return;
+  int min_idx = 0, max_idx = 0, lt = 0;
+  int prev = I[hullbuf[0]], vmin = prev, vmax = prev;
+  for (int i = 1; i < nout; ++i) {
+    const int idx = I[hullbuf[i]];
+    lt += prev < idx;
+    if (lt > 1 && lt <= i - 2) break;
+    if (idx < vmin) vmin = idx, min_idx = i;
+    if (idx > vmax) vmax = idx, max_idx = i;
+    prev = idx;
+  }
+  const int mmdist = abs(max_idx - min_idx);
+  if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
+    const int ascending = (max_idx + 1) % nout == min_idx;
+    const int i0 = ascending ? min_idx : max_idx;
+    int j = i0;
+    if (i0 > 0) {
+      int i;
+      int curr_idx = I[hullbuf[j]];
+      for (i = 0; i < nout; ++i) {
+        tmp[i] = hullbuf[j];
+        const int next_j = j + 1 < nout ? j + 1 : 0;
+        const int next_idx = I[hullbuf[next_j]];
+        if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
+        j = next_j;
+        curr_idx = next_idx;
+      }
+      if (i == nout)
+        for (i = 0; i < nout; ++i) hullbuf[i] = tmp[i];
+    }
+  }
+}
+
+__device__ inline void hull_to_box(const RectSmem& S, int n, int* out_box, float* out_rect);
+
+// Hull of DISTINCT points without sorting and without the sequential Sklansky scans (decode path:
+// row extremes are distinct).  Same vertex sequence as cv::convexHull(clockwise=false) before the
+// index shift (oracle/minarearect.py::convex_hull_giftwrap, pinned against the Sklansky restatement
+// and cv2): start at the lexicographic maximum (x, then y); the successor of p is the point q with every
+// other point on the clockwise side of p->q (x, y-down), the farthest among collinear candidates.
+// Successors of all points are computed in parallel (O(n^2) integer cross products), then thread 0
+// follows the pointers.  X/Y/I hold the points in any order; called by the whole CTA.
+__device__ inline void min_area_box_distinct(const RectSmem& S, int total, int* out_box, float* out_rect) {
+  __shared__ int s_start, s_nh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int* X = S.X;
+  const int* Y = S.Y;
+  int* succ = S.stack;  // [total]
+  if (warp == 0) {
+    int bx = -0x7fffffff, by = -0x7fffffff, bi = 0;
+    for (int i = lane; i < total; i += 32) {
+      const int x = X[i], y = Y[i];
+      if (x > bx || (x == bx && y > by)) bx = x, by = y, bi = i;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ox > bx || (ox == bx && oy > by)) bx = ox, by = oy, bi = oi;
+    }
+    if (lane == 0) s_start = bi;
+  }
+  // coordinates are < 2^15 in magnitude (checked on the host), so every product below fits in int32
+  for (int i = tid; i < total; i += blockDim.x) {
+    const int xi = X[i], yi = Y[i];
+    int best = -1;
+    int ax = 0, ay = 0;
+    for (int j = 0; j < total; ++j) {
+      const int bx = X[j] - xi, by = Y[j] - yi;
+      if (j == i) continue;
+      if (best < 0) {
+        best = j, ax = bx, ay = by;
+        continue;
+      }
+      const int c = ax * by - ay * bx;
+      bool take = c < 0;
+      if (c == 0) take = (ax * bx + ay * by) > 0 && (bx * bx + by * by) > (ax * ax + ay * ay);
+      if (take) best = j, ax = bx, ay = by;
+    }
+    succ[i] = best;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int* hullbuf = S.hullbuf;
+    const int start = s_start;
+    int nh = 0, cur = start;
+    hullbuf[nh++] = start;
+    if (total > 1) {
+      while (true) {
+        const int nx = succ[cur];
+        if (nx == start || nh > total) break;
+        hullbuf[nh++] = nx;
+        cur = nx;
+      }
+    }
+    hull_index_shift(hullbuf, nh, S.I, S.stack + total);
+    s_nh = nh;
+  }
+  __syncthreads();
+  hull_to_box(S, s_nh, out_box, out_rect);
+}
+
+// Called by the WHOLE CTA (>= 128 threads) after the keys are sorted (explicit point lists, which may
+// contain duplicates: OpenCV's own Sklansky scans are followed literally).  total = number of real
+// points (> 0).  out_box: 8 ints (x0,y0..x3,y3), out_rect: 5 floats or nullptr — valid in thread 0 only.
 __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npad, int* out_box, float* out_rect) {
   __shared__ int s_ind[2];     // miny_ind, maxy_ind
   __shared__ int s_count[4];   // tl, tr, bl, br stack sizes
@@ -216,43 +321,20 @@ __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npa
       }
       for (int i = 0; i < bl_count - 1; ++i) hullbuf[nout++] = bl_stack[i];
       for (int i = br_count - 1; i > 0; --i) hullbuf[nout++] = br_stack[i];
-      // cyclic shift towards a monotone sequence of INPUT indices
-      if (nout >= 3) {
-        int min_idx = 0, max_idx = 0, lt = 0;
-        const int* I = S.I;
-        for (int i = 1; i < nout; ++i) {
-          const int idx = I[hullbuf[i]];
-          lt += I[hullbuf[i - 1]] < idx;
-          if (lt > 1 && lt <= i - 2) break;
-          if (idx < I[hullbuf[min_idx]]) min_idx = i;
-          if (idx > I[hullbuf[max_idx]]) max_idx = i;
-        }
-        const int mmdist = abs(max_idx - min_idx);
-        if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
-          const int ascending = (max_idx + 1) % nout == min_idx;
-          const int i0 = ascending ? min_idx : max_idx;
-          int j = i0;
-          if (i0 > 0) {
-            int* tmp = S.stack;  // the scan stacks are dead now
-            int i;
-            for (i = 0; i < nout; ++i) {
-              const int curr_idx = I[hullbuf[j]];
-              tmp[i] = hullbuf[j];
-              const int next_j = j + 1 < nout ? j + 1 : 0;
-              const int next_idx = I[hullbuf[next_j]];
-              if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
-              j = next_j;
-            }
-            if (i == nout)
-              for (i = 0; i < nout; ++i) hullbuf[i] = tmp[i];
-          }
-        }
-      }
+      hull_index_shift(hullbuf, nout, S.I, S.stack);  // the scan stacks are dead now
     }
     s_nout = nout;
   }
   __syncthreads();
-  const int n = s_nout;
+  hull_to_box(S, s_nout, out_box, out_rect);
+}
+
+// Common tail, called by the whole CTA: hull (positions in S.hullbuf) -> cv::minAreaRect -> boxPoints -> int.
+__device__ inline void hull_to_box(const RectSmem& S, int n, int* out_box, float* out_rect) {
+  const int tid = threadIdx.x;
+  const int* X = S.X;
+  const int* Y = S.Y;
+  const int* hullbuf = S.hullbuf;
   float* hx = S.hx; float* hy = S.hy; float* vx = S.vx; float* vy = S.vy; float* inv = S.inv;
   float* ldx = S.lx; float* ldy = S.ly;
   for (int i = tid; i < n; i += blockDim.x) hx[i] = (float)X[hullbuf[i]], hy[i] = (float)Y[hullbuf[i]];
@@ -300,39 +382,49 @@ __device__ inline void min_area_box_sorted(const RectSmem& S, int total, int npa
     }
     float base_a = orientation, base_b = 0.f;
     int seq[4] = {bottom, right, top, left};
+    // state carried in registers: edge vector and hull point at each of the four calipers positions;
+    // one position advances per step, so one edge vector, one point and one unit lead are (re)loaded
+    float ex[4], ey[4], qx[4], qy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ex[i] = vx[seq[i]], ey[i] = vy[seq[i]], qx[i] = hx[seq[i]], qy[i] = hy[seq[i]];
     float minarea = 3.402823466e+38f;
     int b_left = 0, b_bottom = 0;
     float b_a = 0.f, b_w = 0.f, b_b = 0.f, b_h = 0.f;
     for (int k = 0; k < n; ++k) {
       // edge vectors rotated into a common frame; the first one met when rotating is the main edge
       float rx[4], ry[4];
-      rx[0] = vx[seq[0]], ry[0] = vy[seq[0]];
-      rx[1] = vy[seq[1]], ry[1] = -vx[seq[1]];
-      rx[2] = -vx[seq[2]], ry[2] = -vy[seq[2]];
-      rx[3] = -vy[seq[3]], ry[3] = vx[seq[3]];
+      rx[0] = ex[0], ry[0] = ey[0];
+      rx[1] = ey[1], ry[1] = -ex[1];
+      rx[2] = -ex[2], ry[2] = -ey[2];
+      rx[3] = -ey[3], ry[3] = ex[3];
       int main_element = 0;
+      float mx = rx[0], my = ry[0];
 #pragma unroll
       for (int i = 1; i < 4; ++i) {
         const float tx = ry[i], ty = -rx[i];  // rotate90CW(rv[i])
-        if (__fadd_rn(__fmul_rn(tx, rx[main_element]), __fmul_rn(ty, ry[main_element])) < 0.f) main_element = i;
+        if (__fadd_rn(__fmul_rn(tx, mx), __fmul_rn(ty, my)) < 0.f) main_element = i, mx = rx[i], my = ry[i];
       }
-      {
-        const int pindex = seq[main_element];
-        const float lead_x = ldx[pindex], lead_y = ldy[pindex];
-        switch (main_element) {
-          case 0: base_a = lead_x, base_b = lead_y; break;
-          case 1: base_a = lead_y, base_b = -lead_x; break;
-          case 2: base_a = -lead_x, base_b = -lead_y; break;
-          default: base_a = -lead_y, base_b = lead_x; break;
-        }
+      int pindex = seq[0];
+#pragma unroll
+      for (int i = 1; i < 4; ++i) pindex = main_element == i ? seq[i] : pindex;
+      int nidx = pindex + 1;
+      nidx = nidx == n ? 0 : nidx;
+      const float lead_x = ldx[pindex], lead_y = ldy[pindex];
+      const float nex = vx[nidx], ney = vy[nidx], nqx = hx[nidx], nqy = hy[nidx];
+      switch (main_element) {
+        case 0: base_a = lead_x, base_b = lead_y; break;
+        case 1: base_a = lead_y, base_b = -lead_x; break;
+        case 2: base_a = -lead_x, base_b = -lead_y; break;
+        default: base_a = -lead_y, base_b = lead_x; break;
       }
-      seq[main_element] += 1;
-      if (seq[main_element] == n) seq[main_element] = 0;
-      float dx = __fsub_rn(hx[seq[1]], hx[seq[3]]);
-      float dy = __fsub_rn(hy[seq[1]], hy[seq[3]]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (main_element == i) seq[i] = nidx, ex[i] = nex, ey[i] = ney, qx[i] = nqx, qy[i] = nqy;
+      float dx = __fsub_rn(qx[1], qx[3]);
+      float dy = __fsub_rn(qy[1], qy[3]);
       const float width = __fadd_rn(__fmul_rn(dx, base_a), __fmul_rn(dy, base_b));
-      dx = __fsub_rn(hx[seq[2]], hx[seq[0]]);
-      dy = __fsub_rn(hy[seq[2]], hy[seq[0]]);
+      dx = __fsub_rn(qx[2], qx[0]);
+      dy = __fsub_rn(qy[2], qy[0]);
       const float height = __fadd_rn(__fmul_rn(-dx, base_b), __fmul_rn(dy, base_a));
       const float area = __fmul_rn(width, height);
       if (area <= minarea) {

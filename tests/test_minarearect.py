@@ -79,3 +79,39 @@ def test_row_extremes_are_enough():
                 cand.append((int(xs.max() * 4.0), int(y * 3.75)))
         ref = np.intp(cv2.boxPoints(cv2.minAreaRect(full.astype(np.int32))))
         assert np.array_equal(M.min_area_box_int(np.array(cand, np.int64)), ref)
+
+
+def test_giftwrap_hull_equals_opencv_hull_on_distinct_points():
+    """The CUDA decode computes the hull of the (distinct) row extremes by parallel gift wrapping
+    (csrc/rect.cuh::min_area_box_distinct): it must be the Sklansky/OpenCV vertex sequence exactly."""
+    from oracle import minarearect as M
+    rng = np.random.default_rng(1)
+    n = 0
+    for t in range(1500):
+        mode = t % 3
+        if mode == 0:
+            yx = _blob(rng)
+            if len(yx) == 0:
+                continue
+            sx, sy = [(4.0, 3.75), (1.0, 1.0), (2.0, 1.875)][(t // 3) % 3]
+            cand = []
+            for y in np.unique(yx[:, 0]):
+                xs = yx[yx[:, 0] == y, 1]
+                cand.append((int(xs.min() * sx), int(y * sy)))
+                if xs.max() != xs.min():
+                    cand.append((int(xs.max() * sx), int(y * sy)))
+            pts = np.array(cand)
+        elif mode == 1:
+            k = int(rng.integers(1, 6))
+            p0, d = rng.integers(0, 50, 2), rng.integers(-3, 4, 2)
+            if (d == 0).all():
+                d = np.array([1, 0])
+            pts = np.array([p0 + d * i for i in range(k)])
+        else:
+            pts = np.unique(rng.integers(0, 12, (int(rng.integers(1, 40)), 2)), axis=0)
+        pts = np.array(sorted(pts.tolist(), key=lambda t: (t[1], t[0])))
+        assert M.convex_hull_giftwrap(pts) == M.convex_hull_cv(pts, False, index_shift=False)
+        hull_cv = cv2.convexHull(pts.astype(np.int32), clockwise=False, returnPoints=False).reshape(-1)
+        assert np.array_equal(hull_cv, np.array(M.convex_hull_cv(pts, False)))
+        n += 1
+    assert n > 1200

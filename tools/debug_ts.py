@@ -13,10 +13,14 @@ out = {}
 for i in range(5):
     head.decode_raw(pl, ll, head.DecodeConfig(max_boxes=128), out, want_rects=False)
 torch.cuda.synchronize()
-buf = np.zeros(8, np.int64)
-print("rc", lib.plh_debug_read(buf.ctypes.data_as(ctypes.c_void_p), 8))
-d = np.diff(buf)
-names = ["load", "phase1 runs", "phase2a", "phase2b hier", "phase3 flatten", "phase4 slots", "phase5 labels"]
-for n, c in zip(names, d):
-    print("%-16s %8d cycles" % (n, c))
-print("n_boxes", out["n_boxes"].cpu().numpy().tolist())
+n = 1184
+buf = np.zeros((n, 16), np.int64)
+print("rc", lib.plh_debug_read(buf.ctypes.data_as(ctypes.c_void_p), n * 16))
+done = buf[buf[:, 7] > 0]
+tot = done[:, 7] - done[:, 0]
+print("ctas with work", len(done), "cycles per item: median %d max %d" % (np.median(tot), tot.max()))
+names = ["gather+rank", "start+succ", "follow", "shift", "edge vectors", "calipers", "final"]
+for idx in (np.argsort(tot)[len(tot) // 2], np.argmax(tot)):
+    r = done[idx]
+    print("hull n=%d candidates=%d" % (r[9], r[10]), {nm: int(r[i + 1] - r[i]) for i, nm in enumerate(names)})
+print("start spread (cycles, first item of each CTA):", int(done[:, 0].max() - done[:, 0].min()))
