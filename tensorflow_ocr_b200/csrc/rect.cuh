@@ -203,23 +203,22 @@ __device__ inline void min_area_box_distinct(const RectSmem& S, int total, int* 
     }
     if (lane == 0) s_start = bi;
   }
-  // coordinates are < 2^15 in magnitude (checked on the host), so every product below fits in int32
+  // coordinates are < 2^15 in magnitude (checked on the host), so every product below fits in int32.
+  // Branch-free body: j == i gives b = 0 (cross 0, dot 0 -> not taken) and the initial candidate
+  // compares equal to itself (not farther -> not taken), so neither needs a special case.
   for (int i = tid; i < total; i += blockDim.x) {
     const int xi = X[i], yi = Y[i];
-    int best = -1;
-    int ax = 0, ay = 0;
+    int best = (i == 0 && total > 1) ? 1 : 0;
+    int ax = X[best] - xi, ay = Y[best] - yi;
+#pragma unroll 4
     for (int j = 0; j < total; ++j) {
       const int bx = X[j] - xi, by = Y[j] - yi;
-      if (j == i) continue;
-      if (best < 0) {
-        best = j, ax = bx, ay = by;
-        continue;
-      }
       const int c = ax * by - ay * bx;
-      bool take = c < 0;
-      if (c == 0) take = (ax * bx + ay * by) > 0 && (bx * bx + by * by) > (ax * ax + ay * ay);
-      if (take) best = j, ax = bx, ay = by;
+      const bool far = (ax * bx + ay * by) > 0 && (bx * bx + by * by) > (ax * ax + ay * ay);
+      const bool take = c < 0 || (c == 0 && far);
+      best = take ? j : best, ax = take ? bx : ax, ay = take ? by : ay;
     }
+    if (total == 1) best = -1;
     succ[i] = best;
   }
   __syncthreads();
