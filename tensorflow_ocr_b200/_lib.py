@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplhead.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("PLH_LIB", "libplhead.so"))   # PLH_LIB: instrumented build for tools/
 
 # ---- constants mirrored from include/plhead.h
 OP_LOSS, OP_DECODE, OP_DICE, OP_EAST_LOSS, OP_RESTORE, OP_LOSS_DECODE = range(6)

@@ -445,6 +445,23 @@ extern "C" size_t plh_workspace_bytes(int op, int B, int H, int W, int K) {
   }
 }
 
+#ifdef PLH_TIMELINE
+namespace plh { int tl_set_loss(unsigned long long*); int tl_set_decode(unsigned long long*); }
+static unsigned long long* h_tl = nullptr;
+extern "C" __attribute__((visibility("default"))) int plh_timeline_reset(void) {
+  if (!h_tl) {
+    if (cudaMalloc(&h_tl, 64 * 8) != cudaSuccess) return -1;
+    plh::tl_set_loss(h_tl);
+    plh::tl_set_decode(h_tl);
+  }
+  unsigned long long h[64];
+  for (int i = 0; i < 32; ++i) h[2 * i] = ~0ull, h[2 * i + 1] = 0ull;
+  return (int)cudaMemcpy(h_tl, h, sizeof(h), cudaMemcpyHostToDevice);
+}
+extern "C" __attribute__((visibility("default"))) int plh_timeline_read(unsigned long long* out) {
+  return h_tl ? (int)cudaMemcpy(out, h_tl, 64 * 8, cudaMemcpyDeviceToHost) : -1;
+}
+#endif
 extern "C" int plh_version(void) { return PLH_VERSION; }
 
 extern "C" const char* plh_strerror(int code) {

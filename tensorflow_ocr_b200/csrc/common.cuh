@@ -49,6 +49,30 @@ inline int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cu
   return e == cudaSuccess ? PLH_OK : (int)e;
 }
 
+// Optional device-side timeline (compile with -DPLH_TIMELINE): first-CTA start / last-CTA end of every
+// hot-chain kernel in %globaltimer nanoseconds, read back with plh_timeline_read().
+#ifdef PLH_TIMELINE
+static __device__ unsigned long long* g_tlp;  // one copy per translation unit, set by tl_set_ptr()
+static inline int tl_set_ptr(unsigned long long* p) { return (int)cudaMemcpyToSymbol(g_tlp, &p, sizeof(p)); }
+__device__ __forceinline__ void tl_start(int id) {
+  if (threadIdx.x == 0 && g_tlp) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMin(&g_tlp[2 * id], t);
+  }
+}
+__device__ __forceinline__ void tl_end(int id) {
+  if (threadIdx.x == 0 && g_tlp) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMax(&g_tlp[2 * id + 1], t);
+  }
+}
+#else
+__device__ __forceinline__ void tl_start(int) {}
+__device__ __forceinline__ void tl_end(int) {}
+#endif
+
 // first statement of every PDL-launched kernel
 __device__ __forceinline__ void pdl_wait_and_release() {
   cudaGridDependencySynchronize();             // predecessor complete, its writes visible

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256)
 decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restrict__ link_logits, long long total_px,
                     float tp_logit, float tl_logit, uint16_t* __restrict__ flags, int* __restrict__ n_boxes, int B) {
   pdl_wait_and_release();
+  tl_start(4);
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < B; i += blockDim.x) n_boxes[i] = 0;
@@ -90,6 +91,7 @@ decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restric
       flags[px] = (uint16_t)(bits | (p ? kFlagP : 0));
     }
   }
+  tl_end(4);
 }
 
 // ------------------------------------------------------------------ D1: union-find
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(kTW * kTH)
 decode_tile_cc_kernel(const uint16_t* __restrict__ flags, int H, int W, int* __restrict__ parent,
                       int* __restrict__ size, int* __restrict__ n_boxes) {
   pdl_wait_and_release();
+  tl_start(5);
   __shared__ uint16_t sf[kTH + 2][kTW + 2];
   __shared__ int slab[kTW * kTH];
   const int tid = threadIdx.x;
@@ -213,6 +216,7 @@ decode_tile_cc_kernel(const uint16_t* __restrict__ flags, int H, int W, int* __r
     parent[g] = root;
     size[g] = 0;
   }
+  tl_end(5);
 }
 
 // Cross-tile pairs: only pixels on the right / bottom / left border of a tile have a forward
@@ -220,6 +224,7 @@ decode_tile_cc_kernel(const uint16_t* __restrict__ flags, int H, int W, int* __r
 __global__ void __launch_bounds__(256)
 decode_cross_kernel(const uint16_t* __restrict__ flags, int H, int W, int total_px, int* __restrict__ parent) {
   pdl_wait_and_release();
+  tl_start(6);
   const int N = H * W;
   const int stride = gridDim.x * blockDim.x;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
@@ -243,6 +248,7 @@ decode_cross_kernel(const uint16_t* __restrict__ flags, int H, int W, int total_
       if ((vin && (f & (1u << d))) || (uin && (fu & (1u << c_opp[k])))) unite(parent, g, u);
     }
   }
+  tl_end(6);
 }
 
 // ------------------------------------------------------------------ D2: flatten + sizes
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(256)
 decode_flatten_kernel(const uint16_t* __restrict__ flags, int H, int W, long long total_px, int* __restrict__ parent,
                       int* __restrict__ size) {
   pdl_wait_and_release();
+  tl_start(7);
   const int N = H * W;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long start = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
@@ -287,6 +294,7 @@ decode_flatten_kernel(const uint16_t* __restrict__ flags, int H, int W, long lon
       if ((__ffs(peers) - 1) == lane) atomicAdd(&size[root], __popc(peers));
     }
   }
+  tl_end(7);
 }
 
 // ------------------------------------------------------------------ D3: kept roots -> box slots
@@ -298,6 +306,7 @@ decode_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int 
                     int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes,
                     int* __restrict__ rowmin, int* __restrict__ rowmax, int H) {
   pdl_wait_and_release();
+  tl_start(8);
   const int stride = gridDim.x * blockDim.x;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
     if (parent[g] != g) continue;
@@ -318,6 +327,7 @@ decode_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int 
       size[g] = -1;
     }
   }
+  tl_end(8);
 }
 
 // ------------------------------------------------------------------ D4: labels + row extremes
@@ -325,6 +335,7 @@ __global__ void __launch_bounds__(256)
 decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ size, int H, int W, long long total_px,
                      int K, int32_t* __restrict__ labels, int* __restrict__ rowmin, int* __restrict__ rowmax) {
   pdl_wait_and_release();
+  tl_start(9);
   const int N = H * W;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
@@ -344,6 +355,7 @@ decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ siz
       if (run_end) atomicMax(&rowmax[row], x);
     }
   }
+  tl_end(9);
 }
 
 // ------------------------------------------------------------------ D5: one CTA per component
@@ -356,6 +368,7 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
                     int B, int H, int W, int K, double sx, double sy, int npad, int32_t* __restrict__ boxes,
                     float* __restrict__ rects, int32_t* __restrict__ comp) {
   pdl_wait_and_release();
+  tl_start(10);
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_n, s_rank, s_b, s_slot;
   RectSmem S = rect_carve(smem, npad);
@@ -375,7 +388,7 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
     }
     __syncthreads();
     const int b = s_b, slot = s_slot;
-    if (b < 0) return;
+    if (b < 0) { tl_end(10); return; }
     const int nb = min(n_boxes[b], K);
     const size_t rowbase = ((size_t)b * K + slot) * H;
     const int root = comp_root[(size_t)b * K + slot];
@@ -421,6 +434,7 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
     }
     __syncthreads();  // shared state is reused by the next item
   }
+  tl_end(10);
 }
 
 // explicit point lists: one CTA per list
@@ -526,6 +540,10 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   }
   return PLH_OK;
 }
+
+#ifdef PLH_TIMELINE
+int tl_set_decode(unsigned long long* p) { return tl_set_ptr(p); }
+#endif
 
 }  // namespace plh
 

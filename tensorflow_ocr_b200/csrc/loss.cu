@@ -59,7 +59,7 @@ struct ImageInfo {  // per image, written by K1
 };
 constexpr int kKeysMaxCTAsPerImage = 64;  // K0 writes one (n_pos, n_neg) pair per CTA; K1 sums them (no atomics, no memset)
 
-constexpr int kMainThreads = 512;
+constexpr int kMainThreads = 384;
 constexpr int kMainMaxCTAs = kNumSMs * 2;
 constexpr int kSelectThreads = 1024;
 constexpr size_t kSmemKeysMaxBytes = 200 * 1024;   // keys of one image fit in shared memory up to 51200 px
@@ -103,6 +103,7 @@ score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict_
                   const uint8_t* __restrict__ neg_mask, int N, uint32_t* __restrict__ keys,
                   int2* __restrict__ counts) {
   pdl_wait_and_release();
+  tl_start(0);
   __shared__ int s_np, s_nn;
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -140,6 +141,7 @@ score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict_
   }
   __syncthreads();
   if (tid == 0) counts[(size_t)b * gridDim.x + blockIdx.x] = make_int2(s_np, s_nn);
+  tl_end(0);
 }
 
 // ------------------------------------------------------------------ K1: per-image OHEM threshold
@@ -154,6 +156,7 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict
                    const int* __restrict__ n_pos_override, int N, int ratio, int keymode, int use_smem,
                    ImageInfo* __restrict__ info, float* __restrict__ thr_out, LossHeader* __restrict__ hdr) {
   pdl_wait_and_release();
+  tl_start(1);
   extern __shared__ __align__(16) uint32_t skeys[];
   __shared__ int s_w[2][32];
   const int b = blockIdx.x;
@@ -232,6 +235,7 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict
     // NaN when nothing is selected: `score <= NaN` is false for every pixel
     if (thr_out) thr_out[b] = none ? __int_as_float(0x7fc00000) : __uint_as_float(ans);
   }
+  tl_end(1);
 }
 
 // ------------------------------------------------------------------ K2: mask + integer normalisers
@@ -242,6 +246,7 @@ ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ 
                    const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N,
                    uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr) {
   pdl_wait_and_release();
+  tl_start(2);
   __shared__ int s_c[18];
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -302,6 +307,7 @@ ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ 
   __syncthreads();
   // integer atomics: exact and order independent
   if (tid < 18 && s_c[tid]) atomicAdd(reinterpret_cast<int*>(hdr) + tid, s_c[tid]);  // header ints 0..17
+  tl_end(2);
 }
 
 // ------------------------------------------------------------------ K3: main fused pass
@@ -367,6 +373,7 @@ template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
 __global__ void __launch_bounds__(kMainThreads, 2)
 loss_main_kernel(const MainArgs a, const int B, const int N) {
   pdl_wait_and_release();
+  tl_start(3);
   __shared__ float s_red[kMainThreads / 32][4][5];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
@@ -522,7 +529,7 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&a.hdr->ticket, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) { tl_end(3); return; }
 
   // ---- last CTA: the scalars.  One warp: lane d owns link direction d, so the header loads and the
   // IEEE divisions run side by side instead of as one thread's chain of dependent L2 round trips.
@@ -571,6 +578,7 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
     if (lane < 17) a.hdr->sums[lane] = 0.0;
     if (lane == 0) a.hdr->ticket = 0u;
   }
+  tl_end(3);
 }
 
 // ------------------------------------------------------------------ standalone OHNM_batch apply
@@ -665,6 +673,10 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
 #undef PLH_SELECT
   return rc;
 }
+
+#ifdef PLH_TIMELINE
+int tl_set_loss(unsigned long long* p) { return tl_set_ptr(p); }
+#endif
 
 }  // namespace plh
 

@@ -1,0 +1,54 @@
+"""Device-side timeline of one head step (needs the -DPLH_TIMELINE build: tensorflow_ocr_b200/libplhead_tl.so).
+Prints first-CTA start / last-CTA end of every hot-chain kernel relative to the first kernel, in graph mode."""
+import ctypes, os, sys
+os.environ["PLH_LIB"] = "libplhead_tl.so"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tensorflow_ocr_b200 import head, synth, _lib
+B, H, W = 32, 128, 128
+dev = torch.device("cuda", 0)
+lib = _lib.load()
+lib.plh_timeline_read.argtypes = [ctypes.c_void_p]
+base = synth.make_batch(2, B, H, W, "C")
+sets = []
+for s in range(6):
+    d = {k: torch.as_tensor(np.ascontiguousarray(np.roll(base[k], s, axis=0))).to(dev) for k in ("pix_logits", "link_logits", "pix_lab", "link_lab")}
+    d["out"] = {}
+    sets.append(d)
+ms = torch.cuda.Stream(dev)
+torch.cuda.set_stream(ms)
+lcfg, dcfg = head.LossConfig(), head.DecodeConfig(max_boxes=128)
+def step(i):
+    d = sets[i % 6]
+    head.loss_and_decode_raw(d["pix_logits"], d["link_logits"], d["pix_lab"], d["link_lab"], lcfg, dcfg, d["out"])
+for i in range(6):
+    step(i)
+torch.cuda.synchronize()
+graphs = []
+for i in range(6):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=ms):
+        step(i)
+    graphs.append(g)
+torch.cuda.synchronize()
+torch.cuda.set_stream(ms)
+for i in range(30):
+    graphs[i % 6].replay()
+torch.cuda.synchronize()
+names = ["K0 keys", "K1 select", "K2 counts", "K3 main", "D0 flags", "D1a tile_cc", "D1b cross", "D2 flatten", "D3 roots", "D4 labels", "D5 rects"]
+acc = np.zeros((11, 2))
+reps = 20
+for r in range(reps):
+    lib.plh_timeline_reset()
+    graphs[r % 6].replay()
+    torch.cuda.synchronize()
+    buf = np.zeros(64, np.uint64)
+    lib.plh_timeline_read(buf.ctypes.data_as(ctypes.c_void_p))
+    t = buf.astype(np.int64).reshape(32, 2)[:11]
+    t0 = t[:, 0].min()
+    acc += (t - t0) / 1e3
+acc /= reps
+print("%-14s %9s %9s %9s" % ("kernel", "start us", "end us", "dur us"))
+for n, (a, b) in zip(names, acc):
+    print("%-14s %9.2f %9.2f %9.2f" % (n, a, b, b - a))
+print("step span: %.2f us" % (acc[:, 1].max()))
