@@ -68,8 +68,10 @@ typedef struct plh_loss_params {
   int32_t neg_pos_ratio; /* 3 (nets/model.py:171; config.max_neg_pos_ratio in nets/pixellink.py:116) */
   float focal_alpha;     /* 0.25 */
   float focal_gamma;     /* 2.0 */
-  int32_t reserved[3];   /* reserved[0] bit 0: measurement only — rerun the main pass on a workspace that a
-                            previous full call with the same inputs prepared (skips selection and counts) */
+  int32_t reserved[3];   /* reserved[0] bit 0: run only the main pass, on a workspace that a previous call with the
+                            same inputs prepared (skips selection and counts); bit 1: run only selection and
+                            counts.  The pair lets the caller place the bandwidth-bound main pass in its own
+                            schedule (tensorflow_ocr_b200/head.py) and lets bench.py time it alone. */
 } plh_loss_params;
 
 /* Layout of the `stats` output (device floats).  PLH_STATS_FLOATS + B entries. */
@@ -153,7 +155,8 @@ typedef struct plh_decode_params {
   int32_t max_boxes;  /* capacity K of the per-image box list */
   double scale_x;     /* 4.0  = 1280/320 (test_pixellink_fast.py:196); must be >= 1 */
   double scale_y;     /* 3.75 = 720/192  (test_pixellink_fast.py:197); must be >= 1 */
-  int32_t reserved[2];
+  int32_t reserved[2]; /* reserved[0] bit 0: components + label map only (no boxes); bit 1: boxes only, from the
+                          workspace of a previous bit-0 call */
 } plh_decode_params;
 
 /*

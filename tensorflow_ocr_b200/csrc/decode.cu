@@ -60,6 +60,9 @@ static DecodeWsLayout decode_ws_layout(int B, int H, int W, int K) {
 size_t decode_workspace_bytes(int B, int H, int W, int K) { return decode_ws_layout(B, H, W, K).total; }
 
 // ------------------------------------------------------------------ D0: flags from logits (+ init)
+// Work unit = 32 consecutive pixels per warp: four link iterations (lane = pixel-in-iteration x quarter,
+// one 128-bit load of two directions' logits each) and one pixel phase (lane = pixel: its 2 pixel logits,
+// the 16-bit flag word store).  ~3 instructions per pixel: the kernel is bound by the 72 B/px it reads.
 __global__ void __launch_bounds__(256)
 decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restrict__ link_logits, long long total_px,
                     float tp_logit, float tl_logit, uint16_t* __restrict__ flags, int* __restrict__ n_boxes, int B) {
@@ -68,28 +71,36 @@ decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restric
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < B; i += blockDim.x) n_boxes[i] = 0;
-  const int j = threadIdx.x & 3;
-  const long long Q = total_px * 4;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int j = lane & 3, qp = lane >> 2;
+  const int total = (int)total_px;
+  const int nunits = (total + 31) >> 5;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
   const float4* ll4 = reinterpret_cast<const float4*>(link_logits);
   const float2* pl2 = reinterpret_cast<const float2*>(pix_logits);
-  for (long long w0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < Q; w0 += stride) {
-    const long long q = w0 + lane;
-    const bool valid = q < Q;
-    float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+    const int px0 = u << 5;
+    float4 L[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int px = px0 + it * 8 + qp;
+      L[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (px < total) L[it] = ldg_stream4(ll4 + ((size_t)px * 4 + j));
+    }
+    const int pp = px0 + lane;
     float2 P = make_float2(0.f, 0.f);
-    const long long px = q >> 2;
-    if (valid) {
-      L = ldg_stream4(ll4 + q);
-      P = __ldg(pl2 + px);
+    if (pp < total) P = ldg_stream2(pl2 + pp);
+    unsigned mine = 0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      unsigned bits = ((L[it].y - L[it].x) > tl_logit ? 1u : 0u) << (2 * j) |
+                      ((L[it].w - L[it].z) > tl_logit ? 1u : 0u) << (2 * j + 1);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+      // pixel-phase lane l owns pixel (l >> 3) * 8 + (l & 7): iteration l >> 3, quad l & 7
+      const unsigned got = __shfl_sync(0xffffffffu, bits, (lane & 7) << 2);
+      if ((lane >> 3) == it) mine = got;
     }
-    unsigned bits = ((L.y - L.x) > tl_logit ? 1u : 0u) << (2 * j) | ((L.w - L.z) > tl_logit ? 1u : 0u) << (2 * j + 1);
-    bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-    bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-    if (valid && j == 0) {
-      const bool p = (P.y - P.x) > tp_logit;
-      flags[px] = (uint16_t)(bits | (p ? kFlagP : 0));
-    }
+    if (pp < total) flags[pp] = (uint16_t)(mine | ((P.y - P.x) > tp_logit ? kFlagP : 0));
   }
   tl_end(4);
 }
@@ -373,18 +384,29 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
   __shared__ int s_n, s_rank, s_b, s_slot;
   RectSmem S = rect_carve(smem, npad);
   for (int item = blockIdx.x;; item += gridDim.x) {
-    // locate item in the image-major list (B is small: one thread walks the counts)
-    if (threadIdx.x == 0) {
+    // locate the item in the image-major list: warp 0 loads 32 counts at a time (independent loads,
+    // one L2 round trip) and scans them with shuffles — a one-thread walk would be B dependent round trips
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
       int acc = 0, bb = -1, sl = 0;
-      for (int i = 0; i < B; ++i) {
-        const int nb = min(n_boxes[i], K);
-        if (item < acc + nb) {
-          bb = i, sl = item - acc;
-          break;
+      for (int i0 = 0; i0 < B && bb < 0; i0 += 32) {
+        const int nbi = (i0 + lane < B) ? min(n_boxes[i0 + lane], K) : 0;
+        int inc = nbi;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
         }
-        acc += nb;
+        const int lo = acc + inc - nbi, hi = acc + inc;          // this image covers items [lo, hi)
+        const unsigned hit = __ballot_sync(0xffffffffu, item >= lo && item < hi);
+        if (hit) {
+          const int src = __ffs(hit) - 1;
+          bb = i0 + src;
+          sl = item - __shfl_sync(0xffffffffu, lo, src);
+        }
+        acc = __shfl_sync(0xffffffffu, hi, 31);
       }
-      s_b = bb, s_slot = sl, s_n = 0, s_rank = 0;
+      if (lane == 0) s_b = bb, s_slot = sl, s_n = 0, s_rank = 0;
     }
     __syncthreads();
     const int b = s_b, slot = s_slot;
@@ -503,10 +525,13 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   const int N = H * W;
   int rc;
   const int grid_px = (int)std::min<long long>((total_px + 255) / 256, kNumSMs * 16);
+  const bool skip_rects = (p->reserved[0] & 1) != 0;  // components + label map only
+  const bool rects_only = (p->reserved[0] & 2) != 0;  // boxes from a workspace prepared by a skip_rects call
+  if (rects_only) goto rects;
   if (flags_in) {
     flags = const_cast<uint16_t*>(flags_in);
   } else {
-    const int grid = (int)std::min<long long>((total_px * 4 + 255) / 256, kNumSMs * 16);
+    const int grid = (int)std::min<long long>((total_px / 32 + 7) / 8 + 1, kNumSMs * 8);
     rc = launch(decode_flags_kernel, grid, 256, 0, s, pix_logits, link_logits, total_px,
                                              prob_to_logit_threshold(p->pixel_thresh),
                                              prob_to_logit_threshold(p->link_thresh), flags, n_boxes, B);
@@ -524,6 +549,8 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   if (rc) return rc;
   rc = launch(decode_labels_kernel, grid_px, 256, 0, s, parent, size, H, W, total_px, K, labels, rowmin, rowmax);
   if (rc) return rc;
+  if (skip_rects) return PLH_OK;
+rects:
   {
     const int npad = next_pow2(std::max(2 * H, 32));
     const size_t smem = rect_smem_bytes(npad);
