@@ -15,7 +15,7 @@ for s in range(6):
     d = {k: torch.as_tensor(np.ascontiguousarray(np.roll(base[k], s, axis=0))).to(dev) for k in ("pix_logits", "link_logits", "pix_lab", "link_lab")}
     d["out"] = {}
     sets.append(d)
-ms = torch.cuda.Stream(dev)
+ms = torch.cuda.Stream(dev, priority=int(os.environ.get('BENCH_MAIN_PRIO', '0')))
 torch.cuda.set_stream(ms)
 lcfg, dcfg = head.LossConfig(), head.DecodeConfig(max_boxes=128)
 def step(i):
