@@ -184,3 +184,37 @@ def test_fused_loss_decode_flags(cuda_dev):
         out = {k: v.cpu().numpy() for k, v in fused.items()}
         _check(inp, out)
         assert abs(out["stats"][0] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+
+
+def test_decode_box_capacity_overflow(cuda_dev):
+    """More components than max_boxes: n_boxes reports the true count, the label map is complete, and
+    the K written boxes are K distinct components of the image (an unspecified subset)."""
+    from oracle import decode as D
+    from tensorflow_ocr_b200 import synth
+    inp = synth.make_batch(17, 1, 128, 128, "G")
+    lab, boxes, sizes, _ = D.decode_pixellink(inp["pix_logits"][0], inp["link_logits"][0], min_size=2)
+    assert len(boxes) > 3
+    out = _decode(inp, min_size=2, max_boxes=3)
+    assert out["n_boxes"][0] == len(boxes)
+    assert np.array_equal(out["labels"][0], lab)
+    roots = np.unique(lab[lab >= 0])
+    got_roots = out["comp"][0, :3, 0]
+    assert len(set(got_roots.tolist())) == 3 and set(got_roots.tolist()) <= set(roots.tolist())
+    for k in range(3):
+        j = int(np.nonzero(roots == got_roots[k])[0][0])
+        assert np.array_equal(out["boxes"][0, k], boxes[j])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_decode_random_shapes(seed, cuda_dev):
+    """Ragged map sizes (not multiples of the 32x16 tile), random thresholds and scales."""
+    from tensorflow_ocr_b200 import synth
+    rng = np.random.default_rng(100 + seed)
+    B, H, W = int(rng.integers(1, 4)), int(rng.integers(3, 150)), int(rng.integers(3, 200))
+    fam = "GS"[seed % 2]
+    inp = synth.make_batch(18 + seed, B, H, W, fam)
+    tp, tl = float(rng.choice([0.5, 0.7, 0.8])), float(rng.choice([0.5, 0.8, 0.9]))
+    sc = [(4.0, 3.75), (1.0, 1.0), (2.0, 1.875)][seed % 3]
+    ms = int(rng.integers(0, 12))
+    out = _decode(inp, pixel_thresh=tp, link_thresh=tl, scale=sc, min_size=ms, max_boxes=1024)
+    _check(inp, out, min_size=ms, scale=sc, pixel_thresh=tp, link_thresh=tl)

@@ -174,3 +174,25 @@ def test_full_size_properties(cuda_dev):
         nsel = int((m[b] == 1).sum()) - npos
         k = min(3 * npos, nneg) if npos > 0 else 0
         assert nsel >= k and (k > 0 or nsel == 0)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_loss_random_shapes_and_variants(seed, cuda_dev):
+    """Ragged sizes x all three weight variants x both terms against the oracle."""
+    from oracle import pixellink_loss as O
+    from tensorflow_ocr_b200 import _lib, head, synth
+    rng = np.random.default_rng(200 + seed)
+    B, H, W = int(rng.integers(1, 7)), int(rng.integers(2, 90)), int(rng.integers(2, 120))
+    inp = synth.make_batch(40 + seed, B, H, W, "G", edge_images=(B >= 4))
+    ratio = int(rng.integers(1, 5))
+    ref = O.loss_model(inp["pix_lab"], inp["pix_logits"], inp["link_lab"], inp["link_logits"], ratio=ratio)
+    _compare(_run(inp, head.LossConfig(neg_pos_ratio=ratio)), ref, B)
+    ref = O.loss_model(inp["pix_lab"], inp["pix_logits"], inp["link_lab"], inp["link_logits"], weight_mode="pos_only",
+                       term="focal")
+    _compare(_run(inp, head.LossConfig(variant=_lib.VARIANT_POS_ONLY, term=_lib.TERM_FOCAL)), ref, B)
+    ref = O.build_loss_pixellink(inp["pix_logits"], inp["link_logits"], inp["pix_lab"], inp["link_lab"], ratio)
+    out = _run(inp, head.LossConfig(variant=_lib.VARIANT_PIXELLINK, neg_pos_ratio=ratio))
+    assert rel_err(out["stats"][0], ref["loss"]) <= TOL
+    assert rel_err(out["grad_pixel"], ref["grad_pixel"]) <= TOL
+    assert rel_err(out["grad_link"], ref["grad_link"]) <= TOL
+    assert np.array_equal(out["ohem_mask"].astype(np.float32), ref["ohem_mask"])
