@@ -69,9 +69,11 @@ typedef struct plh_loss_params {
   float focal_alpha;     /* 0.25 */
   float focal_gamma;     /* 2.0 */
   int32_t reserved[3];   /* reserved[0] bit 0: run only the main pass, on a workspace that a previous call with the
-                            same inputs prepared (skips selection and counts); bit 1: run only selection and
-                            counts.  The pair lets the caller place the bandwidth-bound main pass in its own
-                            schedule (tensorflow_ocr_b200/head.py) and lets bench.py time it alone. */
+                            same inputs prepared (skips selection, mask and normalisers): lets bench.py time
+                            the bandwidth-bound pass alone.  Bit 1: scheduling hint, results identical — keep
+                            the mask + normaliser pass a separate kernel instead of fusing it into the
+                            selection kernel (better when another pipeline shares the GPU).
+                            Other bits must be 0. */
 } plh_loss_params;
 
 /* Layout of the `stats` output (device floats).  PLH_STATS_FLOATS + B entries. */
@@ -122,6 +124,7 @@ PLH_API int plh_pixellink_loss(const float* pix_logits, const float* link_logits
  *  n_pos   [B] int32 optional (device): overrides the count of pos_mask, as in
  *          OHNM_single_image(scores, n_pos, neg_mask) where n_pos is an argument
  *  selected_mask [B,N] float: pos + selected negatives;  thr [B] float.
+ *  workspace: plh_workspace_bytes(PLH_OP_LOSS, B, 1, N, 0).
  */
 PLH_API int plh_ohnm_batch(const float* scores, const uint8_t* pos_mask, const uint8_t* neg_mask,
                            const int32_t* n_pos, int B, int N, int variant, int neg_pos_ratio,
@@ -183,6 +186,14 @@ PLH_API int plh_decode(const float* pix_logits, const float* link_logits, int B,
 PLH_API int plh_decode_from_flags(const uint16_t* flags, int B, int H, int W, const plh_decode_params* p,
                           int32_t* labels, int32_t* boxes, int32_t* n_boxes, float* rects, int32_t* comp,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The threshold pass of the decode alone (test_pixellink_fast.py:120-128): flags[b,y,x] = bit 8: pixel
+ * score > pixel_thresh, bits 0..7: link d score > link_thresh, for plh_decode_from_flags.  Lets a caller
+ * schedule this bandwidth-bound pass separately from the latency-bound component labelling.
+ */
+PLH_API int plh_decode_flags(const float* pix_logits, const float* link_logits, int B, int H, int W,
+                             const plh_decode_params* p, uint16_t* flags, void* stream);
 
 /*
  * cv2.minAreaRect -> cv2.boxPoints -> np.int0 for explicit point lists

@@ -43,6 +43,7 @@ SIGNATURES = {
     "plh_dice_head": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _sz, _vp]),
     "plh_decode": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(DecodeParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "plh_decode_from_flags": (_i, [_vp, _i, _i, _i, C.POINTER(DecodeParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "plh_decode_flags": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(DecodeParams), _vp, _vp]),
     "plh_min_area_boxes": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "plh_pixel_detect": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     "plh_restore_rectangle": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -78,6 +78,10 @@ __device__ __forceinline__ void pdl_wait_and_release() {
   cudaGridDependencySynchronize();             // predecessor complete, its writes visible
   cudaTriggerProgrammaticLaunchCompletion();   // let the successor start scheduling
 }
+// Split form for long kernels on few SMs: a successor released at the top would park its CTAs on the
+// idle SMs for the whole kernel and keep the other branch's kernels off them, so release late.
+__device__ __forceinline__ void pdl_wait() { cudaGridDependencySynchronize(); }
+__device__ __forceinline__ void pdl_release() { cudaTriggerProgrammaticLaunchCompletion(); }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

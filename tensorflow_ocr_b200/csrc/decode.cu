@@ -593,6 +593,18 @@ extern "C" int plh_decode_from_flags(const uint16_t* flags, int B, int H, int W,
                        workspace_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int plh_decode_flags(const float* pix_logits, const float* link_logits, int B, int H, int W,
+                                const plh_decode_params* p, uint16_t* flags, void* stream) {
+  if (!pix_logits || !link_logits || !p || !flags) return PLH_E_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (!aligned16(pix_logits) || !aligned16(link_logits) || !aligned16(flags)) return PLH_E_ALIGN;
+  const long long total_px = (long long)B * H * W;
+  const int grid = (int)std::min<long long>((total_px / 32 + 7) / 8 + 1, kNumSMs * 8);
+  return launch(decode_flags_kernel, grid, 256, 0, (cudaStream_t)stream, pix_logits, link_logits, total_px,
+                prob_to_logit_threshold(p->pixel_thresh), prob_to_logit_threshold(p->link_thresh), flags,
+                (int*)nullptr, 0);
+}
+
 extern "C" int plh_min_area_boxes(const int32_t* pts, const int32_t* offsets, int n_sets, int32_t* boxes, float* rects,
                                   void* stream) {
   if (!pts || !offsets || !boxes) return PLH_E_NULL;

@@ -22,6 +22,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace plh {
 
@@ -36,27 +37,40 @@ static int g_prof_created = 0;
 static int g_prof_n = -1;  // -1: disabled
 
 // ------------------------------------------------------------------ workspace layout
-struct LossHeader {  // 384 B, zeroed by K1 (or a memset when there is no K1) at the start of every call
-  int n_seg_pos;
-  int cntP[8];
-  int cntN[8];
-  int n_selected;
-  unsigned ticket;    // K3 last-CTA election
-  int pad[13];
+constexpr int kSumReplicas = 16;
+enum { HC_N_SEG_POS = 0, HC_CNT_P = 1, HC_CNT_N = 9, HC_N_SELECTED = 17, HC_COUNT = 18 };
+struct LossHeader {  // zeroed by K1 (or a memset when there is no K1) at the start of every call
+  unsigned ticket;   // K3 last-CTA election
+  int pad[63];
   // 17 loss sums (s_pos[8], s_neg[8], s_pix): fp64 atomic adds of fp32 per-CTA partials.  The
   // partials carry 24 significant bits and similar exponents, so the fp64 additions are exact
   // and the result does not depend on the order in which the CTAs arrive (deterministic).
-  double sums[17];
-  double pad2[15];
+  // Same-address atomics serialise in one L2 slice, so CTA c adds into replica c % kSumReplicas
+  // (256 B apart) and the last CTA adds the replicas up in a fixed order.
+  double sums[kSumReplicas][32];
 };
-static_assert(sizeof(LossHeader) == 384, "header size");
+static_assert(sizeof(LossHeader) == 256 + kSumReplicas * 256, "header size");
+constexpr int kHdrInts = (int)(sizeof(LossHeader) / sizeof(int));
 
-struct ImageInfo {  // per image, written by K1
+struct ImageInfo {  // per image, 128 B; written by K1 (cnt: by the cluster form of K1, else by K2)
   int n_pos;
   int n_neg;
   unsigned thr_key;  // bit pattern of the threshold score
   int valid;         // 0: select no negatives
+  // integer normalisers of this image: n_seg_pos, cntP[8], cntN[8], n_selected (HC_* indices); the
+  // batch totals K3 needs are the sums over the images (integers: exact, order independent)
+  int cnt[HC_COUNT];
+  int pad[10];
 };
+static_assert(sizeof(ImageInfo) == 128, "one line per image");
+
+// batch totals of the HC_COUNT counters: lane l < HC_COUNT returns counter l summed over the images
+__device__ __forceinline__ int batch_count(const ImageInfo* info, int B, int lane) {
+  int v = 0;
+  if (lane < HC_COUNT)
+    for (int b = 0; b < B; ++b) v += __ldcg(&info[b].cnt[lane]);
+  return v;
+}
 constexpr int kKeysMaxCTAsPerImage = 64;  // K0 writes one (n_pos, n_neg) pair per CTA; K1 sums them (no atomics, no memset)
 
 constexpr int kMainThreads = 384;
@@ -96,6 +110,31 @@ enum { KEYS_MODEL = 0, KEYS_PIXELLINK = 1 };
 constexpr uint32_t kExcluded = 0x7FFFFFFFu;  // > every real key, and (t - key) stays negative in int32
 constexpr int kKeysThreads = 256;
 
+// key + class of one pixel (shared by K0 and the cluster form of K1)
+template <int KEYMODE>
+__device__ __forceinline__ uint32_t class_key(float sc, bool p, bool n, bool& isp, bool& isn) {
+  isp = p, isn = n;
+  return n ? __float_as_uint(sc) : ((KEYMODE == KEYS_MODEL) ? kExcluded : 0u);
+}
+template <int KEYMODE>
+__device__ __forceinline__ uint32_t logit_key(float2 x, float l, bool& isp, bool& isn) {
+  bool p, n;
+  if (KEYMODE == KEYS_MODEL) {  // int32 cast truncates (model.py:213), ==1 / ==0 (:199-202)
+    const int li = (int)l;
+    p = li == 1, n = li == 0;
+  } else {                      // pixellink.py:98-99: pos = labels > 0, neg = !pos
+    p = l > 0.f, n = !p;
+  }
+  return class_key<KEYMODE>(neg_class_score(x.x, x.y), p, n, isp, isn);
+}
+template <int KEYMODE, bool FROM_SCORES>
+__device__ __forceinline__ uint32_t pixel_key(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
+                                              const float* __restrict__ scores, const uint8_t* __restrict__ pos_mask,
+                                              const uint8_t* __restrict__ neg_mask, size_t px, bool& isp, bool& isn) {
+  if (FROM_SCORES) return class_key<KEYMODE>(scores[px], pos_mask[px] != 0, neg_mask[px] != 0, isp, isn);
+  return logit_key<KEYMODE>(__ldg(reinterpret_cast<const float2*>(pix_logits) + px), __ldg(pix_lab + px), isp, isn);
+}
+
 template <int KEYMODE, bool FROM_SCORES>
 __global__ void __launch_bounds__(kKeysThreads)
 score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
@@ -112,26 +151,9 @@ score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict_
   const size_t base = (size_t)b * N;
   int npos = 0, nneg = 0;
   for (int i = blockIdx.x * kKeysThreads + tid; i < N; i += gridDim.x * kKeysThreads) {
-    float sc;
     bool isp, isn;
-    if (FROM_SCORES) {
-      sc = scores[base + i];
-      isp = pos_mask[base + i] != 0, isn = neg_mask[base + i] != 0;
-    } else {
-      const float2 x = __ldg(reinterpret_cast<const float2*>(pix_logits) + base + i);
-      const float l = __ldg(pix_lab + base + i);
-      sc = neg_class_score(x.x, x.y);
-      if (KEYMODE == KEYS_MODEL) {  // int32 cast truncates (model.py:213), ==1 / ==0 (:199-202)
-        const int li = (int)l;
-        isp = li == 1, isn = li == 0;
-      } else {                      // pixellink.py:98-99: pos = labels > 0, neg = !pos
-        isp = l > 0.f, isn = !isp;
-      }
-    }
+    keys[base + i] = pixel_key<KEYMODE, FROM_SCORES>(pix_logits, pix_lab, scores, pos_mask, neg_mask, base + i, isp, isn);
     npos += isp, nneg += isn;
-    uint32_t key = __float_as_uint(sc);
-    if (!isn) key = (KEYMODE == KEYS_MODEL) ? kExcluded : 0u;
-    keys[base + i] = key;
   }
   npos = __reduce_add_sync(0xffffffffu, npos);
   nneg = __reduce_add_sync(0xffffffffu, nneg);
@@ -145,17 +167,299 @@ score_keys_kernel(const float* __restrict__ pix_logits, const float* __restrict_
 }
 
 // ------------------------------------------------------------------ K1: per-image OHEM threshold
-// Exact k-th smallest key, built MSB first: bit b of the answer is 1 iff fewer than k
-// keys are <= (prefix | all lower bits set).  Keys of real scores are <= bits(1.0f) =
-// 0x3F800000 < 2^30, so 30 rounds; excluded keys (0x7FFFFFFF) never count.
-// KPT > 0: the image's keys live in registers (KPT per thread); KPT == 0: they are read
-// from `keys` (shared memory copy if it fits, else global/L2) every round.
-template <int KPT>
+// Exact k-th smallest key, built MSB first: a bit of the answer is 1 iff fewer than k keys are
+// <= (prefix | that bit clear | all lower bits set).  Keys of real scores are <= bits(1.0f) =
+// 0x3F800000 < 2^30, so 30 bits; excluded keys (0x7FFFFFFF) never count.
+//
+// Cluster form (images up to 65536 px) — also does K0's work, so the loss chain is one launch
+// shorter: a cluster of 8 CTAs owns one image, every thread keeps KPT keys in registers, and each
+// round resolves TWO bits (three pivots).  Per round every warp posts its three counts, packed with
+// the round number into one 64-bit word, straight into the shared memory of all 8 CTAs of the
+// cluster (DSMEM store), then spins on its OWN shared memory until the 64 words of the round have
+// landed: no __syncthreads and no cluster barrier inside the loop (a cluster barrier alone costs
+// more than the counting).  Slots are double buffered by round parity; a slot is rewritten two
+// rounds later, which every warp can only reach after all warps have consumed the older value.
+constexpr int kClusterSize = 8;
+constexpr int kClThreads = 256;
+constexpr int kClWarps = kClThreads / 32;
+constexpr int kClSlots = kClusterSize * kClWarps;  // 64: two per lane
+constexpr int kClMaxKPT = 32;
+constexpr int kClReleaseRound = 13;  // of 15
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, int rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
+// post (c0,c1,c2) of this warp for exchange `e`, return the cluster-wide sums (same on every lane).
+// Barrier `e & 1` of every CTA expects the 64 words of the exchange (one arrival + 512 transaction
+// bytes); st.async delivers a word and signals the destination's barrier in one operation.
+__device__ __forceinline__ void cluster_exchange3(unsigned long long (*slot)[kClSlots], unsigned long long* mbar,
+                                                  int e, int rank, int warp, int lane, unsigned c0, unsigned c1,
+                                                  unsigned c2, int& t0, int& t1, int& t2) {
+  const unsigned long long v = ((unsigned long long)c2 << 32) | ((unsigned long long)c1 << 16) | c0;
+  unsigned long long* mine = slot[e & 1];
+  const uint32_t bar = smem_u32(mbar + (e & 1));
+  if (warp == 0 && lane == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kClSlots * 8) : "memory");
+  if (lane < kClusterSize) {
+    const uint32_t dst = mapa_u32(smem_u32(mine + rank * kClWarps + warp), lane);
+    const uint32_t rbar = mapa_u32(bar, lane);
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst), "l"(v),
+                 "r"(rbar)
+                 : "memory");
+  }
+  const uint32_t phase = (e >> 1) & 1;
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(bar), "r"(phase)
+                 : "memory");
+  } while (!done);
+  const unsigned long long v0 = mine[lane], v1 = mine[lane + 32];
+  t0 = __reduce_add_sync(0xffffffffu, (unsigned)(v0 & 0xffffu) + (unsigned)(v1 & 0xffffu));
+  t1 = __reduce_add_sync(0xffffffffu, (unsigned)((v0 >> 16) & 0xffffu) + (unsigned)((v1 >> 16) & 0xffffu));
+  t2 = __reduce_add_sync(0xffffffffu, (unsigned)((v0 >> 32) & 0xffffu) + (unsigned)((v1 >> 32) & 0xffffu));
+}
+
+// COUNTS (the loss): the kernel also does K2's work for its image.  The link labels of the slice are
+// packed to 2 bits per direction while the keys are loaded; once the threshold is known every thread
+// derives the selected mask of its pixels and the 18 integer normalisers, which are reduced over the
+// cluster into rank 0's shared memory (DSMEM atomics) and stored, not accumulated, into the image's
+// ImageInfo row: nothing to zero, nothing for K3 to wait for but this one kernel.
+template <int KEYMODE, bool FROM_SCORES, int KPT, bool COUNTS>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThreads, KPT <= 8 ? 5 : 4)
+ohem_select_cluster_kernel(const float* __restrict__ pix_logits, const float* __restrict__ pix_lab,
+                           const float* __restrict__ link_lab, const float* __restrict__ scores,
+                           const uint8_t* __restrict__ pos_mask, const uint8_t* __restrict__ neg_mask,
+                           const int* __restrict__ n_pos_override, int N, int ratio, ImageInfo* __restrict__ info,
+                           float* __restrict__ thr_out, uint8_t* __restrict__ mask, uint32_t* __restrict__ keys_out,
+                           LossHeader* __restrict__ hdr) {
+  static_assert(KPT <= kClMaxKPT && 32 * KPT < 65536, "per-warp counts are exchanged in 16-bit fields");
+  static_assert(!(COUNTS && FROM_SCORES), "the standalone OHNM has no link labels");
+  pdl_wait();
+  tl_start(1);
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(128) unsigned char s_stage[];  // COUNTS: link labels of up to 8 chunks (64 KB)
+  __shared__ unsigned long long s_slot[2][kClSlots];
+  __shared__ __align__(8) unsigned long long s_mbar[3];      // two exchange barriers + the staging barrier
+  __shared__ int s_c[HC_COUNT];    // this CTA's normalisers
+  __shared__ int s_tot[HC_COUNT];  // rank 0: the image's normalisers
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = blockIdx.x % kClusterSize;  // == %cluster_ctarank for a 1-D cluster
+  const int b = blockIdx.x / kClusterSize;
+  if (tid < HC_COUNT) s_c[tid] = 0, s_tot[tid] = 0;
+  if (!COUNTS && !FROM_SCORES && rank == 0 && tid < HC_COUNT) info[b].cnt[tid] = 0;  // the separate K2 accumulates into it
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[1])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[2])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();  // the staging barrier is used by this CTA right away
+  cluster_arrive();  // peers may signal this CTA's barriers only after it has initialised them
+  // the accumulators of K3 are cleared here (K1 precedes it on the stream)
+  if (hdr && blockIdx.x == 0)
+    for (int i = tid; i < kHdrInts; i += kClThreads) reinterpret_cast<int*>(hdr)[i] = 0;
+
+  // ---- this CTA's slice of the image: KPT chunks of 256 consecutive pixels, keys into registers.
+  // The link labels of the slice are needed only after the threshold is known: they are fetched into
+  // shared memory by bulk async copies (TMA, 8 KB per chunk, up to 8 chunks per pass) that fly while
+  // the selection rounds run, and cost no registers.
+  const size_t base = (size_t)b * N;
+  constexpr int KB = KPT < 8 ? KPT : 8;
+  auto stage_pass = [&](int j0) {  // one thread: bulk copies of chunks j0 .. j0+KB-1
+    const uint32_t bar = smem_u32(&s_mbar[2]);
+    uint32_t bytes = 0;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) bytes += (uint32_t)min(max(N - (rank * KPT + j0 + j) * kClThreads, 0), kClThreads) * 32u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+      const int i0 = (rank * KPT + j0 + j) * kClThreads;
+      const int valid = min(max(N - i0, 0), kClThreads);
+      if (valid > 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(s_stage + j * (kClThreads * 32))),
+                     "l"(link_lab + (base + i0) * 8), "r"(valid * 32), "r"(bar)
+                     : "memory");
+    }
+  };
+  uint32_t rk[KPT];
+  uint32_t posbits = 0, negbits = 0;  // bit j: pixel j of this thread is positive / negative
+  unsigned npos = 0, nneg = 0;
+#pragma unroll
+  for (int j0 = 0; j0 < KPT; j0 += KB) {
+    // all loads of a batch are issued before the first score is computed
+    float2 x[KB];
+    float l[KB];
+    uint8_t mp[KB], mn[KB];
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+      const int i = (rank * KPT + j0 + j) * kClThreads + tid;
+      const size_t px = base + (i < N ? i : N - 1);
+      if (FROM_SCORES) {
+        x[j].x = scores[px], mp[j] = pos_mask[px], mn[j] = neg_mask[px];
+      } else {
+        x[j] = __ldg(reinterpret_cast<const float2*>(pix_logits) + px);
+        l[j] = __ldg(pix_lab + px);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+      const int i = (rank * KPT + j0 + j) * kClThreads + tid;
+      bool isp, isn;
+      const uint32_t key = FROM_SCORES ? class_key<KEYMODE>(x[j].x, mp[j] != 0, mn[j] != 0, isp, isn)
+                                       : logit_key<KEYMODE>(x[j], l[j], isp, isn);
+      const bool in = i < N;
+      rk[j0 + j] = in ? key : kExcluded;
+      if (!COUNTS && keys_out && in) keys_out[base + i] = key;  // for the separate K2
+      isp = isp && in, isn = isn && in;
+      npos += isp, nneg += isn;
+      posbits |= (uint32_t)isp << (j0 + j), negbits |= (uint32_t)isn << (j0 + j);
+    }
+  }
+  npos = __reduce_add_sync(0xffffffffu, npos);
+  nneg = __reduce_add_sync(0xffffffffu, nneg);
+  cluster_wait();
+  int n_pos, n_neg, unused;
+  cluster_exchange3(s_slot, s_mbar, 0, rank, warp, lane, npos, nneg, 0u, n_pos, n_neg, unused);
+  tl_end(11);
+  if (COUNTS && tid == 0) stage_pass(0);  // behind the logits: the first exchange does not wait for 64 KB of labels
+  if (n_pos_override) n_pos = n_pos_override[b];  // OHNM_single_image(scores, n_pos, neg_mask): n_pos is an argument
+  // ---- k (model.py:170-173 / pixellink.py:116-120)
+  const long long kk = (long long)n_pos * ratio;
+  const int cap = (KEYMODE == KEYS_MODEL) ? n_neg : max(n_neg, 1);
+  const int k = (int)(kk < (long long)cap ? kk : (long long)cap);
+  const bool none = (n_pos <= 0) || (k <= 0);  // n_pos == 0 -> no_pos(); k == 0 -> "select none" 
+
+  uint32_t ans = 0;
+  if (!none) {  // uniform over the cluster
+    for (int e = 1; e <= 15; ++e) {
+      const int lo = 30 - 2 * e;  // this round resolves bits lo+1, lo
+      const uint32_t low = (1u << lo) - 1u;
+      const uint32_t p0 = ans | low, p1 = p0 | (1u << lo), p2 = p0 | (2u << lo);
+      // count(key > p) from the sign of (p - key): keys and pivots are < 2^31, so no wrap
+      unsigned g0 = 0, g1 = 0, g2 = 0;
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        g0 += (p0 - rk[j]) >> 31;
+        g1 += (p1 - rk[j]) >> 31;
+        g2 += (p2 - rk[j]) >> 31;
+      }
+      g0 = __reduce_add_sync(0xffffffffu, g0);
+      g1 = __reduce_add_sync(0xffffffffu, g1);
+      g2 = __reduce_add_sync(0xffffffffu, g2);
+      int t0, t1, t2;  // #keys <= pivot over the whole image
+      cluster_exchange3(s_slot, s_mbar, e, rank, warp, lane, 32u * KPT - g0, 32u * KPT - g1, 32u * KPT - g2, t0, t1, t2);
+      ans |= (uint32_t)((t0 < k) + (t1 < k) + (t2 < k)) << lo;
+    }
+  }
+  tl_end(12);
+  if (COUNTS) {
+    // ---- selected mask + normalisers of this thread's pixels (what K2 does in the general form)
+    // Branch-free so that the pixels interleave; the class tests are float compares instead of the
+    // reference's int cast (same result for every finite label: (int)l == 1 <=> 1 <= l < 2 and
+    // (int)l == 0 <=> |l| < 1), which keeps the quarter-rate F2I unit out of the loop.
+    // Two sweeps over the staged labels (directions 0-3, then 4-7): 8 live counters instead of 16 keep
+    // the kernel at <= 48 registers, which is what lets the decode's kernels share the SMs with it.
+    unsigned nsp = 0, nsel = 0;
+#pragma unroll
+    for (int j0 = 0; j0 < KPT; j0 += KB) {
+      {  // the pass's labels have landed (pass 0 was issued before the selection rounds)
+        const uint32_t bar = smem_u32(&s_mbar[2]);
+        const uint32_t phase = (j0 / KB) & 1;
+        uint32_t done;
+        do {
+          asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                       : "=r"(done)
+                       : "r"(bar), "r"(phase)
+                       : "memory");
+        } while (!done);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        unsigned cP[4] = {0u, 0u, 0u, 0u}, cN[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int jj = 0; jj < KB; ++jj) {
+          const int j = j0 + jj;
+          const int i = (rank * KPT + j) * kClThreads + tid;
+          const bool in = i < N;
+          const bool pos = (posbits >> j) & 1u, neg = (negbits >> j) & 1u;  // both false outside the image
+          const bool M = pos || (neg && !none && rk[j] <= ans);  // model.py:178 ties at the threshold are all selected
+          if (h == 0) {
+            nsel += M;
+            nsp += (KEYMODE == KEYS_PIXELLINK) ? M : pos;  // pixellink.py:155 sum(selected) / model.py:221 sum(pos)
+            if (in) mask[base + i] = M ? 1 : 0;
+          }
+          const bool Ml = (KEYMODE == KEYS_PIXELLINK) ? in : M;  // pixellink.py:193-194: not x the OHEM mask
+          // (stale shared memory outside the image: masked by Ml)
+          const float4 lq = *reinterpret_cast<const float4*>(s_stage + jj * (kClThreads * 32) + tid * 32 + h * 16);
+          const float lv[4] = {lq.x, lq.y, lq.z, lq.w};
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            bool lp, ln;
+            if (KEYMODE == KEYS_PIXELLINK) lp = lv[d] > 0.f, ln = !lp;          // pixellink.py:185-186
+            else lp = lv[d] >= 1.f && lv[d] < 2.f, ln = fabsf(lv[d]) < 1.f;      // model.py:238-241
+            cP[d] += (Ml && lp), cN[d] += (Ml && ln);
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int cp = __reduce_add_sync(0xffffffffu, cP[d]);
+          const int cn = __reduce_add_sync(0xffffffffu, cN[d]);
+          if (lane == 0) {
+            if (cp) atomicAdd(&s_c[HC_CNT_P + 4 * h + d], cp);
+            if (cn) atomicAdd(&s_c[HC_CNT_N + 4 * h + d], cn);
+          }
+        }
+      }
+      if (j0 + KB < KPT) {  // next pass reuses the staging buffer
+        __syncthreads();
+        if (tid == 0) stage_pass(j0 + KB);
+      }
+    }
+    nsp = __reduce_add_sync(0xffffffffu, nsp);
+    nsel = __reduce_add_sync(0xffffffffu, nsel);
+    if (lane == 0) {
+      if (nsp) atomicAdd(&s_c[HC_N_SEG_POS], nsp);
+      if (nsel) atomicAdd(&s_c[HC_N_SELECTED], nsel);
+    }
+    tl_end(13);
+    __syncthreads();
+    if (tid < HC_COUNT && s_c[tid]) atomicAdd(cg::this_cluster().map_shared_rank(&s_tot[tid], 0), s_c[tid]);
+  }
+  tl_end(14);
+  pdl_release();
+  // no CTA may retire while a peer's store to it could still be in flight; rank 0 reads the totals after it
+  cluster_arrive();
+  cluster_wait();
+  if (rank == 0) {
+    if (COUNTS && tid < HC_COUNT) info[b].cnt[tid] = s_tot[tid];
+    if (tid == 0) {
+      info[b].n_pos = n_pos, info[b].n_neg = n_neg;
+      info[b].thr_key = ans;
+      info[b].valid = none ? 0 : 1;
+      // NaN when nothing is selected: `score <= NaN` is false for every pixel
+      if (thr_out) thr_out[b] = none ? __int_as_float(0x7fc00000) : __uint_as_float(ans);
+    }
+  }
+  tl_end(1);
+}
+
+// General form (any image size): one CTA per image after K0; keys are re-read every round from a
+// shared-memory copy if it fits, else from global/L2; one bit per round.
 __global__ void __launch_bounds__(kSelectThreads, 1)
 ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict__ counts, int ncounts,
                    const int* __restrict__ n_pos_override, int N, int ratio, int keymode, int use_smem,
                    ImageInfo* __restrict__ info, float* __restrict__ thr_out, LossHeader* __restrict__ hdr) {
-  pdl_wait_and_release();
+  pdl_wait();
   tl_start(1);
   extern __shared__ __align__(16) uint32_t skeys[];
   __shared__ int s_w[2][32];
@@ -164,9 +468,9 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict
   const int lane = tid & 31, warp = tid >> 5;
   const uint32_t* gkeys = keys_all + (size_t)b * N;
 
-  // the counters K2/K3 accumulate into are cleared here (K1 precedes them on the stream)
-  if (hdr && b == 0 && tid < (int)(sizeof(LossHeader) / sizeof(int))) reinterpret_cast<int*>(hdr)[tid] = 0;
-  static_assert(sizeof(LossHeader) / sizeof(int) <= kSelectThreads, "header is cleared by one CTA");
+  if (hdr && b == 0)
+    for (int i = tid; i < kHdrInts; i += kSelectThreads) reinterpret_cast<int*>(hdr)[i] = 0;
+  if (tid < HC_COUNT) info[b].cnt[tid] = 0;  // K2 accumulates into it
   int npos = 0, nneg = 0;
   if (warp == 0) {
     for (int i = lane; i < ncounts; i += 32) {
@@ -180,24 +484,16 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict
   __syncthreads();
   npos = s_w[0][0], nneg = s_w[0][1];
   __syncthreads();
-  if (n_pos_override) npos = n_pos_override[b];  // OHNM_single_image(scores, n_pos, neg_mask): n_pos is an argument
-  // ---- k (model.py:170-173 / pixellink.py:116-120)
+  if (n_pos_override) npos = n_pos_override[b];
   const long long kk = (long long)npos * ratio;
   const int cap = (keymode == KEYS_MODEL) ? nneg : max(nneg, 1);
   const int k = (int)(kk < (long long)cap ? kk : (long long)cap);
-  const bool none = (npos <= 0) || (k <= 0);  // n_pos == 0 -> no_pos(); k == 0 -> "select none" 
+  const bool none = (npos <= 0) || (k <= 0);
 
   uint32_t ans = 0;
   if (!none) {
-    uint32_t rk[KPT > 0 ? KPT : 1];
     const uint32_t* keys = gkeys;
-    if (KPT > 0) {
-#pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        const int i = tid + j * kSelectThreads;
-        rk[j] = i < N ? __ldg(gkeys + i) : kExcluded;
-      }
-    } else if (use_smem) {
+    if (use_smem) {
       for (int i = tid; i < N; i += kSelectThreads) skeys[i] = __ldg(gkeys + i);
       keys = skeys;
       __syncthreads();
@@ -205,21 +501,7 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict
     for (int bit = 29; bit >= 0; --bit) {
       const uint32_t t = ans | ((1u << bit) - 1u);
       int c = 0;
-      if (KPT > 0) {
-        // count(key > t) from the sign of (t - key): keys and t are < 2^31, so the subtraction
-        // cannot wrap; two instructions per key (IADD3 + LEA.HI) in four independent chains
-        unsigned g0 = 0, g1 = 0, g2 = 0, g3 = 0;
-#pragma unroll
-        for (int j = 0; j < KPT; j += 4) {
-          g0 += (t - rk[j]) >> 31;
-          g1 += (t - rk[j + 1]) >> 31;
-          g2 += (t - rk[j + 2]) >> 31;
-          g3 += (t - rk[j + 3]) >> 31;
-        }
-        c = KPT - (int)(g0 + g1 + g2 + g3);
-      } else {
-        for (int i = tid; i < N; i += kSelectThreads) c += (keys[i] <= t);
-      }
+      for (int i = tid; i < N; i += kSelectThreads) c += (keys[i] <= t);
       c = __reduce_add_sync(0xffffffffu, c);
       int* sw = s_w[bit & 1];  // double-buffered: one barrier per round
       if (lane == 0) sw[warp] = c;
@@ -228,11 +510,11 @@ ohem_select_kernel(const uint32_t* __restrict__ keys_all, const int2* __restrict
       if (total < k) ans |= (1u << bit);
     }
   }
+  pdl_release();
   if (tid == 0) {
     info[b].n_pos = npos, info[b].n_neg = nneg;
     info[b].thr_key = ans;
     info[b].valid = none ? 0 : 1;
-    // NaN when nothing is selected: `score <= NaN` is false for every pixel
     if (thr_out) thr_out[b] = none ? __int_as_float(0x7fc00000) : __uint_as_float(ans);
   }
   tl_end(1);
@@ -243,8 +525,8 @@ constexpr int kCountsThreads = 512;
 template <int VARIANT>
 __global__ void __launch_bounds__(kCountsThreads)
 ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ pix_lab,
-                   const float* __restrict__ link_lab, const ImageInfo* __restrict__ info, int N,
-                   uint8_t* __restrict__ mask, LossHeader* __restrict__ hdr) {
+                   const float* __restrict__ link_lab, ImageInfo* __restrict__ info, int N,
+                   uint8_t* __restrict__ mask) {
   pdl_wait_and_release();
   tl_start(2);
   __shared__ int s_c[18];
@@ -306,7 +588,7 @@ ohem_counts_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ 
   }
   __syncthreads();
   // integer atomics: exact and order independent
-  if (tid < 18 && s_c[tid]) atomicAdd(reinterpret_cast<int*>(hdr) + tid, s_c[tid]);  // header ints 0..17
+  if (tid < HC_COUNT && s_c[tid]) atomicAdd(&info[b].cnt[tid], s_c[tid]);  // row zeroed by K1 / the memset
   tl_end(2);
 }
 
@@ -318,6 +600,7 @@ struct MainArgs {
   const float* link_lab;
   const uint8_t* mask;
   LossHeader* hdr;
+  const ImageInfo* info;
   float* stats;
   float* grad_pix;
   float* grad_link;
@@ -375,22 +658,27 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
   pdl_wait_and_release();
   tl_start(3);
   __shared__ float s_red[kMainThreads / 32][4][5];
+  __shared__ int s_cnt[HC_COUNT];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int j = tid & 3;  // which quarter of a pixel: link directions 2j and 2j+1
 
   // ---- normalisers (final: K2 completed before this launch)
-  const LossHeader* hdr = a.hdr;
   float pix_scale, invP[2], invN[2];
   {
-    const float nsp = (float)hdr->n_seg_pos;
+    if (warp == 0) {
+      const int c = batch_count(a.info, B, lane);
+      if (lane < HC_COUNT) s_cnt[lane] = c;
+    }
+    __syncthreads();
+    const float nsp = (float)s_cnt[HC_N_SEG_POS];
     if (VARIANT == PLH_VARIANT_MODEL) pix_scale = nsp > 0.f ? __fdiv_rn(2.f, nsp) : 0.f;  // model.py:226-233
     else if (VARIANT == PLH_VARIANT_POS_ONLY) pix_scale = __fdiv_rn(2.f, nsp);            // vgg16 :267 unguarded
     else pix_scale = __fdiv_rn(2.f, (float)((long long)B * N));                          // pixellink.py:160,170
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const float cp = (float)hdr->cntP[2 * j + c], cn = (float)hdr->cntN[2 * j + c];
+      const float cp = (float)s_cnt[HC_CNT_P + 2 * j + c], cn = (float)s_cnt[HC_CNT_N + 2 * j + c];
       if (VARIANT == PLH_VARIANT_PIXELLINK) {  // pixellink.py:198-211 zero guards
         invP[c] = cp != 0.f ? __fdiv_rn(1.f, cp) : 0.f;
         invN[c] = cn != 0.f ? __fdiv_rn(1.f, cn) : 0.f;
@@ -523,7 +811,7 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kMainThreads / 32; ++w) s += s_red[w][jj][slot];
-    atomicAdd(&a.hdr->sums[tid], (double)s);  // exact in fp64: order independent (see LossHeader)
+    atomicAdd(&a.hdr->sums[blockIdx.x % kSumReplicas][tid], (double)s);  // exact in fp64: order independent
   }
   __threadfence();
   __syncthreads();
@@ -536,13 +824,16 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
   __threadfence();
   if (warp == 0) {
     float* st = a.stats;
-    const int* hi = reinterpret_cast<const int*>(a.hdr);
-    const float nsp = (float)__ldcg(hi + 0);                     // n_seg_pos
-    const float nsel = (float)__ldcg(hi + 17);                   // n_selected
+    const float nsp = (float)s_cnt[HC_N_SEG_POS], nsel = (float)s_cnt[HC_N_SELECTED];
     const int dd = lane & 7;
-    const float cp = (float)__ldcg(hi + 1 + dd), cn = (float)__ldcg(hi + 9 + dd);
-    const float s_pos = (float)__ldcg(&a.hdr->sums[dd]), s_neg = (float)__ldcg(&a.hdr->sums[8 + dd]);
-    const double s_pix_d = __ldcg(&a.hdr->sums[16]);
+    const float cp = (float)s_cnt[HC_CNT_P + dd], cn = (float)s_cnt[HC_CNT_N + dd];
+    double sum = 0.0;  // lane l < 17: sum l, replicas added in a fixed order (independent loads: one round trip)
+    if (lane < 17) {
+#pragma unroll
+      for (int r = 0; r < kSumReplicas; ++r) sum += __ldcg(&a.hdr->sums[r][lane]);
+    }
+    const float s_pos = (float)__shfl_sync(0xffffffffu, sum, dd), s_neg = (float)__shfl_sync(0xffffffffu, sum, 8 + dd);
+    const double s_pix_d = __shfl_sync(0xffffffffu, sum, 16);
     const float s_pix = (float)s_pix_d;
     float Ld;
     if (VARIANT == PLH_VARIANT_PIXELLINK)
@@ -575,7 +866,10 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
     // leave the accumulators clean, so that this kernel can be relaunched on the same prepared
     // workspace (plh_loss_params.reserved[0] = 1: measurement of the main pass alone)
     __syncwarp();
-    if (lane < 17) a.hdr->sums[lane] = 0.0;
+    if (lane < 17) {
+#pragma unroll
+      for (int r = 0; r < kSumReplicas; ++r) a.hdr->sums[r][lane] = 0.0;
+    }
     if (lane == 0) a.hdr->ticket = 0u;
   }
   tl_end(3);
@@ -639,39 +933,54 @@ static int launch_main(bool grad, bool flags, int grid, cudaStream_t s, const Ma
   return rc;
 }
 
+static inline bool select_uses_cluster(int N) { return N <= kClusterSize * kClThreads * kClMaxKPT; }
+
 // K0 + K1
 template <int KEYMODE, bool FROM_SCORES>
-static int launch_keys_and_select(const float* pix_logits, const float* pix_lab, const float* scores,
-                                  const uint8_t* pos, const uint8_t* neg, const int* n_pos_override, int B, int N,
-                                  int ratio, uint32_t* keys, int2* counts, ImageInfo* info, float* thr_out,
-                                  LossHeader* hdr, cudaStream_t s) {
+static int launch_keys_and_select(const float* pix_logits, const float* pix_lab, const float* link_lab,
+                                  const float* scores, const uint8_t* pos, const uint8_t* neg,
+                                  const int* n_pos_override, int B, int N, int ratio, uint32_t* keys, int2* counts,
+                                  ImageInfo* info, float* thr_out, uint8_t* mask, LossHeader* hdr, bool fuse_counts,
+                                  cudaStream_t s) {
+  int rc;
+  if (select_uses_cluster(N)) {
+    // cluster form: scores, keys, threshold (and for the loss: mask + normalisers) in one launch
+#define PLH_CLUSTER(KPT)                                                                                         \
+  {                                                                                                              \
+    const bool fused = !FROM_SCORES && fuse_counts;                                                            \
+    auto kern = fused ? ohem_select_cluster_kernel<KEYMODE, FROM_SCORES, KPT, !FROM_SCORES>                      \
+                      : ohem_select_cluster_kernel<KEYMODE, FROM_SCORES, KPT, false>;                            \
+    const size_t smem = fused ? (size_t)(KPT < 8 ? KPT : 8) * kClThreads * 32 : 0;                               \
+    static bool attr_set = false; /* idempotent; benign if raced */                                              \
+    if (smem > 48 * 1024 && !attr_set) {                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+      if (e != cudaSuccess) return (int)e;                                                                       \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    rc = launch(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg,    \
+                n_pos_override, N, ratio, info, thr_out, mask, FROM_SCORES ? (uint32_t*)nullptr : keys, hdr);    \
+  }
+    if (N <= kClusterSize * kClThreads * 2) PLH_CLUSTER(2)
+    else if (N <= kClusterSize * kClThreads * 8) PLH_CLUSTER(8)
+    else PLH_CLUSTER(kClMaxKPT)
+#undef PLH_CLUSTER
+    return rc;
+  }
   const int per_image = std::max(1, std::min({(N + kKeysThreads - 1) / kKeysThreads, (kNumSMs * 8 + B - 1) / B,
                                               kKeysMaxCTAsPerImage}));
-  int rc = launch(score_keys_kernel<KEYMODE, FROM_SCORES>, dim3(per_image, B), kKeysThreads, 0, s, pix_logits, pix_lab, scores, pos,
-                                                                                      neg, N, keys, counts);
+  rc = launch(score_keys_kernel<KEYMODE, FROM_SCORES>, dim3(per_image, B), kKeysThreads, 0, s, pix_logits, pix_lab,
+              scores, pos, neg, N, keys, counts);
   if (rc) return rc;
-#define PLH_SELECT(KPT, SMEM, USE)                                                                                   \
-  rc = launch(ohem_select_kernel<KPT>, B, kSelectThreads, SMEM, s, keys, counts, per_image, n_pos_override, N, ratio, KEYMODE, \
-                                                         USE, info, thr_out, hdr)
-  if (N <= kSelectThreads * 4) {
-    PLH_SELECT(4, 0, 0);
-  } else if (N <= kSelectThreads * 16) {
-    PLH_SELECT(16, 0, 0);
-  } else if (N <= kSelectThreads * 36) {
-    PLH_SELECT(36, 0, 0);
-  } else {
-    const bool use_smem = (size_t)N * 4 <= kSmemKeysMaxBytes;
-    static bool attr_set = false;  // idempotent; benign if raced
-    if (use_smem && !attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(ohem_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kSmemKeysMaxBytes);
-      if (e != cudaSuccess) return (int)e;
-      attr_set = true;
-    }
-    PLH_SELECT(0, use_smem ? (size_t)N * 4 : 0, use_smem ? 1 : 0);
+  const bool use_smem = (size_t)N * 4 <= kSmemKeysMaxBytes;
+  static bool attr_set = false;  // idempotent; benign if raced
+  if (use_smem && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ohem_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemKeysMaxBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
   }
-#undef PLH_SELECT
-  return rc;
+  return launch(ohem_select_kernel, B, kSelectThreads, use_smem ? (size_t)N * 4 : 0, s, keys, counts, per_image,
+                n_pos_override, N, ratio, KEYMODE, use_smem ? 1 : 0, info, thr_out, hdr);
 }
 
 #ifdef PLH_TIMELINE
@@ -710,38 +1019,41 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   cudaError_t e;
   int rc = PLH_OK;
   const bool main_only = (p->reserved[0] & 1) != 0;  // K0-K2 already ran on this workspace
+  const bool fuse_counts = (p->reserved[0] & 2) == 0;  // bit 1: keep the normalisers in their own pass (K2)
   // K0 + K1 (not needed for the positives-only variant: there is no mining, vgg16 :265)
   if (main_only) {
   } else if (p->variant == PLH_VARIANT_MODEL)
-    rc = launch_keys_and_select<KEYS_MODEL, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
-                                                   p->neg_pos_ratio, keys, counts, info, stats + PLH_ST_THR, hdr, s);
+    rc = launch_keys_and_select<KEYS_MODEL, false>(pix_logits, pix_lab, link_lab, nullptr, nullptr, nullptr, nullptr, B,
+                                                   N, p->neg_pos_ratio, keys, counts, info, stats + PLH_ST_THR, mask,
+                                                   hdr, fuse_counts, s);
   else if (p->variant == PLH_VARIANT_PIXELLINK)
-    rc = launch_keys_and_select<KEYS_PIXELLINK, false>(pix_logits, pix_lab, nullptr, nullptr, nullptr, nullptr, B, N,
-                                                       p->neg_pos_ratio, keys, counts, info, stats + PLH_ST_THR, hdr,
-                                                       s);
+    rc = launch_keys_and_select<KEYS_PIXELLINK, false>(pix_logits, pix_lab, link_lab, nullptr, nullptr, nullptr,
+                                                       nullptr, B, N, p->neg_pos_ratio, keys, counts, info,
+                                                       stats + PLH_ST_THR, mask, hdr, fuse_counts, s);
   else {
     e = cudaMemsetAsync(stats + PLH_ST_THR, 0xff, sizeof(float) * B, s);  // thr[b] = NaN
-    if (e == cudaSuccess) e = cudaMemsetAsync(hdr, 0, sizeof(LossHeader), s);
+    // header and the ImageInfo rows (adjacent in the workspace): K2 accumulates into the rows
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + l.header, 0, l.counts - l.header, s);
     rc = e == cudaSuccess ? PLH_OK : (int)e;
   }
   if (rc) return rc;
-  // K2
-  if (!main_only) {
+  // K2 (the cluster form of K1 has already done this)
+  if (!main_only && (p->variant == PLH_VARIANT_POS_ONLY || !select_uses_cluster(N) || !fuse_counts)) {
     const int per_image = std::max(1, std::min((N + kCountsThreads - 1) / kCountsThreads, (kNumSMs * 2 + B - 1) / B));
     const dim3 grid(per_image, B);
     if (p->variant == PLH_VARIANT_MODEL)
-      rc = launch(ohem_counts_kernel<PLH_VARIANT_MODEL>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask, hdr);
+      rc = launch(ohem_counts_kernel<PLH_VARIANT_MODEL>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask);
     else if (p->variant == PLH_VARIANT_POS_ONLY)
-      rc = launch(ohem_counts_kernel<PLH_VARIANT_POS_ONLY>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask, hdr);
+      rc = launch(ohem_counts_kernel<PLH_VARIANT_POS_ONLY>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask);
     else
-      rc = launch(ohem_counts_kernel<PLH_VARIANT_PIXELLINK>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask, hdr);
+      rc = launch(ohem_counts_kernel<PLH_VARIANT_PIXELLINK>, grid, kCountsThreads, 0, s, keys, pix_lab, link_lab, info, N, mask);
     if (rc) return rc;
   }
   // K3
   {
     MainArgs a;
     a.pix_logits = pix_logits, a.link_logits = link_logits, a.pix_lab = pix_lab, a.link_lab = link_lab;
-    a.mask = mask, a.hdr = hdr, a.stats = stats;
+    a.mask = mask, a.hdr = hdr, a.info = info, a.stats = stats;
     a.grad_pix = grad_pix, a.grad_link = grad_link, a.flags = decode_flags;
     a.total_px = total_px, a.alpha = p->focal_alpha, a.gamma = p->focal_gamma;
     a.tp_logit = dp ? prob_to_logit_threshold(dp->pixel_thresh) : 0.f;
@@ -815,10 +1127,11 @@ extern "C" int plh_ohnm_batch(const float* scores, const uint8_t* pos_mask, cons
   uint32_t* keys = (uint32_t*)((char*)workspace + info_bytes + cnt_bytes);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = variant == PLH_VARIANT_MODEL
-               ? launch_keys_and_select<KEYS_MODEL, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B, N,
-                                                          neg_pos_ratio, keys, counts, info, thr, nullptr, s)
-               : launch_keys_and_select<KEYS_PIXELLINK, true>(nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B,
-                                                              N, neg_pos_ratio, keys, counts, info, thr, nullptr, s);
+               ? launch_keys_and_select<KEYS_MODEL, true>(nullptr, nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B,
+                                                          N, neg_pos_ratio, keys, counts, info, thr, nullptr, nullptr, false, s)
+               : launch_keys_and_select<KEYS_PIXELLINK, true>(nullptr, nullptr, nullptr, scores, pos_mask, neg_mask,
+                                                              n_pos, B, N, neg_pos_ratio, keys, counts, info, thr,
+                                                              nullptr, nullptr, false, s);
   if (rc) return rc;
   const long long total = (long long)B * N;
   const int grid = (int)std::min<long long>((total + 255) / 256, kNumSMs * 8);

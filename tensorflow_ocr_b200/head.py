@@ -10,6 +10,7 @@ tool/pixellink_fn.py:114,157).
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -33,10 +34,11 @@ class LossConfig:
     focal_alpha: float = 0.25     # Lin et al. 2017 (not in the reference)
     focal_gamma: float = 2.0
     main_only: bool = False       # measurement hook: rerun the main pass on an already prepared workspace
+    split_counts: bool = False    # scheduling hint: normalisers in their own pass instead of fused into the selection
 
     def c_struct(self):
         p = _lib.LossParams(self.variant, self.term, self.neg_pos_ratio, self.focal_alpha, self.focal_gamma)
-        p.reserved[0] = 1 if self.main_only else 0
+        p.reserved[0] = (1 if self.main_only else 0) | (2 if self.split_counts else 0)
         return p
 
 
@@ -172,9 +174,7 @@ def ohnm_batch_raw(scores, pos_mask, neg_mask, variant=_lib.VARIANT_MODEL, ratio
     _require_gpu(dev)
     sel = torch.empty((B, N), dtype=torch.float32, device=dev)
     thr = torch.empty((B,), dtype=torch.float32, device=dev)
-    # ImageInfo[B] | per-CTA counts [B*64] | keys [B*N]
-    ws = torch.empty(((B * 16 + 255) // 256) * 256 + ((B * 64 * 8 + 255) // 256) * 256 + B * N * 4,
-                     dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.plh_workspace_bytes(_lib.OP_LOSS, B, 1, N, 0), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.plh_ohnm_batch(_p(scores), _p(pos_mask), _p(neg_mask), _p(n_pos), B, N, variant, ratio, _p(sel),
                                 _p(thr), _p(ws), 0 if ws is None else ws.numel(), _stream(dev))
@@ -236,6 +236,23 @@ def decode_from_flags_raw(flags, cfg: DecodeConfig = DecodeConfig(), out: Option
     return out
 
 
+def decode_flags_raw(pix_logits, link_logits, cfg: DecodeConfig = DecodeConfig(), out: Optional[dict] = None) -> dict:
+    """plh_decode_flags: the threshold pass alone -> out["flags"] uint16 [B,H,W]."""
+    lib = _lib.load()
+    B, H, W = pix_logits.shape[:3]
+    dev = pix_logits.device
+    _require_gpu(dev)
+    out = {} if out is None else out
+    flags = out.get("flags")
+    if flags is None or flags.shape != (B, H, W):
+        flags = out["flags"] = torch.empty((B, H, W), dtype=torch.int16, device=dev)
+    dp = cfg.c_struct()
+    with torch.cuda.device(dev):
+        rc = lib.plh_decode_flags(_p(pix_logits), _p(link_logits), B, H, W, C.byref(dp), _p(flags), _stream(dev))
+    _lib.check(rc, "plh_decode_flags")
+    return out
+
+
 _aux_streams = {}
 
 
@@ -267,9 +284,14 @@ def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossCo
     cur = torch.cuda.current_stream(dev)
     aux = _aux_stream(dev)
     aux.wait_stream(cur)
+    # Loss first: its cluster launch (8 co-scheduled CTAs per image) must not queue behind the decode's
+    # full-occupancy threshold kernel.  The normalisers stay in their own pass here (split_counts): the
+    # fused selection kernel is the shortest loss chain on its own, but next to the decode its longer
+    # residency costs the tile labelling more than the saved launch gains.
+    lstep = dataclasses.replace(lcfg, split_counts=True)
+    pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, lstep, True, False, None, out)
     with torch.cuda.stream(aux):
         decode_raw(pix_logits, link_logits, dcfg, out, want_rects)
-    pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg, True, False, None, out)
     cur.wait_stream(aux)
     return out
 

@@ -196,3 +196,25 @@ def test_loss_random_shapes_and_variants(seed, cuda_dev):
     assert rel_err(out["grad_pixel"], ref["grad_pixel"]) <= TOL
     assert rel_err(out["grad_link"], ref["grad_link"]) <= TOL
     assert np.array_equal(out["ohem_mask"].astype(np.float32), ref["ohem_mask"])
+
+
+def test_loss_large_image_general_select_path(cuda_dev):
+    """> 65536 px per image: K0 + the one-CTA-per-image selection (keys not register resident)."""
+    from oracle import pixellink_loss as O
+    from tensorflow_ocr_b200 import head, synth
+    for H, W in ((272, 256), (512, 160)):
+        inp = synth.make_batch(77, 2, H, W, "G", edge_images=False)
+        ref = O.loss_model(inp["pix_lab"], inp["pix_logits"], inp["link_lab"], inp["link_logits"])
+        _compare(_run(inp, head.LossConfig()), ref, 2)
+
+
+@pytest.mark.parametrize("variant", ["model", "pixellink"])
+def test_split_counts_hint_is_result_neutral(variant, cuda_dev):
+    """plh_loss_params.reserved[0] bit 1 only moves the mask + normaliser pass into its own kernel."""
+    from tensorflow_ocr_b200 import _lib, head, synth
+    inp = synth.make_batch(91, 5, 48, 80, "G", edge_images=True)
+    v = _lib.VARIANT_MODEL if variant == "model" else _lib.VARIANT_PIXELLINK
+    a = _run(inp, head.LossConfig(variant=v))
+    b = _run(inp, head.LossConfig(variant=v, split_counts=True))
+    for k in ("stats", "grad_pixel", "grad_link", "ohem_mask"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k

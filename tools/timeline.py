@@ -20,7 +20,10 @@ torch.cuda.set_stream(ms)
 lcfg, dcfg = head.LossConfig(), head.DecodeConfig(max_boxes=128)
 def step(i):
     d = sets[i % 6]
-    head.loss_and_decode_raw(d["pix_logits"], d["link_logits"], d["pix_lab"], d["link_lab"], lcfg, dcfg, d["out"])
+    if os.environ.get("TL_MODE", "fused") == "loss":
+        head.pixellink_loss_raw(d["pix_logits"], d["link_logits"], d["pix_lab"], d["link_lab"], lcfg, True, False, None, d["out"])
+    else:
+        head.loss_and_decode_raw(d["pix_logits"], d["link_logits"], d["pix_lab"], d["link_lab"], lcfg, dcfg, d["out"])
 for i in range(6):
     step(i)
 torch.cuda.synchronize()
@@ -35,8 +38,8 @@ torch.cuda.set_stream(ms)
 for i in range(30):
     graphs[i % 6].replay()
 torch.cuda.synchronize()
-names = ["K0 keys", "K1 select", "K2 counts", "K3 main", "D0 flags", "D1a tile_cc", "D1b cross", "D2 flatten", "D3 roots", "D4 labels", "D5 rects"]
-acc = np.zeros((11, 2))
+names = ["K0 keys", "K1 select", "K2 counts", "K3 main", "D0 flags", "D1a tile_cc", "D1b cross", "D2 flatten", "D3 roots", "D4 labels", "D5 rects", "K1 preamble", "K1 loop", "K1 counted", "K1 posted"]
+acc = np.zeros((15, 2))
 reps = 20
 for r in range(reps):
     lib.plh_timeline_reset()
@@ -44,9 +47,10 @@ for r in range(reps):
     torch.cuda.synchronize()
     buf = np.zeros(64, np.uint64)
     lib.plh_timeline_read(buf.ctypes.data_as(ctypes.c_void_p))
-    t = buf.astype(np.int64).reshape(32, 2)[:11]
-    t0 = t[:, 0].min()
-    acc += (t - t0) / 1e3
+    t = buf.astype(np.int64).reshape(32, 2)[:15]
+    used = t[:, 1] > 0
+    t0 = t[used & (t[:, 0] > 0) & (t[:, 0] < 2**62), 0].min()
+    acc += np.where(used[:, None], (t - t0) / 1e3, 0.0)
 acc /= reps
 print("%-14s %9s %9s %9s" % ("kernel", "start us", "end us", "dur us"))
 for n, (a, b) in zip(names, acc):
