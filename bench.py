@@ -308,9 +308,20 @@ def run_gpu(args):
         _lib.check(lib.plh_profile_begin(min(nprof, 4096)), "plh_profile_begin")
         for i in range(min(nprof, 4096)):
             step(i)
-        tot, n = ctypes.c_float(0), ctypes.c_int(0)
+        tot, n, win = ctypes.c_float(0), ctypes.c_int(0), ctypes.c_float(0)
+        _lib.check(lib.plh_profile_kernel_window(ctypes.byref(win)), "plh_profile_kernel_window")
         _lib.check(lib.plh_profile_end(ctypes.byref(tot), ctypes.byref(n)), "plh_profile_end")
         in_step_us = tot.value * 1e3 / max(1, n.value)
+        in_step_window_us = win.value * 1e3 / max(1, n.value)
+        # (3) device-side window of the kernel alone (first CTA start .. last CTA end, %globaltimer):
+        #     what is left of (1) after subtracting it is launch + drain latency between dependent launches
+        nwin = min(nprof, 600)
+        _lib.check(lib.plh_profile_begin(nwin), "plh_profile_begin")
+        for i in range(nwin):
+            loss_call(i, only)
+        _lib.check(lib.plh_profile_kernel_window(ctypes.byref(win)), "plh_profile_kernel_window")
+        _lib.check(lib.plh_profile_end(ctypes.byref(tot), ctypes.byref(n)), "plh_profile_end")
+        alone_window_us = win.value * 1e3 / max(1, n.value)
         assert abs(outs[0]["stats"][0].item() - ref_loss) <= 1e-6 * abs(ref_loss)   # main-only reruns compute the same loss
 
         peak, peak_src = _peaks()
@@ -323,6 +334,12 @@ def run_gpu(args):
                     "method": "kernel relaunched alone back to back (CUDA graph of %d launches over the rotating "
                               "input sets, replayed), CUDA events around the sequence / launches" % NSETS,
                     "us_per_launch_inside_step_event_bracketed": in_step_us,
+                    "us_device_window_alone": alone_window_us,
+                    "us_device_window_inside_step": in_step_window_us,
+                    "frac_device_window_alone": alg / (alone_window_us * 1e-6) / 1e9 / peak,
+                    "window_note": "device window = first CTA start to last CTA end (%globaltimer); us_per_launch minus "
+                                   "it is the launch/drain latency between dependent launches, which the step hides "
+                                   "behind the preceding kernel (programmatic dependent launch)",
                     "traffic_note": "ncu dram__bytes_read+write per launch (profiles/): 57.2 MB read + 4.4 MB written "
                                     "to DRAM; the 37.7 MB of gradients are still dirty in the 126 MB L2 at kernel end",
                     "frac_of_nominal_8TBs": ach / 8000.0,

@@ -254,6 +254,9 @@ PLH_API const char* plh_strerror(int code);
  */
 PLH_API int plh_profile_begin(int max_launches);
 PLH_API int plh_profile_end(float* total_ms, int* n_launches);
+/* device-side view of the same launches: sum of (last CTA end - first CTA start), %globaltimer; call it
+   before plh_profile_end.  Event time minus this is launch/drain latency, not kernel work. */
+PLH_API int plh_profile_kernel_window(float* total_ms);
 /* number of kernels the library has launched in this process (for bench.py's gpu_launches) */
 PLH_API long long plh_launch_count(void);
 

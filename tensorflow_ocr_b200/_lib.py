@@ -55,6 +55,7 @@ SIGNATURES = {
     "plh_launch_count": (_ll, []),
     "plh_profile_begin": (_i, [_i]),
     "plh_profile_end": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "plh_profile_kernel_window": (_i, [C.POINTER(C.c_float)]),
 }
 
 _lib = None

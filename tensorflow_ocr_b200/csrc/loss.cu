@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <vector>
 
 namespace plh {
 
@@ -35,6 +36,7 @@ constexpr int kProfMax = 8192;
 static cudaEvent_t g_prof_ev[2 * kProfMax];
 static int g_prof_created = 0;
 static int g_prof_n = -1;  // -1: disabled
+static unsigned long long* g_prof_ts = nullptr;  // device: [start, end] of the kernel per profiled launch
 
 // ------------------------------------------------------------------ workspace layout
 constexpr int kSumReplicas = 16;
@@ -601,6 +603,7 @@ struct MainArgs {
   const uint8_t* mask;
   LossHeader* hdr;
   const ImageInfo* info;
+  unsigned long long* ts;  // profiling only: [first CTA start, last CTA end] in %globaltimer ns, else null
   float* stats;
   float* grad_pix;
   float* grad_link;
@@ -645,164 +648,12 @@ __device__ __forceinline__ void classify(float l, bool& p, bool& n) {
   else { const int li = (int)l; p = li == 1, n = li == 0; }
 }
 
-// Work unit = 16 consecutive pixels, handled by one warp:
-//   link phase : 2 iterations x 32 lanes, lane = (pixel-in-iteration, quarter j): 128-bit loads of the
-//                two link directions 2j, 2j+1 of that pixel (logits) + 64-bit load of their labels;
-//   pixel phase: lanes 0..15 own one pixel each (lanes 16..31 shadow them; same addresses, no extra
-//                traffic) — the pixel term is computed once per pixel instead of once per quarter.
-// Units are dealt round-robin to the warps of the persistent grid (16-pixel granularity keeps the
-// per-warp imbalance at ~1%); two units are in flight per trip for memory-level parallelism.
-template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
-__global__ void __launch_bounds__(kMainThreads, 2)
-loss_main_kernel(const MainArgs a, const int B, const int N) {
-  pdl_wait_and_release();
-  tl_start(3);
-  __shared__ float s_red[kMainThreads / 32][4][5];
-  __shared__ int s_cnt[HC_COUNT];
-  __shared__ bool s_last;
+// ---- CTA totals -> header (fp64 atomics), last CTA -> the scalars.  s_red holds the consumer warps' sums.
+template <int VARIANT>
+__device__ __forceinline__ void main_epilogue(const MainArgs& a, int B, int N, float (*s_red)[4][5], const int* s_cnt,
+                                              bool* s_last) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int j = tid & 3;  // which quarter of a pixel: link directions 2j and 2j+1
-
-  // ---- normalisers (final: K2 completed before this launch)
-  float pix_scale, invP[2], invN[2];
-  {
-    if (warp == 0) {
-      const int c = batch_count(a.info, B, lane);
-      if (lane < HC_COUNT) s_cnt[lane] = c;
-    }
-    __syncthreads();
-    const float nsp = (float)s_cnt[HC_N_SEG_POS];
-    if (VARIANT == PLH_VARIANT_MODEL) pix_scale = nsp > 0.f ? __fdiv_rn(2.f, nsp) : 0.f;  // model.py:226-233
-    else if (VARIANT == PLH_VARIANT_POS_ONLY) pix_scale = __fdiv_rn(2.f, nsp);            // vgg16 :267 unguarded
-    else pix_scale = __fdiv_rn(2.f, (float)((long long)B * N));                          // pixellink.py:160,170
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const float cp = (float)s_cnt[HC_CNT_P + 2 * j + c], cn = (float)s_cnt[HC_CNT_N + 2 * j + c];
-      if (VARIANT == PLH_VARIANT_PIXELLINK) {  // pixellink.py:198-211 zero guards
-        invP[c] = cp != 0.f ? __fdiv_rn(1.f, cp) : 0.f;
-        invN[c] = cn != 0.f ? __fdiv_rn(1.f, cn) : 0.f;
-      } else {                                 // model.py:252-253 unguarded: 0/0 = NaN is data
-        invP[c] = __fdiv_rn(1.f, cp);
-        invN[c] = __fdiv_rn(1.f, cn);
-      }
-    }
-  }
-
-  float sp[2] = {0.f, 0.f}, sn[2] = {0.f, 0.f}, spx = 0.f;
-  const int total_px = (int)a.total_px;
-  const int nunits = (total_px + 15) >> 4;
-  const int nwarps = gridDim.x * (kMainThreads / 32);
-  const float4* ll4 = reinterpret_cast<const float4*>(a.link_logits);
-  const float2* lab2 = reinterpret_cast<const float2*>(a.link_lab);
-  const float2* pl2 = reinterpret_cast<const float2*>(a.pix_logits);
-  const int pl_lane = lane & 15;        // pixel-phase lane -> pixel of the unit
-  const int q_pix = lane >> 2;          // link-phase lane -> pixel of the iteration (0..7)
-
-  constexpr int U = 2;
-  for (int u0 = blockIdx.x * (kMainThreads / 32) + warp; u0 < nunits; u0 += nwarps * U) {
-    float4 L[U][2];
-    float2 LB[U][2], P[U];
-    float PLB[U], MF[U];
-    // ---- all loads of the trip first
-#pragma unroll
-    for (int uu = 0; uu < U; ++uu) {
-      const int u = u0 + uu * nwarps;
-      const int px0 = u << 4;  // first pixel of the unit (may be >= total_px for the shadow unit of the last trip)
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int px = px0 + it * 8 + q_pix;
-        L[uu][it] = make_float4(0.f, 0.f, 0.f, 0.f), LB[uu][it] = make_float2(0.f, 0.f);
-        if (px < total_px) {
-          const size_t q = (size_t)px * 4 + j;
-          L[uu][it] = ldg_stream4(ll4 + q);
-          LB[uu][it] = ldg_stream2(lab2 + q);
-        }
-      }
-      const int pp = px0 + pl_lane;
-      P[uu] = make_float2(0.f, 0.f), PLB[uu] = 0.f, MF[uu] = 0.f;
-      if (pp < total_px) {
-        P[uu] = __ldg(pl2 + pp);
-        PLB[uu] = __ldg(a.pix_lab + pp);
-        MF[uu] = (VARIANT == PLH_VARIANT_PIXELLINK) ? 1.f : (float)__ldg(a.mask + pp);
-      }
-    }
-#pragma unroll
-    for (int uu = 0; uu < U; ++uu) {
-      const int px0 = (u0 + uu * nwarps) << 4;
-      // ---- pixel phase: one pixel per lane (0..15)
-      const int pp = px0 + pl_lane;
-      {
-        bool ppos, pneg;
-        classify<VARIANT>(PLB[uu], ppos, pneg);
-        float t, g1;
-        term_and_grad<TERM>(P[uu].x, P[uu].y, ppos, a.alpha, a.gamma, t, g1);
-        if (lane < 16 && pp < total_px) {
-          spx += t * MF[uu];
-          if (GRAD) {
-            const float gp = (MF[uu] * pix_scale) * g1;
-            stg_stream2(reinterpret_cast<float2*>(a.grad_pix) + pp, make_float2(-gp, gp));
-          }
-        }
-      }
-      unsigned lbits[2] = {0u, 0u};
-      // ---- link phase: two iterations of 8 pixels x 4 quarters
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int px = px0 + it * 8 + q_pix;
-        const float Mf = __shfl_sync(0xffffffffu, MF[uu], it * 8 + q_pix);  // the pixel's selected-mask weight
-        bool p0, n0, p1, n1;
-        classify<VARIANT>(LB[uu][it].x, p0, n0);
-        classify<VARIANT>(LB[uu][it].y, p1, n1);
-        float t0, g0, t1, g1;
-        term_and_grad<TERM>(L[uu][it].x, L[uu][it].y, p0, a.alpha, a.gamma, t0, g0);
-        term_and_grad<TERM>(L[uu][it].z, L[uu][it].w, p1, a.alpha, a.gamma, t1, g1);
-        if (px < total_px) {
-          const float tm0 = t0 * Mf, tm1 = t1 * Mf;
-          sp[0] += p0 ? tm0 : 0.f, sn[0] += n0 ? tm0 : 0.f;
-          sp[1] += p1 ? tm1 : 0.f, sn[1] += n1 ? tm1 : 0.f;
-          if (GRAD) {
-            const float a0 = (Mf * (p0 ? invP[0] : (n0 ? invN[0] : 0.f))) * g0;
-            const float a1 = (Mf * (p1 ? invP[1] : (n1 ? invN[1] : 0.f))) * g1;
-            stg_stream4(reinterpret_cast<float4*>(a.grad_link) + ((size_t)px * 4 + j), make_float4(-a0, a0, -a1, a1));
-          }
-        }
-        if (FLAGS) {
-          unsigned bits = ((L[uu][it].y - L[uu][it].x) > a.tl_logit ? 1u : 0u) << (2 * j) |
-                          ((L[uu][it].w - L[uu][it].z) > a.tl_logit ? 1u : 0u) << (2 * j + 1);
-          bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-          bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-          lbits[it] = bits;  // all four lanes of the quad hold the pixel's 8 link bits
-        }
-      }
-      if (FLAGS) {
-        // pixel-phase lane t (< 16) owns pixel t = it * 8 + quad: fetch that quad's bits of iteration it
-        const unsigned b0 = __shfl_sync(0xffffffffu, lbits[0], (lane & 7) << 2);
-        const unsigned b1 = __shfl_sync(0xffffffffu, lbits[1], (lane & 7) << 2);
-        if (lane < 16 && pp < total_px)
-          a.flags[pp] = (uint16_t)(((lane & 8) ? b1 : b0) | (((P[uu].y - P[uu].x) > a.tp_logit ? 1u : 0u) << 8));
-      }
-    }
-  }
-
-  // ---- block reduction of the 17 sums (lanes with equal j hold the same directions; the pixel sum is
-  // spread over all lanes, so it is first folded across the quad)
-  spx += __shfl_xor_sync(0xffffffffu, spx, 1);
-  spx += __shfl_xor_sync(0xffffffffu, spx, 2);
-#pragma unroll
-  for (int o = 4; o <= 16; o <<= 1) {
-    sp[0] += __shfl_xor_sync(0xffffffffu, sp[0], o);
-    sp[1] += __shfl_xor_sync(0xffffffffu, sp[1], o);
-    sn[0] += __shfl_xor_sync(0xffffffffu, sn[0], o);
-    sn[1] += __shfl_xor_sync(0xffffffffu, sn[1], o);
-    spx += __shfl_xor_sync(0xffffffffu, spx, o);
-  }
-  if (lane < 4) {
-    s_red[warp][lane][0] = sp[0], s_red[warp][lane][1] = sp[1];
-    s_red[warp][lane][2] = sn[0], s_red[warp][lane][3] = sn[1];
-    s_red[warp][lane][4] = spx;
-  }
-  __syncthreads();
   if (tid < 17) {
     // sum index: 0..7 s_pos[d], 8..15 s_neg[d], 16 s_pix ; d = 2*jj + c
     int jj, slot;
@@ -815,9 +666,9 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&a.hdr->ticket, 1u) == gridDim.x - 1);
+  if (tid == 0) *s_last = (atomicAdd(&a.hdr->ticket, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (!s_last) { tl_end(3); return; }
+  if (!*s_last) return;
 
   // ---- last CTA: the scalars.  One warp: lane d owns link direction d, so the header loads and the
   // IEEE divisions run side by side instead of as one thread's chain of dependent L2 round trips.
@@ -872,6 +723,276 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
     }
     if (lane == 0) a.hdr->ticket = 0u;
   }
+}
+
+// ------------------------------------------------------------------ K3: main fused pass, TMA-staged
+// Work unit = 16 consecutive pixels, handled by one warp:
+//   link phase : 2 iterations x 32 lanes, lane = (pixel-in-iteration, quarter j): 128-bit operands of the
+//                two link directions 2j, 2j+1 of that pixel (logits) + 64 bits of their labels;
+//   pixel phase: lanes 0..15 own one pixel each (lanes 16..31 shadow them) — the pixel term is computed
+//                once per pixel instead of once per quarter.
+// Every CTA owns a contiguous range of units and walks it in tiles of 12 units (one per consumer warp).  A
+// producer warp streams the five input arrays of a tile into a ring of shared-memory stages with bulk
+// async copies (TMA; 20.9 KB per tile, completion on an mbarrier), several tiles ahead of the
+// consumers, so the bytes in flight no longer live in registers and no warp ever waits on a global
+// load; consumers read their unit from shared memory (conflict-free 128-bit reads), hand the stage
+// back at once and compute.  Gradients leave through streaming 128-bit stores as before.
+constexpr int kTileUnits = kMainThreads / 32;          // 12 consumer warps, one unit each
+constexpr int kTilePx = kTileUnits * 16;               // 192
+constexpr int kOffLL = 0;                              // link logits  64 B/px
+constexpr int kOffLB = kOffLL + kTilePx * 64;          // link labels  32 B/px
+constexpr int kOffPL = kOffLB + kTilePx * 32;          // pixel logits  8 B/px
+constexpr int kOffPB = kOffPL + kTilePx * 8;           // pixel labels  4 B/px
+constexpr int kOffMK = kOffPB + kTilePx * 4;           // selected mask 1 B/px
+constexpr int kStageBytes = ((kOffMK + kTilePx + 127) / 128) * 128;
+constexpr int kStages = 4;
+constexpr int kMainBlock = kMainThreads + 32;          // + the producer warp
+constexpr size_t kMainSmem = (size_t)kStages * kStageBytes;
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// one 16-pixel unit, operands already in registers (see loss_main_kernel for the lane mapping)
+template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
+__device__ __forceinline__ void main_unit(const MainArgs& a, int px0, int total_px, const float4 (&L)[2],
+                                          const float2 (&LB)[2], float2 P, float PLB, float MF, float pix_scale,
+                                          const float (&invP)[2], const float (&invN)[2], int lane, float (&sp)[2],
+                                          float (&sn)[2], float& spx) {
+  const int j = lane & 3, q_pix = lane >> 2, pl_lane = lane & 15;
+  const int pp = px0 + pl_lane;
+  {
+    bool ppos, pneg;
+    classify<VARIANT>(PLB, ppos, pneg);
+    float t, g1;
+    term_and_grad<TERM>(P.x, P.y, ppos, a.alpha, a.gamma, t, g1);
+    if (lane < 16 && pp < total_px) {
+      spx += t * MF;
+      if (GRAD) {
+        const float gp = (MF * pix_scale) * g1;
+        stg_stream2(reinterpret_cast<float2*>(a.grad_pix) + pp, make_float2(-gp, gp));
+      }
+    }
+  }
+  unsigned lbits[2] = {0u, 0u};
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int px = px0 + it * 8 + q_pix;
+    const float Mf = __shfl_sync(0xffffffffu, MF, it * 8 + q_pix);  // the pixel's selected-mask weight
+    bool p0, n0, p1, n1;
+    classify<VARIANT>(LB[it].x, p0, n0);
+    classify<VARIANT>(LB[it].y, p1, n1);
+    float t0, g0, t1, g1;
+    term_and_grad<TERM>(L[it].x, L[it].y, p0, a.alpha, a.gamma, t0, g0);
+    term_and_grad<TERM>(L[it].z, L[it].w, p1, a.alpha, a.gamma, t1, g1);
+    if (px < total_px) {
+      const float tm0 = t0 * Mf, tm1 = t1 * Mf;
+      sp[0] += p0 ? tm0 : 0.f, sn[0] += n0 ? tm0 : 0.f;
+      sp[1] += p1 ? tm1 : 0.f, sn[1] += n1 ? tm1 : 0.f;
+      if (GRAD) {
+        const float a0 = (Mf * (p0 ? invP[0] : (n0 ? invN[0] : 0.f))) * g0;
+        const float a1 = (Mf * (p1 ? invP[1] : (n1 ? invN[1] : 0.f))) * g1;
+        stg_stream4(reinterpret_cast<float4*>(a.grad_link) + ((size_t)px * 4 + j), make_float4(-a0, a0, -a1, a1));
+      }
+    }
+    if (FLAGS) {
+      unsigned bits = ((L[it].y - L[it].x) > a.tl_logit ? 1u : 0u) << (2 * j) |
+                      ((L[it].w - L[it].z) > a.tl_logit ? 1u : 0u) << (2 * j + 1);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+      lbits[it] = bits;
+    }
+  }
+  if (FLAGS) {
+    const unsigned b0 = __shfl_sync(0xffffffffu, lbits[0], (lane & 7) << 2);
+    const unsigned b1 = __shfl_sync(0xffffffffu, lbits[1], (lane & 7) << 2);
+    if (lane < 16 && pp < total_px)
+      a.flags[pp] = (uint16_t)(((lane & 8) ? b1 : b0) | (((P.y - P.x) > a.tp_logit ? 1u : 0u) << 8));
+  }
+}
+
+template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
+__global__ void __launch_bounds__(kMainBlock, 2)
+loss_main_kernel(const MainArgs a, const int B, const int N) {
+  pdl_wait_and_release();
+  tl_start(3);
+  if (a.ts && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMin(a.ts, t);
+  }
+  extern __shared__ __align__(128) unsigned char stages[];
+  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
+  __shared__ float s_red[kMainThreads / 32][4][5];
+  __shared__ int s_cnt[HC_COUNT];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int j = tid & 3;
+  const bool producer = warp == kTileUnits;
+
+  // ---- this CTA's contiguous range of full units, in tiles of kTileUnits
+  const int total_px = (int)a.total_px;
+  const int nfull = total_px >> 4;
+  const int per = nfull / (int)gridDim.x, rem = nfull % (int)gridDim.x;
+  const int u_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int u_count = per + ((int)blockIdx.x < rem ? 1 : 0);
+  const int ntiles = (u_count + kTileUnits - 1) / kTileUnits;
+  constexpr bool kNeedMask = VARIANT != PLH_VARIANT_PIXELLINK;
+
+  // ---- producer: one thread initialises the barriers and starts streaming at once, while the
+  // consumer warps are still fetching the normalisers (they meet the barriers behind a named barrier)
+  if (producer) {
+    if (lane == 0) {
+#pragma unroll
+      for (int st = 0; st < kStages; ++st) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[st])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_empty[st])), "r"(kTileUnits));
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("bar.arrive 1, %0;" ::"r"(kMainBlock) : "memory");  // barriers are live
+    if (lane == 0) {
+      for (int k = 0; k < ntiles; ++k) {
+        const int st = k % kStages;
+        mbar_wait(smem_u32(&s_empty[st]), ((k / kStages) & 1) ^ 1);  // passes at once on the first lap
+        const int nu = min(kTileUnits, u_count - k * kTileUnits);
+        const size_t px0 = (size_t)(u_begin + k * kTileUnits) << 4;
+        const uint32_t npx = (uint32_t)nu * 16u;
+        const uint32_t bar = smem_u32(&s_full[st]);
+        const uint32_t base = smem_u32(stages + (size_t)st * kStageBytes);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"(npx * (kNeedMask ? 109u : 108u))
+                     : "memory");
+        bulk_g2s(base + kOffLL, a.link_logits + px0 * 16, npx * 64u, bar);
+        bulk_g2s(base + kOffLB, a.link_lab + px0 * 8, npx * 32u, bar);
+        bulk_g2s(base + kOffPL, a.pix_logits + px0 * 2, npx * 8u, bar);
+        bulk_g2s(base + kOffPB, a.pix_lab + px0, npx * 4u, bar);
+        if (kNeedMask) bulk_g2s(base + kOffMK, a.mask + px0, npx, bar);
+      }
+    }
+  } else {
+    // ---- normalisers (final: the selection/count kernels completed before this launch)
+    if (warp == 0) {
+      const int c = batch_count(a.info, B, lane);
+      if (lane < HC_COUNT) s_cnt[lane] = c;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(kMainBlock) : "memory");  // s_cnt written, mbarriers initialised
+  }
+  float pix_scale, invP[2], invN[2];
+  {
+    const float nsp = (float)s_cnt[HC_N_SEG_POS];
+    if (VARIANT == PLH_VARIANT_MODEL) pix_scale = nsp > 0.f ? __fdiv_rn(2.f, nsp) : 0.f;  // model.py:226-233
+    else if (VARIANT == PLH_VARIANT_POS_ONLY) pix_scale = __fdiv_rn(2.f, nsp);            // vgg16 :267 unguarded
+    else pix_scale = __fdiv_rn(2.f, (float)((long long)B * N));                          // pixellink.py:160,170
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float cp = (float)s_cnt[HC_CNT_P + 2 * j + c], cn = (float)s_cnt[HC_CNT_N + 2 * j + c];
+      if (VARIANT == PLH_VARIANT_PIXELLINK) {  // pixellink.py:198-211 zero guards
+        invP[c] = cp != 0.f ? __fdiv_rn(1.f, cp) : 0.f;
+        invN[c] = cn != 0.f ? __fdiv_rn(1.f, cn) : 0.f;
+      } else {                                 // model.py:252-253 unguarded: 0/0 = NaN is data
+        invP[c] = __fdiv_rn(1.f, cp);
+        invN[c] = __fdiv_rn(1.f, cn);
+      }
+    }
+  }
+
+  // ---- consumers: operands of this warp's unit from the stage, stage back to the producer, compute
+  float sp[2] = {0.f, 0.f}, sn[2] = {0.f, 0.f}, spx = 0.f;
+  if (!producer) {
+    const int pl_lane = lane & 15;
+    for (int k = 0; k < ntiles; ++k) {
+      const int st = k % kStages;
+      const int nu = min(kTileUnits, u_count - k * kTileUnits);
+      mbar_wait(smem_u32(&s_full[st]), (k / kStages) & 1);
+      const unsigned char* sb = stages + (size_t)st * kStageBytes;
+      float4 L[2];
+      float2 LB[2], P;
+      float PLB, MF;
+      const bool mine = warp < nu;
+      if (mine) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          L[it] = *reinterpret_cast<const float4*>(sb + kOffLL + warp * 1024 + (it * 32 + lane) * 16);
+          LB[it] = *reinterpret_cast<const float2*>(sb + kOffLB + warp * 512 + (it * 32 + lane) * 8);
+        }
+        P = *reinterpret_cast<const float2*>(sb + kOffPL + (warp * 16 + pl_lane) * 8);
+        PLB = *reinterpret_cast<const float*>(sb + kOffPB + (warp * 16 + pl_lane) * 4);
+        MF = kNeedMask ? (float)sb[kOffMK + warp * 16 + pl_lane] : 1.f;
+      }
+      __syncwarp();
+      if (lane == 0)  // the stage goes back to the producer as soon as this warp holds its operands
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[st])) : "memory");
+      if (mine)
+        main_unit<VARIANT, TERM, GRAD, FLAGS>(a, (u_begin + k * kTileUnits + warp) << 4, total_px, L, LB, P, PLB, MF,
+                                              pix_scale, invP, invN, lane, sp, sn, spx);
+    }
+    // the ragged last unit of the batch (total_px % 16 pixels): guarded global loads, one warp
+    if ((total_px & 15) && blockIdx.x == gridDim.x - 1 && warp == 0) {
+      const int px0 = nfull << 4;
+      const int q_pix = lane >> 2;
+      float4 L[2];
+      float2 LB[2], P = make_float2(0.f, 0.f);
+      float PLB = 0.f, MF = 0.f;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int px = px0 + it * 8 + q_pix;
+        L[it] = make_float4(0.f, 0.f, 0.f, 0.f), LB[it] = make_float2(0.f, 0.f);
+        if (px < total_px) {
+          const size_t q = (size_t)px * 4 + j;
+          L[it] = ldg_stream4(reinterpret_cast<const float4*>(a.link_logits) + q);
+          LB[it] = ldg_stream2(reinterpret_cast<const float2*>(a.link_lab) + q);
+        }
+      }
+      const int pp = px0 + pl_lane;
+      if (pp < total_px) {
+        P = __ldg(reinterpret_cast<const float2*>(a.pix_logits) + pp);
+        PLB = __ldg(a.pix_lab + pp);
+        MF = kNeedMask ? (float)__ldg(a.mask + pp) : 1.f;
+      }
+      main_unit<VARIANT, TERM, GRAD, FLAGS>(a, px0, total_px, L, LB, P, PLB, MF, pix_scale, invP, invN, lane, sp, sn,
+                                            spx);
+    }
+  }
+
+  // ---- block reduction of the 17 sums (consumer warps only) and the last-CTA epilogue
+  if (!producer) {
+    spx += __shfl_xor_sync(0xffffffffu, spx, 1);
+    spx += __shfl_xor_sync(0xffffffffu, spx, 2);
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1) {
+      sp[0] += __shfl_xor_sync(0xffffffffu, sp[0], o);
+      sp[1] += __shfl_xor_sync(0xffffffffu, sp[1], o);
+      sn[0] += __shfl_xor_sync(0xffffffffu, sn[0], o);
+      sn[1] += __shfl_xor_sync(0xffffffffu, sn[1], o);
+      spx += __shfl_xor_sync(0xffffffffu, spx, o);
+    }
+    if (lane < 4) {
+      s_red[warp][lane][0] = sp[0], s_red[warp][lane][1] = sp[1];
+      s_red[warp][lane][2] = sn[0], s_red[warp][lane][3] = sn[1];
+      s_red[warp][lane][4] = spx;
+    }
+  }
+  __syncthreads();
+  main_epilogue<VARIANT>(a, B, N, s_red, s_cnt, &s_last);
+  if (a.ts && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMax(a.ts + 1, t);
+  }
   tl_end(3);
 }
 
@@ -923,14 +1044,24 @@ float prob_to_logit_threshold(float t) {
   return from_ordered_bits((int32_t)lo);
 }
 
+template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
+static int launch_main_one(int grid, cudaStream_t s, const MainArgs& a, int B, int N) {
+  auto kern = loss_main_kernel<VARIANT, TERM, GRAD, FLAGS>;
+  static bool attr_set = false;  // idempotent; benign if raced
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMainSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  return launch(kern, grid, kMainBlock, kMainSmem, s, a, B, N);
+}
+
 template <int VARIANT, int TERM>
 static int launch_main(bool grad, bool flags, int grid, cudaStream_t s, const MainArgs& a, int B, int N) {
-  int rc;
-  if (grad && flags) rc = launch(loss_main_kernel<VARIANT, TERM, true, true>, grid, kMainThreads, 0, s, a, B, N);
-  else if (grad) rc = launch(loss_main_kernel<VARIANT, TERM, true, false>, grid, kMainThreads, 0, s, a, B, N);
-  else if (flags) rc = launch(loss_main_kernel<VARIANT, TERM, false, true>, grid, kMainThreads, 0, s, a, B, N);
-  else rc = launch(loss_main_kernel<VARIANT, TERM, false, false>, grid, kMainThreads, 0, s, a, B, N);
-  return rc;
+  if (grad && flags) return launch_main_one<VARIANT, TERM, true, true>(grid, s, a, B, N);
+  if (grad) return launch_main_one<VARIANT, TERM, true, false>(grid, s, a, B, N);
+  if (flags) return launch_main_one<VARIANT, TERM, false, true>(grid, s, a, B, N);
+  return launch_main_one<VARIANT, TERM, false, false>(grid, s, a, B, N);
 }
 
 static inline bool select_uses_cluster(int N) { return N <= kClusterSize * kClThreads * kClMaxKPT; }
@@ -1003,7 +1134,8 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   if (B <= 0 || H <= 0 || W <= 0 || (long long)B * H * W > (1ll << 29)) return PLH_E_SHAPE;
   if (p->variant < 0 || p->variant > 2 || p->term < 0 || p->term > 1 || p->neg_pos_ratio < 0) return PLH_E_PARAM;
   if (!aligned16(pix_logits) || !aligned16(link_logits) || !aligned16(pix_lab) || !aligned16(link_lab) ||
-      !aligned16(stats) || (grad_pix && (!aligned16(grad_pix) || !aligned16(grad_link))) || !aligned16(workspace))
+      !aligned16(stats) || (grad_pix && (!aligned16(grad_pix) || !aligned16(grad_link))) || !aligned16(workspace) ||
+      (ohem_mask && !aligned16(ohem_mask)))
     return PLH_E_ALIGN;
   const int N = H * W;
   const LossWsLayout l = loss_ws_layout(B, N);
@@ -1054,6 +1186,7 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
     MainArgs a;
     a.pix_logits = pix_logits, a.link_logits = link_logits, a.pix_lab = pix_lab, a.link_lab = link_lab;
     a.mask = mask, a.hdr = hdr, a.info = info, a.stats = stats;
+    a.ts = nullptr;
     a.grad_pix = grad_pix, a.grad_link = grad_link, a.flags = decode_flags;
     a.total_px = total_px, a.alpha = p->focal_alpha, a.gamma = p->focal_gamma;
     a.tp_logit = dp ? prob_to_logit_threshold(dp->pixel_thresh) : 0.f;
@@ -1062,7 +1195,10 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
     const int grid = (int)std::min<long long>((Q + kMainThreads * 2 - 1) / (kMainThreads * 2), kMainMaxCTAs);
     const bool g = grad_pix != nullptr, f = decode_flags != nullptr;
     const bool prof = g_prof_n >= 0 && g_prof_n < g_prof_created / 2;
-    if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], s);
+    if (prof) {
+      a.ts = g_prof_ts + 2 * g_prof_n;
+      cudaEventRecord(g_prof_ev[2 * g_prof_n], s);
+    }
 #define PLH_DISPATCH(V, T) rc = launch_main<V, T>(g, f, grid, s, a, B, N)
     if (p->term == PLH_TERM_CE) {
       if (p->variant == PLH_VARIANT_MODEL) PLH_DISPATCH(PLH_VARIANT_MODEL, PLH_TERM_CE);
@@ -1089,7 +1225,30 @@ extern "C" int plh_profile_begin(int max_launches) {
     cudaError_t e = cudaEventCreate(&g_prof_ev[g_prof_created]);
     if (e != cudaSuccess) return (int)e;
   }
+  if (!g_prof_ts && cudaMalloc(&g_prof_ts, sizeof(unsigned long long) * 2 * kProfMax) != cudaSuccess) return PLH_E_DEVICE;
+  {
+    std::vector<unsigned long long> init(2 * (size_t)max_launches);
+    for (int i = 0; i < max_launches; ++i) init[2 * i] = ~0ull, init[2 * i + 1] = 0ull;
+    cudaError_t e = cudaMemcpy(g_prof_ts, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+  }
   g_prof_n = 0;
+  return PLH_OK;
+}
+
+// sum over the profiled launches of (last CTA end - first CTA start); call before plh_profile_end
+extern "C" int plh_profile_kernel_window(float* total_ms) {
+  if (!total_ms) return PLH_E_NULL;
+  if (g_prof_n < 0 || !g_prof_ts) return PLH_E_PARAM;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  std::vector<unsigned long long> h(2 * (size_t)std::max(g_prof_n, 1));
+  e = cudaMemcpy(h.data(), g_prof_ts, sizeof(unsigned long long) * 2 * g_prof_n, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return (int)e;
+  double ns = 0.0;
+  for (int i = 0; i < g_prof_n; ++i)
+    if (h[2 * i + 1] > h[2 * i]) ns += (double)(h[2 * i + 1] - h[2 * i]);
+  *total_ms = (float)(ns * 1e-6);
   return PLH_OK;
 }
 
