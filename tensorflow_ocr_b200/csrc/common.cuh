@@ -32,8 +32,9 @@ inline bool pdl_enabled() {
   return v == 1;
 }
 
-template <typename... KArgs, typename... Args>
-inline int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+// launch_plain: ordinary stream order (no early launch of this kernel's CTAs under its predecessor)
+template <bool PDL = true, typename... KArgs, typename... Args>
+inline int launch_as(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -43,10 +44,18 @@ inline int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cu
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (PDL && pdl_enabled()) ? 1 : 0;
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   return e == cudaSuccess ? PLH_OK : (int)e;
+}
+template <typename... KArgs, typename... Args>
+inline int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  return launch_as<true>(kern, grid, block, smem, s, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline int launch_plain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  return launch_as<false>(kern, grid, block, smem, s, static_cast<Args&&>(args)...);
 }
 
 // Optional device-side timeline (compile with -DPLH_TIMELINE): first-CTA start / last-CTA end of every

@@ -532,7 +532,7 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
     flags = const_cast<uint16_t*>(flags_in);
   } else {
     const int grid = (int)std::min<long long>((total_px / 32 + 7) / 8 + 1, kNumSMs * 8);
-    rc = launch(decode_flags_kernel, grid, 256, 0, s, pix_logits, link_logits, total_px,
+    rc = launch_plain(decode_flags_kernel, grid, 256, 0, s, pix_logits, link_logits, total_px,
                                              prob_to_logit_threshold(p->pixel_thresh),
                                              prob_to_logit_threshold(p->link_thresh), flags, n_boxes, B);
     if (rc) return rc;
@@ -600,7 +600,7 @@ extern "C" int plh_decode_flags(const float* pix_logits, const float* link_logit
   if (!aligned16(pix_logits) || !aligned16(link_logits) || !aligned16(flags)) return PLH_E_ALIGN;
   const long long total_px = (long long)B * H * W;
   const int grid = (int)std::min<long long>((total_px / 32 + 7) / 8 + 1, kNumSMs * 8);
-  return launch(decode_flags_kernel, grid, 256, 0, (cudaStream_t)stream, pix_logits, link_logits, total_px,
+  return launch_plain(decode_flags_kernel, grid, 256, 0, (cudaStream_t)stream, pix_logits, link_logits, total_px,
                 prob_to_logit_threshold(p->pixel_thresh), prob_to_logit_threshold(p->link_thresh), flags,
                 (int*)nullptr, 0);
 }

@@ -75,8 +75,18 @@ __device__ __forceinline__ int batch_count(const ImageInfo* info, int B, int lan
 }
 constexpr int kKeysMaxCTAsPerImage = 64;  // K0 writes one (n_pos, n_neg) pair per CTA; K1 sums them (no atomics, no memset)
 
-constexpr int kMainThreads = 384;
-constexpr int kMainMaxCTAs = kNumSMs * 2;
+#ifndef PLH_K3_WARPS
+#define PLH_K3_WARPS 12
+#endif
+#ifndef PLH_K3_CTAS_PER_SM
+#define PLH_K3_CTAS_PER_SM 2
+#endif
+#ifndef PLH_K3_STAGES
+#define PLH_K3_STAGES 4
+#endif
+constexpr int kMainThreads = 32 * PLH_K3_WARPS;   // consumer threads
+constexpr int kMainCTAsPerSM = PLH_K3_CTAS_PER_SM;
+constexpr int kMainMaxCTAs = kNumSMs * kMainCTAsPerSM;
 constexpr int kSelectThreads = 1024;
 constexpr size_t kSmemKeysMaxBytes = 200 * 1024;   // keys of one image fit in shared memory up to 51200 px
 
@@ -745,7 +755,7 @@ constexpr int kOffPL = kOffLB + kTilePx * 32;          // pixel logits  8 B/px
 constexpr int kOffPB = kOffPL + kTilePx * 8;           // pixel labels  4 B/px
 constexpr int kOffMK = kOffPB + kTilePx * 4;           // selected mask 1 B/px
 constexpr int kStageBytes = ((kOffMK + kTilePx + 127) / 128) * 128;
-constexpr int kStages = 4;
+constexpr int kStages = PLH_K3_STAGES;
 constexpr int kMainBlock = kMainThreads + 32;          // + the producer warp
 constexpr size_t kMainSmem = (size_t)kStages * kStageBytes;
 
@@ -823,7 +833,7 @@ __device__ __forceinline__ void main_unit(const MainArgs& a, int px0, int total_
 }
 
 template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
-__global__ void __launch_bounds__(kMainBlock, 2)
+__global__ void __launch_bounds__(kMainBlock, kMainCTAsPerSM)
 loss_main_kernel(const MainArgs a, const int B, const int N) {
   pdl_wait_and_release();
   tl_start(3);
@@ -1088,7 +1098,8 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
       if (e != cudaSuccess) return (int)e;                                                                       \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    rc = launch(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg,    \
+    /* first kernel of the chain: plain stream order (its CTAs parked under a foreign predecessor only get in its way) */ \
+    rc = launch_plain(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg, \
                 n_pos_override, N, ratio, info, thr_out, mask, FROM_SCORES ? (uint32_t*)nullptr : keys, hdr);    \
   }
     if (N <= kClusterSize * kClThreads * 2) PLH_CLUSTER(2)
@@ -1099,7 +1110,7 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
   }
   const int per_image = std::max(1, std::min({(N + kKeysThreads - 1) / kKeysThreads, (kNumSMs * 8 + B - 1) / B,
                                               kKeysMaxCTAsPerImage}));
-  rc = launch(score_keys_kernel<KEYMODE, FROM_SCORES>, dim3(per_image, B), kKeysThreads, 0, s, pix_logits, pix_lab,
+  rc = launch_plain(score_keys_kernel<KEYMODE, FROM_SCORES>, dim3(per_image, B), kKeysThreads, 0, s, pix_logits, pix_lab,
               scores, pos, neg, N, keys, counts);
   if (rc) return rc;
   const bool use_smem = (size_t)N * 4 <= kSmemKeysMaxBytes;
