@@ -158,8 +158,11 @@ typedef struct plh_decode_params {
   int32_t max_boxes;  /* capacity K of the per-image box list */
   double scale_x;     /* 4.0  = 1280/320 (test_pixellink_fast.py:196); must be >= 1 */
   double scale_y;     /* 3.75 = 720/192  (test_pixellink_fast.py:197); must be >= 1 */
-  int32_t reserved[2]; /* reserved[0] bit 0: components + label map only (no boxes); bit 1: boxes only, from the
-                          workspace of a previous bit-0 call */
+  int32_t reserved[2]; /* reserved[0], phase selection on one workspace (results identical to the whole call):
+                          bit 0: components + label map only (no boxes); bit 1: boxes only, from the workspace
+                          of a previous bit-0 call; bit 2: only the first kernel (thresholds + labelling inside
+                          32x16 tiles); bit 3: everything after it, on the workspace of a bit-2 call.  Lets a
+                          caller interleave the decode with another pipeline (tensorflow_ocr_b200/head.py). */
 } plh_decode_params;
 
 /*

@@ -177,8 +177,12 @@ __device__ __forceinline__ void unite_s(int* lab, int a, int b) {
   }
 }
 
+// FROM_LOGITS: the tile thresholds its own pixels (D0 folded in: one thread = one pixel = 72 B of logits,
+// a warp = 32 consecutive pixels of a row) and also writes the flag words for the later passes.
+template <bool FROM_LOGITS>
 __global__ void __launch_bounds__(kTW * kTH)
-decode_tile_cc_kernel(const uint16_t* __restrict__ flags, int H, int W, int* __restrict__ parent,
+decode_tile_cc_kernel(const float* __restrict__ pix_logits, const float* __restrict__ link_logits, float tp_logit,
+                      float tl_logit, uint16_t* __restrict__ flags, int H, int W, int* __restrict__ parent,
                       int* __restrict__ size, int* __restrict__ n_boxes) {
   pdl_wait_and_release();
   tl_start(5);
@@ -188,14 +192,31 @@ decode_tile_cc_kernel(const uint16_t* __restrict__ flags, int H, int W, int* __r
   const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH, b = blockIdx.z;
   const size_t base = (size_t)b * H * W;
   if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) n_boxes[b] = 0;
-  for (int i = tid; i < (kTH + 2) * (kTW + 2); i += kTW * kTH) {
-    const int r = i / (kTW + 2), c = i - r * (kTW + 2);
-    const int gy = ty0 - 1 + r, gx = tx0 - 1 + c;
-    sf[r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? flags[base + (size_t)gy * W + gx] : (uint16_t)0;
-  }
   const int ly = tid / kTW, lx = tid - ly * kTW;
   const int gy = ty0 + ly, gx = tx0 + lx;
   const bool inimg = gy < H && gx < W;
+  if (FROM_LOGITS) {
+    unsigned fl = 0;
+    if (inimg) {
+      const size_t g = base + (size_t)gy * W + gx;
+      const float4* ll4 = reinterpret_cast<const float4*>(link_logits) + g * 4;
+      const float4 l0 = ldg_stream4(ll4), l1 = ldg_stream4(ll4 + 1), l2 = ldg_stream4(ll4 + 2), l3 = ldg_stream4(ll4 + 3);
+      const float2 pp = ldg_stream2(reinterpret_cast<const float2*>(pix_logits) + g);
+      fl = ((l0.y - l0.x) > tl_logit ? 1u : 0u) | ((l0.w - l0.z) > tl_logit ? 2u : 0u) |
+           ((l1.y - l1.x) > tl_logit ? 4u : 0u) | ((l1.w - l1.z) > tl_logit ? 8u : 0u) |
+           ((l2.y - l2.x) > tl_logit ? 16u : 0u) | ((l2.w - l2.z) > tl_logit ? 32u : 0u) |
+           ((l3.y - l3.x) > tl_logit ? 64u : 0u) | ((l3.w - l3.z) > tl_logit ? 128u : 0u) |
+           ((pp.y - pp.x) > tp_logit ? kFlagP : 0u);
+      flags[g] = (uint16_t)fl;
+    }
+    sf[ly + 1][lx + 1] = (uint16_t)fl;
+  } else {
+    for (int i = tid; i < (kTH + 2) * (kTW + 2); i += kTW * kTH) {
+      const int r = i / (kTW + 2), c = i - r * (kTW + 2);
+      const int yy = ty0 - 1 + r, xx = tx0 - 1 + c;
+      sf[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? flags[base + (size_t)yy * W + xx] : (uint16_t)0;
+    }
+  }
   __syncthreads();
   const unsigned f = sf[ly + 1][lx + 1];
   const bool P = inimg && (f & kFlagP);
@@ -527,19 +548,25 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   const int grid_px = (int)std::min<long long>((total_px + 255) / 256, kNumSMs * 16);
   const bool skip_rects = (p->reserved[0] & 1) != 0;  // components + label map only
   const bool rects_only = (p->reserved[0] & 2) != 0;  // boxes from a workspace prepared by a skip_rects call
+  const bool tile_only = (p->reserved[0] & 4) != 0;   // stop after the threshold + tile-labelling kernel
+  const bool after_tile = (p->reserved[0] & 8) != 0;  // resume on a workspace a tile_only call prepared
   if (rects_only) goto rects;
-  if (flags_in) {
-    flags = const_cast<uint16_t*>(flags_in);
-  } else {
-    const int grid = (int)std::min<long long>((total_px / 32 + 7) / 8 + 1, kNumSMs * 8);
-    rc = launch_plain(decode_flags_kernel, grid, 256, 0, s, pix_logits, link_logits, total_px,
-                                             prob_to_logit_threshold(p->pixel_thresh),
-                                             prob_to_logit_threshold(p->link_thresh), flags, n_boxes, B);
+  if (after_tile) goto merge;
+  {
+    const dim3 tiles((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, B);
+    if (flags_in) {
+      flags = const_cast<uint16_t*>(flags_in);
+      rc = launch(decode_tile_cc_kernel<false>, tiles, kTW * kTH, 0, s, (const float*)nullptr, (const float*)nullptr,
+                  0.f, 0.f, flags, H, W, parent, size, n_boxes);
+    } else {  // first kernel of the chain: thresholds + tile labelling in one pass over the logits
+      rc = launch_plain(decode_tile_cc_kernel<true>, tiles, kTW * kTH, 0, s, pix_logits, link_logits,
+                        prob_to_logit_threshold(p->pixel_thresh), prob_to_logit_threshold(p->link_thresh), flags, H,
+                        W, parent, size, n_boxes);
+    }
     if (rc) return rc;
   }
-  rc = launch(decode_tile_cc_kernel, dim3((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, B), kTW * kTH, 0, s, flags, H, W, parent, size,
-                                                                                                n_boxes);
-  if (rc) return rc;
+  if (tile_only) return PLH_OK;
+merge:
   rc = launch(decode_cross_kernel, grid_px, 256, 0, s, flags, H, W, (int)total_px, parent);
   if (rc) return rc;
   rc = launch(decode_flatten_kernel, grid_px, 256, 0, s, flags, H, W, total_px, parent, size);

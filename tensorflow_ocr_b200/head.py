@@ -49,10 +49,13 @@ class DecodeConfig:
     min_size: int = 10                      # test_pixellink_fast.py:174 (200 in test_pixellink.py:177)
     scale: Tuple[float, float] = (4.0, 3.75)  # (1280/320, 720/192) test_pixellink_fast.py:196-197
     max_boxes: int = 128
+    phase: int = 0    # plh_decode_params.reserved[0]: 0 whole decode, 4 tile pass only, 8 resume after the tile pass
 
     def c_struct(self):
-        return _lib.DecodeParams(self.pixel_thresh, self.link_thresh, self.min_size, self.max_boxes,
-                                 float(self.scale[0]), float(self.scale[1]))
+        p = _lib.DecodeParams(self.pixel_thresh, self.link_thresh, self.min_size, self.max_boxes,
+                              float(self.scale[0]), float(self.scale[1]))
+        p.reserved[0] = self.phase
+        return p
 
 
 # ----------------------------------------------------------------------------- plumbing
@@ -202,7 +205,7 @@ def _decode_outputs(B, H, W, K, dev, out, want_rects):
 
 
 def decode_raw(pix_logits, link_logits, cfg: DecodeConfig = DecodeConfig(), out: Optional[dict] = None,
-               want_rects: bool = True) -> dict:
+               want_rects: bool = True, workspace: Optional[torch.Tensor] = None) -> dict:
     """plh_decode on CUDA tensors.  Returns labels int32 [B,H,W], boxes int32 [B,K,4,2],
     n_boxes int32 [B], comp int32 [B,K,2] (label, size), rects fp32 [B,K,5]."""
     lib = _lib.load()
@@ -211,7 +214,7 @@ def decode_raw(pix_logits, link_logits, cfg: DecodeConfig = DecodeConfig(), out:
     _require_gpu(dev)
     K = cfg.max_boxes
     out, labels, boxes, n_boxes, comp, rects = _decode_outputs(B, H, W, K, dev, out, want_rects)
-    ws = _workspace(_lib.OP_DECODE, B, H, W, K, dev)
+    ws = workspace if workspace is not None else _workspace(_lib.OP_DECODE, B, H, W, K, dev)
     dp = cfg.c_struct()
     with torch.cuda.device(dev):
         rc = lib.plh_decode(_p(pix_logits), _p(link_logits), B, H, W, C.byref(dp), _p(labels), _p(boxes),
@@ -269,10 +272,9 @@ def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossCo
                         want_rects: bool = False, parallel: bool = True) -> dict:
     """The head step: loss fwd+bwd and decode of the same logits.
 
-    parallel=True (default): the two pipelines are independent chains of small kernels, so the
-    decode runs on a second stream concurrently with the loss (fork/join with events; under
-    CUDA-graph capture this becomes two parallel branches).  The per-image radix select of the
-    loss occupies one SM per image; the decode fills the rest of the chip meanwhile.
+    parallel=True (default): the two pipelines are independent chains of small kernels, so after the
+    decode's first kernel they run on two streams (fork/join with events; under CUDA-graph capture
+    this becomes two parallel branches).
     parallel=False: one stream; the loss kernel emits the 2 B/px threshold flags and the decode
     starts from them (one read of the logits instead of two).
     """
@@ -284,14 +286,21 @@ def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossCo
     cur = torch.cuda.current_stream(dev)
     aux = _aux_stream(dev)
     aux.wait_stream(cur)
-    # Loss first: its cluster launch (8 co-scheduled CTAs per image) must not queue behind the decode's
-    # full-occupancy threshold kernel.  The normalisers stay in their own pass here (split_counts): the
-    # fused selection kernel is the shortest loss chain on its own, but next to the decode its longer
-    # residency costs the tile labelling more than the saved launch gains.
-    lstep = dataclasses.replace(lcfg, split_counts=True)
-    pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, lstep, True, False, None, out)
+    # The decode's threshold + tile-labelling kernel and the loss's selection kernel are both bound by
+    # integer issue and only slow each other down, so the tile pass runs first, alone (13 us); then the
+    # loss chain runs beside the decode's latency-bound merge / flatten / label kernels.  The normalisers
+    # stay in their own pass here (split_counts): the fused selection kernel is the shortest loss chain
+    # on its own, but next to the decode its longer residency costs more than the saved launch
+    # (DESIGN.md section 5).
+    B, H, W = pix_logits.shape[:3]
+    with torch.cuda.device(dev):
+        ws = _workspace(_lib.OP_DECODE, B, H, W, dcfg.max_boxes, dev)
+    decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=4), out, want_rects, ws)
+    aux.wait_stream(cur)
+    pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, dataclasses.replace(lcfg, split_counts=True), True,
+                       False, None, out)
     with torch.cuda.stream(aux):
-        decode_raw(pix_logits, link_logits, dcfg, out, want_rects)
+        decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=8), out, want_rects, ws)
     cur.wait_stream(aux)
     return out
 

@@ -218,3 +218,25 @@ def test_decode_random_shapes(seed, cuda_dev):
     ms = int(rng.integers(0, 12))
     out = _decode(inp, pixel_thresh=tp, link_thresh=tl, scale=sc, min_size=ms, max_boxes=1024)
     _check(inp, out, min_size=ms, scale=sc, pixel_thresh=tp, link_thresh=tl)
+
+
+def test_decode_phase_bits_compose(cuda_dev):
+    """reserved[0] bit 2 (tile pass only) followed by bit 3 (the rest) on one workspace == the whole decode."""
+    import dataclasses
+    import torch
+    from tensorflow_ocr_b200 import _lib, head, synth
+    inp = synth.make_batch(23, 3, 70, 100, "G")
+    dev = torch.device("cuda", 0)
+    pl, ll = torch.as_tensor(inp["pix_logits"]).to(dev), torch.as_tensor(inp["link_logits"]).to(dev)
+    cfg = head.DecodeConfig(min_size=3, max_boxes=256)
+    whole = {k: v.clone() for k, v in head.decode_raw(pl, ll, cfg, None, True).items()}
+    ws = torch.empty(_lib.load().plh_workspace_bytes(_lib.OP_DECODE, 3, 70, 100, 256), dtype=torch.uint8, device=dev)
+    out = {}
+    head.decode_raw(pl, ll, dataclasses.replace(cfg, phase=4), out, True, ws)
+    head.decode_raw(pl, ll, dataclasses.replace(cfg, phase=8), out, True, ws)
+    torch.cuda.synchronize()
+    nb = whole["n_boxes"].cpu().numpy()
+    assert np.array_equal(out["n_boxes"].cpu().numpy(), nb)
+    assert np.array_equal(out["labels"].cpu().numpy(), whole["labels"].cpu().numpy())
+    for b in range(3):
+        assert np.array_equal(out["boxes"][b, :nb[b]].cpu().numpy(), whole["boxes"][b, :nb[b]].cpu().numpy())
