@@ -72,8 +72,9 @@ typedef struct plh_loss_params {
                             same inputs prepared (skips selection, mask and normalisers): lets bench.py time
                             the bandwidth-bound pass alone.  Bit 1: scheduling hint, results identical — keep
                             the mask + normaliser pass a separate kernel instead of fusing it into the
-                            selection kernel (better when another pipeline shares the GPU).
-                            Other bits must be 0. */
+                            selection kernel.  Bit 2: scheduling hint — the kernel that precedes this call on
+                            the stream is one of this library's (plh_decode phase), so the first kernel here
+                            may launch programmatically under its tail.  Other bits must be 0. */
 } plh_loss_params;
 
 /* Layout of the `stats` output (device floats).  PLH_STATS_FLOATS + B entries. */

@@ -40,7 +40,7 @@ __constant__ int c_dx[8] = {-1, -1, -1, 1, 1, 1, 0, 0};
 constexpr int kFlagP = 1 << 8;
 
 struct DecodeWsLayout {
-  size_t flags, parent, size, comp_root, comp_size, rowmin, rowmax, total;
+  size_t flags, parent, size, comp_root, comp_size, nrec, recs, total;
 };
 
 static DecodeWsLayout decode_ws_layout(int B, int H, int W, int K) {
@@ -52,8 +52,8 @@ static DecodeWsLayout decode_ws_layout(int B, int H, int W, int K) {
   l.size = off; off = align_up(off + px * 4, 256);
   l.comp_root = off; off = align_up(off + (size_t)B * K * 4, 256);
   l.comp_size = off; off = align_up(off + (size_t)B * K * 4, 256);
-  l.rowmin = off; off = align_up(off + (size_t)B * K * H * 4, 256);
-  l.rowmax = off; off = align_up(off + (size_t)B * K * H * 4, 256);
+  l.nrec = off; off = align_up(off + (size_t)B * 4, 256);
+  l.recs = off; off = align_up(off + px * 8, 256);   // one run-boundary record per pixel at most
   l.total = off;
   return l;
 }
@@ -183,7 +183,7 @@ template <bool FROM_LOGITS>
 __global__ void __launch_bounds__(kTW * kTH)
 decode_tile_cc_kernel(const float* __restrict__ pix_logits, const float* __restrict__ link_logits, float tp_logit,
                       float tl_logit, uint16_t* __restrict__ flags, int H, int W, int* __restrict__ parent,
-                      int* __restrict__ size, int* __restrict__ n_boxes) {
+                      int* __restrict__ size, int* __restrict__ n_boxes, int* __restrict__ nrec) {
   pdl_wait_and_release();
   tl_start(5);
   __shared__ uint16_t sf[kTH + 2][kTW + 2];
@@ -191,7 +191,7 @@ decode_tile_cc_kernel(const float* __restrict__ pix_logits, const float* __restr
   const int tid = threadIdx.x;
   const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH, b = blockIdx.z;
   const size_t base = (size_t)b * H * W;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) n_boxes[b] = 0;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) n_boxes[b] = 0, nrec[b] = 0;
   const int ly = tid / kTW, lx = tid - ly * kTW;
   const int gy = ty0 + ly, gx = tx0 + lx;
   const bool inimg = gy < H && gx < W;
@@ -329,62 +329,59 @@ decode_flatten_kernel(const uint16_t* __restrict__ flags, int H, int W, long lon
   tl_end(7);
 }
 
-// ------------------------------------------------------------------ D3: kept roots -> box slots
-// Every root with size > min_size takes a slot (arrival order; the ascending-label order
-// of the output is restored by ranking in D5).  Afterwards size[root] holds the slot of a
-// kept component (may be >= K: kept in the label map, but no box row) or -1 for a filtered one.
-__global__ void __launch_bounds__(256)
-decode_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int N, int total_px, int min_size, int K,
-                    int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes,
-                    int* __restrict__ rowmin, int* __restrict__ rowmax, int H) {
-  pdl_wait_and_release();
-  tl_start(8);
-  const int stride = gridDim.x * blockDim.x;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
-    if (parent[g] != g) continue;
-    const int sz = size[g];
-    if (sz > min_size) {  // test_pixellink_fast.py:174 `len(index_list) > 10`
-      const int b = g / N;
-      const int slot = atomicAdd(&n_boxes[b], 1);
-      size[g] = slot;
-      if (slot < K) {
-        comp_root[(size_t)b * K + slot] = g - b * N;
-        comp_size[(size_t)b * K + slot] = sz;
-        // this slot's row-extreme table (only used slots are initialised: no memset of the whole table)
-        int* rmin = rowmin + ((size_t)b * K + slot) * H;
-        int* rmax = rowmax + ((size_t)b * K + slot) * H;
-        for (int y = (g - b * N) / (N / H); y < H; ++y) rmin[y] = 0x7fffffff, rmax[y] = -1;
-      }
-    } else {
-      size[g] = -1;
-    }
-  }
-  tl_end(8);
-}
-
-// ------------------------------------------------------------------ D4: labels + row extremes
+// ------------------------------------------------------------------ D4: labels, components, run records
+// One pass over the flattened forest does everything the boxes need:
+//  * label map: the component's minimum pixel index if its size > min_size, else -1;
+//  * every kept root takes a box slot (arrival order; D5 restores the ascending-label order by ranking);
+//  * every kept pixel that starts or ends a horizontal run of its component appends one record
+//    (root, y, x) to its image's list: the row extremes D5 needs are the min / max x over the records
+//    of a (component, row), and a list needs no initialisation, unlike a per-slot row table.
 __global__ void __launch_bounds__(256)
 decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ size, int H, int W, long long total_px,
-                     int K, int32_t* __restrict__ labels, int* __restrict__ rowmin, int* __restrict__ rowmax) {
+                     int min_size, int K, int32_t* __restrict__ labels, int* __restrict__ comp_root,
+                     int* __restrict__ comp_size, int* __restrict__ n_boxes, int* __restrict__ nrec,
+                     unsigned long long* __restrict__ recs) {
   pdl_wait_and_release();
   tl_start(9);
   const int N = H * W;
+  const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
-    const int b = (int)(g / N);
-    const int v = (int)(g - (long long)b * N);
-    const int y = v / W, x = v - y * W;
-    const int r = parent[g];
-    int slot = -1;
-    if (r >= 0) slot = size[r];
-    labels[g] = slot >= 0 ? r - b * N : -1;
-    if (slot >= 0 && slot < K) {
-      // run ends only: the first / last pixel of each horizontal run of this component
-      const bool run_start = (x == 0) || (parent[g - 1] != r);
-      const bool run_end = (x == W - 1) || (parent[g + 1] != r);
-      const size_t row = ((size_t)b * K + slot) * H + y;
-      if (run_start) atomicMin(&rowmin[row], x);
-      if (run_end) atomicMax(&rowmax[row], x);
+  const long long start = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  for (long long w0 = start; w0 < total_px; w0 += stride) {
+    const long long g = w0 + lane;
+    int b = -1;
+    bool emit = false;
+    unsigned long long rec = 0;
+    if (g < total_px) {
+      b = (int)(g / N);
+      const int v = (int)(g - (long long)b * N);
+      const int y = v / W, x = v - y * W;
+      const int r = parent[g];
+      int sz = 0;
+      if (r >= 0) sz = size[r];
+      const bool kept = r >= 0 && sz > min_size;  // test_pixellink_fast.py:174 `len(index_list) > 10`
+      const int rl = r - b * N;
+      labels[g] = kept ? rl : -1;
+      if (kept) {
+        const bool run_start = (x == 0) || (parent[g - 1] != r);
+        const bool run_end = (x == W - 1) || (parent[g + 1] != r);
+        emit = run_start || run_end;
+        rec = ((unsigned long long)(unsigned)rl << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
+        if (r == (int)g) {
+          const int slot = atomicAdd(&n_boxes[b], 1);
+          if (slot < K) comp_root[(size_t)b * K + slot] = rl, comp_size[(size_t)b * K + slot] = sz;
+        }
+      }
+    }
+    // warp-aggregated append: one atomic per (warp, image)
+    const unsigned em = __ballot_sync(0xffffffffu, emit);
+    if (emit) {
+      const unsigned peers = __match_any_sync(em, b);
+      const int leader = __ffs(peers) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&nrec[b], __popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      recs[(size_t)b * N + base + __popc(peers & ((1u << lane) - 1u))] = rec;
     }
   }
   tl_end(9);
@@ -396,7 +393,8 @@ decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ siz
 // scheduled ahead of the real ones).
 __global__ void __launch_bounds__(256)
 decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ comp_root,
-                    const int* __restrict__ comp_size, const int* __restrict__ rowmin, const int* __restrict__ rowmax,
+                    const int* __restrict__ comp_size, const int* __restrict__ nrec,
+                    const unsigned long long* __restrict__ recs,
                     int B, int H, int W, int K, double sx, double sy, int npad, int32_t* __restrict__ boxes,
                     float* __restrict__ rects, int32_t* __restrict__ comp) {
   pdl_wait_and_release();
@@ -433,8 +431,27 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
     const int b = s_b, slot = s_slot;
     if (b < 0) { tl_end(10); return; }
     const int nb = min(n_boxes[b], K);
-    const size_t rowbase = ((size_t)b * K + slot) * H;
     const int root = comp_root[(size_t)b * K + slot];
+    // row extremes of this component from the image's run records (the table lives where the explicit-list
+    // path keeps its sort keys, unused here)
+    int* s_rmin = reinterpret_cast<int*>(S.keys);
+    int* s_rmax = s_rmin + H;
+    const int y0 = root / W;  // the component's first row: its minimum pixel index lives there
+    for (int y = y0 + threadIdx.x; y < H; y += blockDim.x) s_rmin[y] = 0x7fffffff, s_rmax[y] = -1;
+    __syncthreads();
+    {
+      const int nr = nrec[b];
+      const unsigned long long* rb = recs + (size_t)b * H * W;
+#pragma unroll 4
+      for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+        const unsigned long long rc = rb[i];
+        if ((int)(rc >> 32) == root) {
+          const int y = (int)(rc >> 16) & 0xffff, x = (int)rc & 0xffff;
+          atomicMin(&s_rmin[y], x);
+          atomicMax(&s_rmax[y], x);
+        }
+      }
+    }
     // output position = rank of this component's label among the image's kept components
     {
       int r = 0;
@@ -445,9 +462,9 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
     // candidates: (minx, y) and (maxx, y) of every occupied row; input index = row-major order
     // (test_pixellink_fast.py:194-197: x*scale_x, y*scale_y assigned into an int64 array -> trunc).
     // Scales >= 1 keep the candidates distinct, so the sort-free hull applies.
-    const int y0 = root / W;  // the component's first row: its minimum pixel index lives there
+    __syncthreads();
     for (int y = y0 + threadIdx.x; y < H; y += blockDim.x) {
-      const int mn = rowmin[rowbase + y], mx = rowmax[rowbase + y];
+      const int mn = s_rmin[y], mx = s_rmax[y];
       if (mx >= 0) {
         const int py = (int)((double)y * sy);
         const int pos = atomicAdd(&s_n, mn == mx ? 1 : 2);
@@ -540,8 +557,8 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   int* size = (int*)(ws + l.size);
   int* comp_root = (int*)(ws + l.comp_root);
   int* comp_size = (int*)(ws + l.comp_size);
-  int* rowmin = (int*)(ws + l.rowmin);
-  int* rowmax = (int*)(ws + l.rowmax);
+  int* nrec = (int*)(ws + l.nrec);
+  unsigned long long* recs = (unsigned long long*)(ws + l.recs);
   const long long total_px = (long long)B * H * W;
   const int N = H * W;
   int rc;
@@ -557,11 +574,11 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
     if (flags_in) {
       flags = const_cast<uint16_t*>(flags_in);
       rc = launch(decode_tile_cc_kernel<false>, tiles, kTW * kTH, 0, s, (const float*)nullptr, (const float*)nullptr,
-                  0.f, 0.f, flags, H, W, parent, size, n_boxes);
+                  0.f, 0.f, flags, H, W, parent, size, n_boxes, nrec);
     } else {  // first kernel of the chain: thresholds + tile labelling in one pass over the logits
       rc = launch_plain(decode_tile_cc_kernel<true>, tiles, kTW * kTH, 0, s, pix_logits, link_logits,
                         prob_to_logit_threshold(p->pixel_thresh), prob_to_logit_threshold(p->link_thresh), flags, H,
-                        W, parent, size, n_boxes);
+                        W, parent, size, n_boxes, nrec);
     }
     if (rc) return rc;
   }
@@ -571,10 +588,8 @@ merge:
   if (rc) return rc;
   rc = launch(decode_flatten_kernel, grid_px, 256, 0, s, flags, H, W, total_px, parent, size);
   if (rc) return rc;
-  rc = launch(decode_roots_kernel, grid_px, 256, 0, s, parent, size, N, (int)total_px, p->min_size, K, comp_root, comp_size,
-                                              n_boxes, rowmin, rowmax, H);
-  if (rc) return rc;
-  rc = launch(decode_labels_kernel, grid_px, 256, 0, s, parent, size, H, W, total_px, K, labels, rowmin, rowmax);
+  rc = launch(decode_labels_kernel, grid_px, 256, 0, s, parent, size, H, W, total_px, p->min_size, K, labels, comp_root,
+              comp_size, n_boxes, nrec, recs);
   if (rc) return rc;
   if (skip_rects) return PLH_OK;
 rects:
@@ -588,7 +603,7 @@ rects:
       attr_bytes = smem;
     }
     const int rect_grid = (int)std::min<long long>((long long)B * K, kNumSMs * 8);
-    rc = launch(decode_rects_kernel, rect_grid, 256, smem, s, n_boxes, comp_root, comp_size, rowmin, rowmax, B, H, W, K,
+    rc = launch(decode_rects_kernel, rect_grid, 256, smem, s, n_boxes, comp_root, comp_size, nrec, recs, B, H, W, K,
                                                       p->scale_x, p->scale_y, npad, boxes, rects, comp);
     if (rc) return rc;
   }

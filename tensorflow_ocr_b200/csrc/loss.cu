@@ -1082,7 +1082,7 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
                                   const float* scores, const uint8_t* pos, const uint8_t* neg,
                                   const int* n_pos_override, int B, int N, int ratio, uint32_t* keys, int2* counts,
                                   ImageInfo* info, float* thr_out, uint8_t* mask, LossHeader* hdr, bool fuse_counts,
-                                  cudaStream_t s) {
+                                  bool head_pdl, cudaStream_t s) {
   int rc;
   if (select_uses_cluster(N)) {
     // cluster form: scores, keys, threshold (and for the loss: mask + normalisers) in one launch
@@ -1098,8 +1098,11 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
       if (e != cudaSuccess) return (int)e;                                                                       \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    /* first kernel of the chain: plain stream order (its CTAs parked under a foreign predecessor only get in its way) */ \
-    rc = launch_plain(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg, \
+    /* first kernel of the chain: plain stream order unless the caller vouches for the predecessor (its CTAs   \
+       parked under a foreign kernel only get in that kernel's way) */                                        \
+    rc = head_pdl ? launch(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg, \
+                n_pos_override, N, ratio, info, thr_out, mask, FROM_SCORES ? (uint32_t*)nullptr : keys, hdr)    \
+         : launch_plain(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg, \
                 n_pos_override, N, ratio, info, thr_out, mask, FROM_SCORES ? (uint32_t*)nullptr : keys, hdr);    \
   }
     if (N <= kClusterSize * kClThreads * 2) PLH_CLUSTER(2)
@@ -1163,16 +1166,17 @@ extern "C" int plh_pixellink_loss(const float* pix_logits, const float* link_log
   int rc = PLH_OK;
   const bool main_only = (p->reserved[0] & 1) != 0;  // K0-K2 already ran on this workspace
   const bool fuse_counts = (p->reserved[0] & 2) == 0;  // bit 1: keep the normalisers in their own pass (K2)
+  const bool head_pdl = (p->reserved[0] & 4) != 0;     // bit 2: the stream's preceding kernel is this library's
   // K0 + K1 (not needed for the positives-only variant: there is no mining, vgg16 :265)
   if (main_only) {
   } else if (p->variant == PLH_VARIANT_MODEL)
     rc = launch_keys_and_select<KEYS_MODEL, false>(pix_logits, pix_lab, link_lab, nullptr, nullptr, nullptr, nullptr, B,
                                                    N, p->neg_pos_ratio, keys, counts, info, stats + PLH_ST_THR, mask,
-                                                   hdr, fuse_counts, s);
+                                                   hdr, fuse_counts, head_pdl, s);
   else if (p->variant == PLH_VARIANT_PIXELLINK)
     rc = launch_keys_and_select<KEYS_PIXELLINK, false>(pix_logits, pix_lab, link_lab, nullptr, nullptr, nullptr,
                                                        nullptr, B, N, p->neg_pos_ratio, keys, counts, info,
-                                                       stats + PLH_ST_THR, mask, hdr, fuse_counts, s);
+                                                       stats + PLH_ST_THR, mask, hdr, fuse_counts, head_pdl, s);
   else {
     e = cudaMemsetAsync(stats + PLH_ST_THR, 0xff, sizeof(float) * B, s);  // thr[b] = NaN
     // header and the ImageInfo rows (adjacent in the workspace): K2 accumulates into the rows
@@ -1298,10 +1302,10 @@ extern "C" int plh_ohnm_batch(const float* scores, const uint8_t* pos_mask, cons
   cudaStream_t s = (cudaStream_t)stream;
   int rc = variant == PLH_VARIANT_MODEL
                ? launch_keys_and_select<KEYS_MODEL, true>(nullptr, nullptr, nullptr, scores, pos_mask, neg_mask, n_pos, B,
-                                                          N, neg_pos_ratio, keys, counts, info, thr, nullptr, nullptr, false, s)
+                                                          N, neg_pos_ratio, keys, counts, info, thr, nullptr, nullptr, false, false, s)
                : launch_keys_and_select<KEYS_PIXELLINK, true>(nullptr, nullptr, nullptr, scores, pos_mask, neg_mask,
                                                               n_pos, B, N, neg_pos_ratio, keys, counts, info, thr,
-                                                              nullptr, nullptr, false, s);
+                                                              nullptr, nullptr, false, false, s);
   if (rc) return rc;
   const long long total = (long long)B * N;
   const int grid = (int)std::min<long long>((total + 255) / 256, kNumSMs * 8);

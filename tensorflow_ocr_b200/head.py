@@ -35,10 +35,11 @@ class LossConfig:
     focal_gamma: float = 2.0
     main_only: bool = False       # measurement hook: rerun the main pass on an already prepared workspace
     split_counts: bool = False    # scheduling hint: normalisers in their own pass instead of fused into the selection
+    chain_pdl: bool = False       # scheduling hint: the stream's preceding kernel is this library's (early launch ok)
 
     def c_struct(self):
         p = _lib.LossParams(self.variant, self.term, self.neg_pos_ratio, self.focal_alpha, self.focal_gamma)
-        p.reserved[0] = (1 if self.main_only else 0) | (2 if self.split_counts else 0)
+        p.reserved[0] = (1 if self.main_only else 0) | (2 if self.split_counts else 0) | (4 if self.chain_pdl else 0)
         return p
 
 
@@ -287,18 +288,16 @@ def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossCo
     aux = _aux_stream(dev)
     aux.wait_stream(cur)
     # The decode's threshold + tile-labelling kernel and the loss's selection kernel are both bound by
-    # integer issue and only slow each other down, so the tile pass runs first, alone (13 us); then the
-    # loss chain runs beside the decode's latency-bound merge / flatten / label kernels.  The normalisers
-    # stay in their own pass here (split_counts): the fused selection kernel is the shortest loss chain
-    # on its own, but next to the decode its longer residency costs more than the saved launch
-    # (DESIGN.md section 5).
+    # integer issue and only slow each other down, so the tile pass runs first, alone (13 us); the
+    # selection kernel launches programmatically under its tail (chain_pdl), and the loss chain then runs
+    # beside the decode's latency-bound merge / flatten / label kernels.
     B, H, W = pix_logits.shape[:3]
     with torch.cuda.device(dev):
         ws = _workspace(_lib.OP_DECODE, B, H, W, dcfg.max_boxes, dev)
     decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=4), out, want_rects, ws)
     aux.wait_stream(cur)
-    pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, dataclasses.replace(lcfg, split_counts=True), True,
-                       False, None, out)
+    pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, dataclasses.replace(lcfg, chain_pdl=True), True, False,
+                       None, out)
     with torch.cuda.stream(aux):
         decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=8), out, want_rects, ws)
     cur.wait_stream(aux)
