@@ -202,6 +202,22 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Wait for a phase of an mbarrier.  The suspend-time hint lets the hardware park the thread until the
+// phase completes instead of returning to a polling loop every few hundred cycles: waiting warps then
+// issue (almost) nothing, which matters when another kernel shares the SM.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(0x989680)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, int rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -226,14 +242,7 @@ __device__ __forceinline__ void cluster_exchange3(unsigned long long (*slot)[kCl
                  "r"(rbar)
                  : "memory");
   }
-  const uint32_t phase = (e >> 1) & 1;
-  uint32_t done;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(done)
-                 : "r"(bar), "r"(phase)
-                 : "memory");
-  } while (!done);
+  mbar_wait(bar, (e >> 1) & 1);
   const unsigned long long v0 = mine[lane], v1 = mine[lane + 32];
   t0 = __reduce_add_sync(0xffffffffu, (unsigned)(v0 & 0xffffu) + (unsigned)(v1 & 0xffffu));
   t1 = __reduce_add_sync(0xffffffffu, (unsigned)((v0 >> 16) & 0xffffu) + (unsigned)((v1 >> 16) & 0xffffu));
@@ -384,17 +393,7 @@ ohem_select_cluster_kernel(const float* __restrict__ pix_logits, const float* __
     unsigned nsp = 0, nsel = 0;
 #pragma unroll
     for (int j0 = 0; j0 < KPT; j0 += KB) {
-      {  // the pass's labels have landed (pass 0 was issued before the selection rounds)
-        const uint32_t bar = smem_u32(&s_mbar[2]);
-        const uint32_t phase = (j0 / KB) & 1;
-        uint32_t done;
-        do {
-          asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                       : "=r"(done)
-                       : "r"(bar), "r"(phase)
-                       : "memory");
-        } while (!done);
-      }
+      mbar_wait(smem_u32(&s_mbar[2]), (j0 / KB) & 1);  // the pass's labels have landed (pass 0 flew during the rounds)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         unsigned cP[4] = {0u, 0u, 0u, 0u}, cN[4] = {0u, 0u, 0u, 0u};
@@ -759,15 +758,6 @@ constexpr int kStages = PLH_K3_STAGES;
 constexpr int kMainBlock = kMainThreads + 32;          // + the producer warp
 constexpr size_t kMainSmem = (size_t)kStages * kStageBytes;
 
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(done)
-                 : "r"(bar), "r"(parity)
-                 : "memory");
-  } while (!done);
-}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
