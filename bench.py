@@ -328,7 +328,7 @@ def run_gpu(args):
         alg = BYTES_LOSS * PX
         ach = alg / per_launch_s / 1e9
         roofline = {"bound": "hbm", "kernel": "loss_main_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": 61.5e6, "peak_source": peak_src,
+                    "frac": ach / peak, "traffic": 61.0e6, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": per_launch_s * 1e6,
                     "launches_timed": nprof,
                     "method": "kernel relaunched alone back to back (CUDA graph of %d launches over the rotating "
@@ -340,7 +340,7 @@ def run_gpu(args):
                     "window_note": "device window = first CTA start to last CTA end (%globaltimer); us_per_launch minus "
                                    "it is the launch/drain latency between dependent launches, which the step hides "
                                    "behind the preceding kernel (programmatic dependent launch)",
-                    "traffic_note": "ncu dram__bytes_read+write per launch (profiles/): 57.2 MB read + 4.4 MB written "
+                    "traffic_note": "ncu dram__bytes_read+write per launch (profiles/): 57.2 MB read + 3.9 MB written "
                                     "to DRAM; the 37.7 MB of gradients are still dirty in the 126 MB L2 at kernel end",
                     "frac_of_nominal_8TBs": ach / 8000.0,
                     "whole_step_GBs": (BYTES_LOSS + BYTES_DECODE_EXTRA) * PX / (ms_total * 1e-3 / args.steps) / 1e9}
