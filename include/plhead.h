@@ -251,6 +251,18 @@ PLH_API size_t plh_workspace_bytes(int op, int B, int H, int W, int K);
 PLH_API int plh_version(void);
 PLH_API const char* plh_strerror(int code);
 /*
+ * Link (and pixel) labels from a polygon-id map — the GPU part of generate_rbox
+ * (tool/pixellink_fn.py:81-111 with valid_link :9-47).
+ *  ids      [B,H,W] uint8: 0 background, i = polygon i (what cv2.fillPoly(poly_mask, poly, idx+1) and the
+ *           INTER_NEAREST resize to (w/4, h/4) leave, :76-79)
+ *  link_lab [B,H,W,8] float: for a pixel of polygon v: 1 in all directions on the map border (:10-11), else
+ *           1 where the neighbour in that direction has id v; 0 for background.  Channel order as the
+ *           reference: left, left_down, left_up, right, right_down, right_up, up, down.
+ *  pix_lab  [B,H,W] float, optional: 1 where ids != 0.
+ */
+PLH_API int plh_link_labels(const uint8_t* ids, int B, int H, int W, float* link_lab, float* pix_lab, void* stream);
+
+/*
  * Measurement hooks (bench.py roofline): between begin and end, every plh_pixellink_loss call
  * records CUDA events around its dominant kernel (loss_main) on the launching stream;
  * end() returns the summed device time and the number of launches.  Not for use under

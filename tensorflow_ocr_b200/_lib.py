@@ -49,6 +49,7 @@ SIGNATURES = {
     "plh_restore_rectangle": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "plh_east_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _sz, _vp]),
     "plh_lanms": (_i, [_vp, _vp, _i, _i, C.c_double, _vp, _vp, _vp, _sz, _vp]),
+    "plh_link_labels": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "plh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "plh_version": (_i, []),
     "plh_strerror": (C.c_char_p, [_i]),

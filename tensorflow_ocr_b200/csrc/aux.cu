@@ -365,6 +365,43 @@ rr_scatter_kernel(const float* __restrict__ origin, const float* __restrict__ ge
   if (out_index) out_index[row] = i;
 }
 
+
+// ------------------------------------------------------------------ link labels from a polygon-id map
+// tool/pixellink_fn.py:81-111 (generate_rbox's double loop over polygons and their pixels, with
+// valid_link :9-47): a pixel inside polygon v gets link label 1 in every direction if it lies on the map
+// border, else 1 exactly in the directions whose neighbour carries the same id; background stays 0.
+// Channel order = the reference's: left, left_down, left_up, right, right_down, right_up, up, down.
+// One thread per pixel: 1 B read (+8 neighbour bytes from L1), 32 (+4) B written with 128-bit stores.
+__constant__ int c_ldy[8] = {0, 1, -1, 0, 1, -1, -1, 1};
+__constant__ int c_ldx[8] = {-1, -1, -1, 1, 1, 1, 0, 0};
+
+__global__ void __launch_bounds__(256)
+link_labels_kernel(const uint8_t* __restrict__ ids, int H, int W, long long total_px, float* __restrict__ link_lab,
+                   float* __restrict__ pix_lab) {
+  const int N = H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
+    const int v = (int)(g % N);
+    const int y = v / W, x = v - y * W;
+    const unsigned id = ids[g];
+    float l[8];
+    if (id == 0) {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) l[d] = 0.f;
+    } else if (x == 0 || y == 0 || x == W - 1 || y == H - 1) {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) l[d] = 1.f;
+    } else {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) l[d] = ids[g + (long long)c_ldy[d] * W + c_ldx[d]] == id ? 1.f : 0.f;
+    }
+    float4* o = reinterpret_cast<float4*>(link_lab) + g * 2;
+    stg_stream4(o, make_float4(l[0], l[1], l[2], l[3]));
+    stg_stream4(o + 1, make_float4(l[4], l[5], l[6], l[7]));
+    if (pix_lab) pix_lab[g] = id != 0 ? 1.f : 0.f;
+  }
+}
+
 }  // namespace plh
 
 using namespace plh;
@@ -428,6 +465,16 @@ extern "C" int plh_restore_rectangle(const float* origin, const float* geometry,
   rr_scan_kernel<<<1, 1024, 0, s>>>(blockcnt, nb, total);
   if ((rc = launch_status())) return rc;
   rr_scatter_kernel<<<nb, kRRBlock, 0, s>>>(origin, geometry, N, blockcnt, total, out, out_index);
+  return launch_status();
+}
+
+extern "C" int plh_link_labels(const uint8_t* ids, int B, int H, int W, float* link_lab, float* pix_lab, void* stream) {
+  if (!ids || !link_lab) return PLH_E_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (!aligned16(link_lab)) return PLH_E_ALIGN;
+  const long long total = (long long)B * H * W;
+  const int grid = (int)std::min<long long>((total + 255) / 256, kNumSMs * 16);
+  link_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ids, H, W, total, link_lab, pix_lab);
   return launch_status();
 }
 

@@ -261,10 +261,13 @@ ohem_select_cluster_kernel(const float* __restrict__ pix_logits, const float* __
                            const uint8_t* __restrict__ pos_mask, const uint8_t* __restrict__ neg_mask,
                            const int* __restrict__ n_pos_override, int N, int ratio, ImageInfo* __restrict__ info,
                            float* __restrict__ thr_out, uint8_t* __restrict__ mask, uint32_t* __restrict__ keys_out,
-                           LossHeader* __restrict__ hdr) {
+                           LossHeader* __restrict__ hdr, int overlap_prev) {
   static_assert(KPT <= kClMaxKPT && 32 * KPT < 65536, "per-warp counts are exchanged in 16-bit fields");
   static_assert(!(COUNTS && FROM_SCORES), "the standalone OHNM has no link labels");
-  pdl_wait();
+  // overlap_prev: the caller vouches that the preceding kernel of the stream touches nothing this call
+  // touches (the decode's tile pass): no need to wait for it, only for what came before it — which was
+  // complete before that kernel could start.
+  if (!overlap_prev) pdl_wait();
   tl_start(1);
   namespace cg = cooperative_groups;
   extern __shared__ __align__(128) unsigned char s_stage[];  // COUNTS: link labels of up to 8 chunks (64 KB)
@@ -1091,9 +1094,9 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
     /* first kernel of the chain: plain stream order unless the caller vouches for the predecessor (its CTAs   \
        parked under a foreign kernel only get in that kernel's way) */                                        \
     rc = head_pdl ? launch(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg, \
-                n_pos_override, N, ratio, info, thr_out, mask, FROM_SCORES ? (uint32_t*)nullptr : keys, hdr)    \
+                n_pos_override, N, ratio, info, thr_out, mask, FROM_SCORES ? (uint32_t*)nullptr : keys, hdr, 1) \
          : launch_plain(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg, \
-                n_pos_override, N, ratio, info, thr_out, mask, FROM_SCORES ? (uint32_t*)nullptr : keys, hdr);    \
+                n_pos_override, N, ratio, info, thr_out, mask, FROM_SCORES ? (uint32_t*)nullptr : keys, hdr, 0); \
   }
     if (N <= kClusterSize * kClThreads * 2) PLH_CLUSTER(2)
     else if (N <= kClusterSize * kClThreads * 8) PLH_CLUSTER(8)

@@ -304,6 +304,23 @@ def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossCo
     return out
 
 
+def link_labels_raw(ids: torch.Tensor, want_pixel: bool = True):
+    """plh_link_labels: ids uint8 [B,H,W] (CUDA) -> (link_lab fp32 [B,H,W,8], pix_lab fp32 [B,H,W] or None)."""
+    lib = _lib.load()
+    if ids.dtype != torch.uint8 or ids.dim() != 3:
+        raise ValueError("ids must be uint8 [B,H,W]")
+    dev = ids.device
+    _require_gpu(dev)
+    ids = ids.contiguous()
+    B, H, W = ids.shape
+    link = torch.empty((B, H, W, 8), dtype=torch.float32, device=dev)
+    pix = torch.empty((B, H, W), dtype=torch.float32, device=dev) if want_pixel else None
+    with torch.cuda.device(dev):
+        rc = lib.plh_link_labels(_p(ids), B, H, W, _p(link), _p(pix), _stream(dev))
+    _lib.check(rc, "plh_link_labels")
+    return link, pix
+
+
 def min_area_boxes_raw(pts: torch.Tensor, offsets: torch.Tensor, want_rects=True):
     """plh_min_area_boxes: pts int32 [total,2], offsets int32 [n+1] -> boxes int32 [n,4,2], rects [n,5]."""
     lib = _lib.load()

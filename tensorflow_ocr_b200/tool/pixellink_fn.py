@@ -1,4 +1,5 @@
-"""Mirror of the reference's ``tool/pixellink_fn.py`` decode helper (lines 120-158)."""
+"""Mirror of the reference's ``tool/pixellink_fn.py``: the decode helper (lines 120-158) and the
+ground-truth generator ``generate_rbox`` (lines 49-117)."""
 from __future__ import annotations
 
 import numpy as np
@@ -6,7 +7,7 @@ import torch
 
 from .. import head
 
-__all__ = ["pixel_detect", "tf_pixel_detect"]
+__all__ = ["pixel_detect", "tf_pixel_detect", "generate_rbox", "tf_pixellink_get_rbox", "link_labels_from_ids"]
 
 
 def pixel_detect(score_map, geo_map, score_map_thresh=0.8, link_thresh=0.8):
@@ -31,3 +32,50 @@ def pixel_detect(score_map, geo_map, score_map_thresh=0.8, link_thresh=0.8):
 def tf_pixel_detect(score_map, geo_map, score_map_thresh, link_thresh):
     """tool/pixellink_fn.py:156-158 wraps pixel_detect in tf.py_func; here the op is native."""
     return pixel_detect(score_map, geo_map, score_map_thresh, link_thresh)
+
+
+def link_labels_from_ids(poly_mask):
+    """The double loop of generate_rbox (tool/pixellink_fn.py:81-109 with valid_link :9-47) on the GPU.
+
+    ``poly_mask`` uint8 [H,W] or [B,H,W] (0 background, i = polygon i) -> link map fp32 [...,8]."""
+    t, np_in = head.to_device(poly_mask, dtype=torch.uint8)
+    single = t.dim() == 2
+    link, _ = head.link_labels_raw(t[None] if single else t, want_pixel=False)
+    link = link[0] if single else link
+    return link.cpu().numpy() if np_in else link
+
+
+def generate_rbox(h, w, xs, ys, bboxes, ignored):
+    """tool/pixellink_fn.py:53-111.  Same arguments and returns (res_score_map [h/4,w/4] fp32,
+    res_link_map [h/4,w/4,8] fp32, show_bboxes [200,4] fp32) as numpy arrays.
+
+    The polygon rasterisation and the nearest-neighbour resize stay on the host with the same OpenCV
+    calls as the reference (:72-79, a few polygons per image); the per-pixel link-label loop — the part
+    that is O(pixels x 8) interpreted Python in the reference — runs on the GPU."""
+    import cv2
+    if len(xs) != len(ignored):
+        raise AssertionError("the length of xs and ignored must be the same, but got %s and %s" % (len(xs), len(ignored)))
+    h, w = int(h), int(w)
+    new_h, new_w = h // 4, w // 4          # Python-2 integer division in the reference (:56-57)
+    score_map = np.zeros((h, w), dtype=np.float32)
+    poly_mask = np.zeros((h, w), dtype=np.uint8)
+    show_bboxes = np.zeros((200, 4), dtype=np.float32)
+    xs = np.asarray(xs, dtype=np.float32)
+    ys = np.asarray(ys, dtype=np.float32)
+    bboxes = np.asarray(bboxes)
+    for idx in range(xs.shape[0]):
+        points = list(zip(xs[idx, :] * w, ys[idx, :] * h))
+        show_bboxes[idx, :] = bboxes[idx, :]
+        draw_poly = np.array([points], np.int32)
+        cv2.fillPoly(score_map, draw_poly, 1.0)
+        cv2.fillPoly(poly_mask, draw_poly, idx + 1)
+    res_score_map = cv2.resize(score_map, (new_w, new_h), interpolation=cv2.INTER_NEAREST)
+    poly_mask = cv2.resize(poly_mask, (new_w, new_h), interpolation=cv2.INTER_NEAREST)
+    res_link_map = link_labels_from_ids(poly_mask)
+    return res_score_map, res_link_map, show_bboxes
+
+
+def tf_pixellink_get_rbox(img_size, xs, ys, bboxes, ignored):
+    """tool/pixellink_fn.py:113-118 wraps generate_rbox in tf.py_func; here it is called directly."""
+    h, w = img_size
+    return generate_rbox(h, w, xs, ys, bboxes, ignored)

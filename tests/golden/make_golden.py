@@ -253,9 +253,47 @@ def golden_numpy_pieces():
     save("example_softmax", x=x.numpy(), y=tf.slim.softmax(x).numpy())
 
 
+def golden_generate_rbox():
+    """tool/pixellink_fn.py valid_link + generate_rbox, executed as written except for the two Python-2
+    idioms that do not run under Python 3: `h/4`, `w/4` (integer division there) and `zip(...)` (a list there)."""
+    import cv2
+    ns = dict(np=np, cv2=cv2)
+    src, span = cut("tool/pixellink_fn.py", "valid_link")
+    print("tool/pixellink_fn.py valid_link", span)
+    exec(src, ns)
+    src, span = cut("tool/pixellink_fn.py", "generate_rbox")
+    print("tool/pixellink_fn.py generate_rbox", span)
+    assert "new_h = h/4" in src and "new_w = w/4" in src and "points = zip(" in src
+    src = src.replace("new_h = h/4", "new_h = h//4").replace("new_w = w/4", "new_w = w//4")
+    src = src.replace("points = zip(xs[idx, :] * w, ys[idx, :] * h )", "points = list(zip(xs[idx, :] * w, ys[idx, :] * h ))")
+    exec(src, ns)
+    rng = np.random.default_rng(11)
+    cases = {}
+    for ci, (h, w, n) in enumerate([(64, 96, 3), (128, 128, 6), (48, 200, 9)]):
+        xs, ys = [], []
+        for i in range(n):
+            c = rng.uniform(0.1, 0.9, 2)
+            a = rng.uniform(-0.6, 0.6)
+            hw, hh = rng.uniform(0.05, 0.3), rng.uniform(0.03, 0.12)
+            R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+            p = (np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T) + c   # may leave [0,1]: clipped by fillPoly
+            xs.append(p[:, 0]); ys.append(p[:, 1])
+        xs, ys = np.array(xs, np.float32), np.array(ys, np.float32)
+        bboxes = np.stack([ys.min(1), xs.min(1), ys.max(1), xs.max(1)], 1).astype(np.float32)
+        ignored = (rng.uniform(size=n) < 0.3).astype(np.int64)
+        score, link, show = ns["generate_rbox"](h, w, xs, ys, bboxes, ignored)
+        cases.update({"h%d" % ci: h, "w%d" % ci: w, "xs%d" % ci: xs, "ys%d" % ci: ys, "bboxes%d" % ci: bboxes,
+                      "ignored%d" % ci: ignored, "score%d" % ci: score, "link%d" % ci: link, "show%d" % ci: show})
+    save("generate_rbox", n_cases=3, **cases)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rbox":
+        golden_generate_rbox()
+        sys.exit(0)
     golden_model_loss()
     golden_vgg16()
     golden_pixellink_build_loss()
     golden_numpy_pieces()
+    golden_generate_rbox()

@@ -124,3 +124,32 @@ def test_lanms_vs_oracle(cuda_dev):
     for s, r in zip(sets, res):
         ref = E.nms_locality(s, 0.3) if len(s) else np.zeros((0, 9))
         assert r.shape == ref.shape and np.allclose(r, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_link_labels_vs_oracle_and_golden(cuda_dev):
+    """plh_link_labels (the GPU part of generate_rbox) — bit-exact vs the oracle on random id maps, and the
+    drop-in generate_rbox vs the reference-executed golden."""
+    import os
+    import torch
+    from oracle import labels as OL
+    from tensorflow_ocr_b200 import head
+    from tensorflow_ocr_b200.tool import pixellink_fn
+    rng = np.random.default_rng(5)
+    for (B, H, W) in ((1, 1, 1), (2, 3, 5), (3, 37, 61), (2, 128, 128)):
+        ids = np.zeros((B, H, W), np.uint8)
+        for b in range(B):
+            for k in range(1, 6):
+                y0, x0 = rng.integers(0, H), rng.integers(0, W)
+                ids[b, y0:y0 + rng.integers(1, H + 1), x0:x0 + rng.integers(1, W + 1)] = k
+        link, pix = head.link_labels_raw(torch.as_tensor(ids).cuda())
+        torch.cuda.synchronize()
+        for b in range(B):
+            assert np.array_equal(link[b].cpu().numpy(), OL.link_labels_from_ids(ids[b]))
+        assert np.array_equal(pix.cpu().numpy(), (ids != 0).astype(np.float32))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "generate_rbox.npz"))
+    for ci in range(int(g["n_cases"])):
+        score, link, show = pixellink_fn.generate_rbox(int(g["h%d" % ci]), int(g["w%d" % ci]), g["xs%d" % ci],
+                                                       g["ys%d" % ci], g["bboxes%d" % ci], g["ignored%d" % ci])
+        assert np.array_equal(score, g["score%d" % ci])
+        assert np.array_equal(link, g["link%d" % ci])
+        assert np.array_equal(show, g["show%d" % ci])

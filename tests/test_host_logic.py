@@ -102,6 +102,8 @@ def test_drop_in_signatures_match_the_reference_names():
     assert list(sig.parameters) == ["score_map", "geo_map", "score_map_thresh", "link_thresh"]
     assert sig.parameters["score_map_thresh"].default == 0.8 and sig.parameters["link_thresh"].default == 0.8
     assert params(pixellink_fn.tf_pixel_detect) == ["score_map", "geo_map", "score_map_thresh", "link_thresh"]
+    assert params(pixellink_fn.generate_rbox) == ["h", "w", "xs", "ys", "bboxes", "ignored"]
+    assert params(pixellink_fn.tf_pixellink_get_rbox) == ["img_size", "xs", "ys", "bboxes", "ignored"]
     assert params(icdar.restore_rectangle) == ["origin", "geometry"]
     sig = inspect.signature(decode.decode_pixellink)
     assert sig.parameters["pixel_thresh"].default == 0.8 and sig.parameters["link_thresh"].default == 0.9

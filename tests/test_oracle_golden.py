@@ -128,3 +128,17 @@ def test_gradients_match_finite_differences():
             fd = (vals[0] - vals[1]) / (2 * eps)
             an = float(base[key].reshape(-1)[idx])
             assert abs(fd - an) <= 1e-4 * abs(an) + 1e-7, (name, idx, fd, an)
+
+
+def test_generate_rbox_matches_reference_execution(golden_dir):
+    """oracle/labels.py vs tool/pixellink_fn.py generate_rbox executed by tests/golden/make_golden.py."""
+    from oracle import labels as OL
+    g = np.load(golden_dir + "/generate_rbox.npz")
+    for ci in range(int(g["n_cases"])):
+        score, link, show, pm = OL.generate_rbox(int(g["h%d" % ci]), int(g["w%d" % ci]), g["xs%d" % ci], g["ys%d" % ci],
+                                                 g["bboxes%d" % ci], g["ignored%d" % ci])
+        assert np.array_equal(score, g["score%d" % ci])
+        assert np.array_equal(link, g["link%d" % ci])
+        assert np.array_equal(show, g["show%d" % ci])
+        assert link.sum() > 0
+        assert np.array_equal(OL.link_labels_from_ids(pm), OL.link_labels_from_ids_loop(pm))
