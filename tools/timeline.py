@@ -20,7 +20,9 @@ torch.cuda.set_stream(ms)
 lcfg, dcfg = head.LossConfig(), head.DecodeConfig(max_boxes=128)
 def step(i):
     d = sets[i % 6]
-    if os.environ.get("TL_MODE", "fused") == "loss":
+    if os.environ.get("TL_MODE", "fused") == "decode":
+        head.decode_raw(d["pix_logits"], d["link_logits"], dcfg, d["out"], want_rects=False)
+    elif os.environ.get("TL_MODE", "fused") == "loss":
         head.pixellink_loss_raw(d["pix_logits"], d["link_logits"], d["pix_lab"], d["link_lab"], lcfg, True, False, None, d["out"])
     else:
         head.loss_and_decode_raw(d["pix_logits"], d["link_logits"], d["pix_lab"], d["link_lab"], lcfg, dcfg, d["out"])
