@@ -218,3 +218,15 @@ def test_split_counts_hint_is_result_neutral(variant, cuda_dev):
     b = _run(inp, head.LossConfig(variant=v, split_counts=True))
     for k in ("stats", "grad_pixel", "grad_link", "ohem_mask"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("hw", [(256, 256), (257, 255), (64, 32), (8, 256)])
+def test_loss_select_path_boundaries(hw, cuda_dev):
+    """Image sizes at the edges of the cluster kernel's register tiers (2 / 8 / 32 keys per thread: 4096,
+    16384, 65536 px) and one pixel beyond the last tier (general path)."""
+    from oracle import pixellink_loss as O
+    from tensorflow_ocr_b200 import head, synth
+    H, W = hw
+    inp = synth.make_batch(123 + H, 2, H, W, "G", edge_images=False)
+    ref = O.loss_model(inp["pix_lab"], inp["pix_logits"], inp["link_lab"], inp["link_logits"])
+    _compare(_run(inp, head.LossConfig()), ref, 2)
