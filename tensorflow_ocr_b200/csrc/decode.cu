@@ -196,19 +196,37 @@ decode_tile_cc_kernel(const float* __restrict__ pix_logits, const float* __restr
   const int gy = ty0 + ly, gx = tx0 + lx;
   const bool inimg = gy < H && gx < W;
   if (FROM_LOGITS) {
-    unsigned fl = 0;
-    if (inimg) {
-      const size_t g = base + (size_t)gy * W + gx;
-      const float4* ll4 = reinterpret_cast<const float4*>(link_logits) + g * 4;
-      const float4 l0 = ldg_stream4(ll4), l1 = ldg_stream4(ll4 + 1), l2 = ldg_stream4(ll4 + 2), l3 = ldg_stream4(ll4 + 3);
-      const float2 pp = ldg_stream2(reinterpret_cast<const float2*>(pix_logits) + g);
-      fl = ((l0.y - l0.x) > tl_logit ? 1u : 0u) | ((l0.w - l0.z) > tl_logit ? 2u : 0u) |
-           ((l1.y - l1.x) > tl_logit ? 4u : 0u) | ((l1.w - l1.z) > tl_logit ? 8u : 0u) |
-           ((l2.y - l2.x) > tl_logit ? 16u : 0u) | ((l2.w - l2.z) > tl_logit ? 32u : 0u) |
-           ((l3.y - l3.x) > tl_logit ? 64u : 0u) | ((l3.w - l3.z) > tl_logit ? 128u : 0u) |
-           ((pp.y - pp.x) > tp_logit ? kFlagP : 0u);
-      flags[g] = (uint16_t)fl;
+    // A warp is one tile row = 32 consecutive pixels.  Link logits are read like decode_flags_kernel does:
+    // four iterations, lane = (pixel-in-iteration, quarter), one fully coalesced 128-bit load each (512 B
+    // per warp instruction); the quad's bits are OR-ed and handed to the lane that owns the pixel.
+    static_assert(kTW == 32, "one warp per tile row");
+    const int lane = tid & 31;
+    const int j = lane & 3, qp = lane >> 2;
+    const bool rowin = gy < H;
+    const size_t row0 = base + (size_t)(rowin ? gy : 0) * W + tx0;  // first pixel of this warp's row
+    const float4* ll4 = reinterpret_cast<const float4*>(link_logits);
+    float4 L[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int px = it * 8 + qp;
+      L[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rowin && tx0 + px < W) L[it] = ldg_stream4(ll4 + ((row0 + px) * 4 + j));
     }
+    float2 pp = make_float2(0.f, 0.f);
+    if (inimg) pp = ldg_stream2(reinterpret_cast<const float2*>(pix_logits) + row0 + lx);
+    unsigned fl = 0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      unsigned bits = ((L[it].y - L[it].x) > tl_logit ? 1u : 0u) << (2 * j) |
+                      ((L[it].w - L[it].z) > tl_logit ? 1u : 0u) << (2 * j + 1);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+      // pixel lane l owns pixel (l >> 3) * 8 + (l & 7): iteration l >> 3, quad l & 7
+      const unsigned got = __shfl_sync(0xffffffffu, bits, (lane & 7) << 2);
+      if ((lane >> 3) == it) fl = got;
+    }
+    fl = inimg ? (fl | ((pp.y - pp.x) > tp_logit ? kFlagP : 0u)) : 0u;
+    if (inimg) flags[row0 + lx] = (uint16_t)fl;
     sf[ly + 1][lx + 1] = (uint16_t)fl;
   } else {
     for (int i = tid; i < (kTH + 2) * (kTW + 2); i += kTW * kTH) {
