@@ -365,6 +365,8 @@ ohem_select_cluster_kernel(const float* __restrict__ pix_logits, const float* __
 
   uint32_t ans = 0;
   if (!none) {  // uniform over the cluster
+    // c_lo < k <= c_hi: number of keys <= the lower / upper end of the interval the answer is known to lie in
+    int c_lo = 0, c_hi = (KEYMODE == KEYS_MODEL) ? n_neg : N;
     for (int e = 1; e <= 15; ++e) {
       const int lo = 30 - 2 * e;  // this round resolves bits lo+1, lo
       const uint32_t low = (1u << lo) - 1u;
@@ -382,7 +384,22 @@ ohem_select_cluster_kernel(const float* __restrict__ pix_logits, const float* __
       g2 = __reduce_add_sync(0xffffffffu, g2);
       int t0, t1, t2;  // #keys <= pivot over the whole image
       cluster_exchange3(s_slot, s_mbar, e, rank, warp, lane, 32u * KPT - g0, 32u * KPT - g1, 32u * KPT - g2, t0, t1, t2);
-      ans |= (uint32_t)((t0 < k) + (t1 < k) + (t2 < k)) << lo;
+      const int q = (t0 < k) + (t1 < k) + (t2 < k);
+      ans |= (uint32_t)q << lo;
+      c_lo = q == 0 ? c_lo : (q == 1 ? t0 : (q == 2 ? t1 : t2));
+      c_hi = q == 0 ? t0 : (q == 1 ? t1 : (q == 2 ? t2 : c_hi));
+      if (c_hi - c_lo == 1 && e < 14) {
+        // Exactly one key is left in the interval, so it is the answer: its owner posts it (one more
+        // exchange instead of the 15 - e remaining rounds; scores without ties get here after ~8 rounds).
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) mine |= ((rk[j] >> lo) == (ans >> lo)) ? rk[j] : 0u;  // excluded keys: bit 30 set
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        int v0, v1, v2;
+        cluster_exchange3(s_slot, s_mbar, e + 1, rank, warp, lane, mine & 0xffffu, mine >> 16, 0u, v0, v1, v2);
+        ans = (uint32_t)v0 | ((uint32_t)v1 << 16);
+        break;
+      }
     }
   }
   tl_end(12);

@@ -40,7 +40,7 @@ torch.cuda.set_stream(ms)
 for i in range(30):
     graphs[i % 6].replay()
 torch.cuda.synchronize()
-names = ["K0 keys", "K1 select", "K2 counts", "K3 main", "D0 flags", "D1a tile_cc", "D1b cross", "D2 flatten", "D3 roots", "D4 labels", "D5 rects", "K1 preamble", "K1 loop", "K1 counted", "K1 posted"]
+names = ["K0 keys (general path)", "K1 select", "K2 counts (split/general)", "K3 main", "D0 flags (standalone)", "D1a tile_cc", "D1b cross", "D2 flatten", "(unused)", "D4 labels", "D5 rects", "K1 preamble", "K1 loop", "K1 counted", "K1 posted"]
 acc = np.zeros((15, 2))
 reps = 20
 for r in range(reps):
@@ -54,7 +54,8 @@ for r in range(reps):
     t0 = t[used & (t[:, 0] > 0) & (t[:, 0] < 2**62), 0].min()
     acc += np.where(used[:, None], (t - t0) / 1e3, 0.0)
 acc /= reps
-print("%-14s %9s %9s %9s" % ("kernel", "start us", "end us", "dur us"))
+print("%-26s %9s %9s %9s" % ("kernel", "start us", "end us", "dur us"))
 for n, (a, b) in zip(names, acc):
-    print("%-14s %9.2f %9.2f %9.2f" % (n, a, b, b - a))
+    if b > 0:
+        print("%-26s %9.2f %9.2f %9.2f" % (n, max(a, 0.0), b, b - max(a, 0.0)))
 print("step span: %.2f us" % (acc[:, 1].max()))
