@@ -260,7 +260,11 @@ def run_gpu(args):
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    per_rank_ms = [float(ms.item())]
     if world > 1:
+        allms = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(allms, ms)
+        per_rank_ms = [float(t.item()) for t in allms]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = world * B * args.steps / (ms_total * 1e-3)
@@ -422,6 +426,7 @@ def run_gpu(args):
                        "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2" % (
                            NSETS, NSETS * (108 + 72) * PX / 1e6),
                        "cuda_graphs": graphs is not None,
+                       "us_per_step_per_rank": [round(t / args.steps * 1e3, 2) for t in per_rank_ms],
                        "collective": ("async NCCL all-reduce of 64 loss scalars every %d steps (the reference's reporting "
                                       "cadence, multigpu_train.py:179)" % REDUCE_EVERY) if world > 1 else "none"},
             "clocks": clocks,
