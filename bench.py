@@ -218,6 +218,18 @@ def run_gpu(args):
             graphs.append(g)
         torch.cuda.synchronize()
         torch.cuda.set_stream(main_stream)
+    # ... and one graph holding a whole round of NSETS consecutive steps: a graph launch costs the host
+    # ~10-20 us and the device a ~2.5 us gap, which is a visible fraction of a 65 us step (and makes the
+    # loop host-bound as soon as a process group's helper threads compete for the interpreter).
+    # Steps that do not fill a round use the per-set graphs.
+    round_graph = None
+    if graphs is not None and not os.environ.get("BENCH_STEP_GRAPHS"):
+        round_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(round_graph, stream=main_stream):
+            for i in range(NSETS):
+                step(i)
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(main_stream)
 
     launches_per_step = [0]
     # training mode, N > 1: the only exchange of the path is the tower-summed loss for reporting, which the
@@ -226,7 +238,8 @@ def run_gpu(args):
     # compute stream only waits for the all-reduce that last read the stats buffer it is about to
     # overwrite.  (Issuing it every step costs no device time either, but its ~40 us of host-side launch
     # work per step makes a 66 us step host-bound.)
-    reducers = [pdist.LossStatsReducer(dev) for _ in range(NSETS)] if world > 1 else None
+    side_stream = torch.cuda.Stream(dev) if world > 1 else None
+    reducers = [pdist.LossStatsReducer(dev, stream=side_stream) for _ in range(NSETS)] if world > 1 else None
 
     def run_step(i):
         if reducers is not None and reducers[i % NSETS].pending:
@@ -239,6 +252,27 @@ def run_gpu(args):
         if reducers is not None and i % REDUCE_EVERY == 0:
             reducers[i % NSETS].submit(outs[i % NSETS]["stats"])
 
+    def run_round(i):
+        """NSETS steps (i .. i+NSETS-1, i a multiple of NSETS) as one graph launch."""
+        if reducers is not None:
+            for r in reducers:
+                if r.pending:
+                    main_stream.wait_event(r.event)
+                    r.pending = False
+        round_graph.replay()
+        if reducers is not None and (i // NSETS) % max(1, REDUCE_EVERY // NSETS) == 0:
+            reducers[NSETS - 1].submit(outs[NSETS - 1]["stats"])
+
+    def run_steps(first, n):
+        i = first
+        while i < first + n:
+            if round_graph is not None and i % NSETS == 0 and i + NSETS <= first + n:
+                run_round(i)
+                i += NSETS
+            else:
+                run_step(i)
+                i += 1
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -250,13 +284,13 @@ def run_gpu(args):
     torch.cuda.synchronize()
     launches_per_step[0] = int(lib.plh_launch_count() - c0)
 
-    for i in range(args.warmup):
-        run_step(i)
+    run_steps(0, args.warmup)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        run_step(i)
+    host_t0 = time.perf_counter()
+    run_steps(0, args.steps)
+    host_us_per_step = (time.perf_counter() - host_t0) / args.steps * 1e6
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -427,6 +461,8 @@ def run_gpu(args):
                            NSETS, NSETS * (108 + 72) * PX / 1e6),
                        "cuda_graphs": graphs is not None,
                        "us_per_step_per_rank": [round(t / args.steps * 1e3, 2) for t in per_rank_ms],
+                       "host_enqueue_us_per_step": round(host_us_per_step, 2),
+                       "steps_per_graph_launch": NSETS if round_graph is not None else 1,
                        "collective": ("async NCCL all-reduce of 64 loss scalars every %d steps (the reference's reporting "
                                       "cadence, multigpu_train.py:179)" % REDUCE_EVERY) if world > 1 else "none"},
             "clocks": clocks,

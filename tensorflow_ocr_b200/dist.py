@@ -57,9 +57,11 @@ class LossStatsReducer(object):
     `event` can be waited on by a stream that is about to overwrite `stats`.
     """
 
-    def __init__(self, device, group=None):
+    def __init__(self, device, group=None, stream=None):
         self.group = group
-        self.stream = torch.cuda.Stream(device)
+        # several reducers can share one side stream (every extra CUDA stream competes for the device's
+        # few hardware work queues with the streams that carry the head's two branches)
+        self.stream = stream if stream is not None else torch.cuda.Stream(device)
         self.buf = torch.zeros(_lib.STATS_FLOATS, dtype=torch.float32, device=device)
         self.event = torch.cuda.Event()
         self.pending = False
