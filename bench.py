@@ -208,7 +208,7 @@ def run_gpu(args):
         step(i)
     torch.cuda.synchronize()
 
-    # ---- one CUDA graph per input set (the step is ~11 small launches on two branches)
+    # ---- one CUDA graph per input set (the step is 7 small launches on two branches)
     graphs = None
     if not args.no_graphs:
         graphs = []

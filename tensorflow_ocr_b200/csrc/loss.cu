@@ -3,19 +3,19 @@
 // Replaces nets/model.py:145-261, nets/model_vgg_16.py:227-282 and
 // nets/pixellink.py:88-263 of the reference.
 //
-// Pipeline (four launches on one stream, no host sync):
-//   K0 score_keys    all SMs: pixel softmax score -> 32-bit radix key per pixel
-//                    (4 B/px, stays in L2) + per-image n_pos / n_neg.  Reads 12 B/px.
-//   K1 ohem_select   one CTA per image: keys into REGISTERS, exact k-th smallest by
-//                    MSB-first bisection of the fp32 bit pattern (30 count rounds,
-//                    one __syncthreads each, no atomics).
-//   K2 ohem_counts   all SMs: selected mask M (1 B/px) + the 17 integer normalisers
-//                    (n_seg_pos, sum Wp[8], sum Wn[8]), which depend only on labels
-//                    and M.  Reads 37 B/px.
-//   K3 loss_main     all SMs, the HBM-bound pass: reads 108 B/px once, writes the
-//                    72 B/px of gradients once (normalisers are already known),
-//                    accumulates the 17 loss sums, last CTA finalises the scalars
-//                    in a fixed order (deterministic).
+// Pipeline at images <= 65536 px (two launches on one stream, no host sync):
+//   K1 ohem_select_cluster   a cluster of 8 CTAs per image: pixel softmax score -> 32-bit radix key
+//                    per pixel in REGISTERS, exact k-th smallest by MSB-first bisection of the fp32 bit
+//                    pattern (two bits per round, counts exchanged over distributed shared memory),
+//                    then the selected mask (1 B/px) and the 18 integer normalisers of the image from
+//                    link labels that TMA staged into shared memory during the rounds.
+//   K3 loss_main     all SMs, the HBM-bound pass: a producer warp streams the inputs through a
+//                    shared-memory ring with TMA bulk copies; reads 108 B/px once, writes the 72 B/px of
+//                    gradients once (normalisers are already known), accumulates the 17 loss sums, last
+//                    CTA finalises the scalars in a fixed order (deterministic).
+// General path (larger images, positives-only variant, or the split hint):
+//   K0 score_keys (keys to HBM, 4 B/px) -> ohem_select (one CTA per image) -> K2 ohem_counts (mask +
+//   normalisers by integer atomics) -> K3.
 // Algorithmic bytes: 180 B/px.
 #include <algorithm>
 #include <cmath>
