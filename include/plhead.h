@@ -104,7 +104,8 @@ typedef struct plh_loss_params {
  *  stats      [PLH_STATS_FLOATS + B] floats (required)
  *  grad_pix   [B,H,W,2]  / grad_link [B,H,W,16]: d loss / d logits for upstream
  *             gradient 1.0; both NULL = forward only; otherwise both required.
- *  ohem_mask  [B,H,W] uint8, optional: pixel_selected_mask (model.py:220).
+ *  ohem_mask  [B,H,W] uint8, optional, 16-byte aligned (the main pass fetches it with bulk copies):
+ *             pixel_selected_mask (model.py:220).
  *  decode_flags [B,H,W] uint16, optional: by-product for plh_decode_from_flags —
  *             bit d (0..7) = link_d score > link_thresh, bit 8 = pixel score >
  *             pixel_thresh (thresholds from `dp`, which may be NULL iff
