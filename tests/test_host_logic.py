@@ -192,3 +192,20 @@ def test_two_rank_gloo_sharding_and_scalar_allreduce():
     (_, l0, m0, n0, p0), (_, l1, m1, n1, p1) = res
     assert abs(m0 - (l0 + l1) / 2) < 1e-6 and abs(m1 - m0) < 1e-9
     assert n0 == p0 + p1 == n1
+
+
+def test_scheduling_hints_map_to_the_reserved_words():
+    """LossConfig / DecodeConfig -> plh_*_params.reserved[0] bits documented in include/plhead.h."""
+    import dataclasses
+    from tensorflow_ocr_b200 import head
+    assert head.LossConfig().c_struct().reserved[0] == 0
+    assert head.LossConfig(main_only=True).c_struct().reserved[0] == 1
+    assert head.LossConfig(split_counts=True).c_struct().reserved[0] == 2
+    assert head.LossConfig(chain_pdl=True, main_only=True).c_struct().reserved[0] == 5
+    d = head.DecodeConfig()
+    assert d.c_struct().reserved[0] == 0
+    assert dataclasses.replace(d, phase=4).c_struct().reserved[0] == 4
+    assert dataclasses.replace(d, phase=8).c_struct().reserved[0] == 8
+    hdr = open(os.path.join(ROOT, "include", "plhead.h")).read()
+    for word in ("bit 2: only the first kernel", "bit 3: everything after it", "Bit 1: scheduling hint", "Bit 2: scheduling hint"):
+        assert word in hdr, word
