@@ -183,12 +183,16 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     sampler.start()
 
-    # ---- synthetic inputs (family C), NSETS rotating sets, distinct per rank
+    # ---- synthetic inputs (family C), NSETS rotating sets.  Weak scaling = the work per GPU
+    # is fixed: every rank draws the SAME 32 synthetic images (in a rank-dependent order).  The step time is
+    # data dependent (number and size of components, selection rounds); with rank-specific images
+    # (first_image=rank*B) rank 1's set measured 6 us/step heavier than rank 0's on the same GPU, and the
+    # loss all-reduce then throttles every rank to the slowest one — that was the whole N>1 "overhead".
     keys = ("pix_logits", "link_logits", "pix_lab", "link_lab")
-    base = synth.make_batch(CONFIG_ID, B, H, W, "C", first_image=rank * B)
+    base = synth.make_batch(CONFIG_ID, B, H, W, "C", first_image=0)
     host_sets, dev_sets = [], []
     for s in range(NSETS):
-        hs = {k: torch.from_numpy(np.ascontiguousarray(np.roll(base[k], s, axis=0))).pin_memory() for k in keys}
+        hs = {k: torch.from_numpy(np.ascontiguousarray(np.roll(base[k], s + rank, axis=0))).pin_memory() for k in keys}
         host_sets.append(hs)
         dev_sets.append({k: v.to(dev) for k, v in hs.items()})
     outs = [{} for _ in range(NSETS)]
@@ -460,6 +464,8 @@ def run_gpu(args):
                        "parallelism": "batch shards, dp%d" % world,
                        "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2" % (
                            NSETS, NSETS * (108 + 72) * PX / 1e6),
+                       "data_per_rank": "the same 32 synthetic images on every rank, order rolled by rank "
+                                        "(weak scaling: fixed work per GPU)",
                        "cuda_graphs": graphs is not None,
                        "us_per_step_per_rank": [round(t / args.steps * 1e3, 2) for t in per_rank_ms],
                        "host_enqueue_us_per_step": round(host_us_per_step, 2),

@@ -5,7 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tensorflow_ocr_b200 import head, synth, _lib
 B, H, W, NS = 32, 128, 128, 6
-dev = torch.device("cuda", 0)
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if os.environ.get("SWEEP_PG"):   # diagnostic: does an initialised process group change the device time?
+    import torch.distributed as dist
+    dist.init_process_group(os.environ["SWEEP_PG"])
+    dist.barrier()
 lib = _lib.load()
 base = synth.make_batch(2, B, H, W, "C")
 sets = []
