@@ -7,7 +7,8 @@ import torch
 
 from .. import head
 
-__all__ = ["pixel_detect", "tf_pixel_detect", "generate_rbox", "tf_pixellink_get_rbox", "link_labels_from_ids"]
+__all__ = ["pixel_detect", "tf_pixel_detect", "generate_rbox", "tf_pixellink_get_rbox", "link_labels_from_ids",
+           "rasterize_polygons"]
 
 
 def pixel_detect(score_map, geo_map, score_map_thresh=0.8, link_thresh=0.8):
@@ -45,34 +46,39 @@ def link_labels_from_ids(poly_mask):
     return link.cpu().numpy() if np_in else link
 
 
+def rasterize_polygons(h, w, xs, ys):
+    """Host part of generate_rbox (tool/pixellink_fn.py:60-79): fill every polygon at full resolution —
+    1.0 into the score map, its 1-based index into the id map — then nearest-neighbour resize both to
+    (w//4, h//4).  Same OpenCV calls and the same float32 -> int32 truncation of the vertex coordinates as
+    the reference; a handful of polygons per image, so this stays on the host."""
+    import cv2
+    h, w = int(h), int(w)
+    full_score = np.zeros((h, w), dtype=np.float32)
+    full_ids = np.zeros((h, w), dtype=np.uint8)
+    vx = np.asarray(xs, dtype=np.float32) * w      # float32 products, like xs[idx, :] * w
+    vy = np.asarray(ys, dtype=np.float32) * h
+    vertices = np.stack([vx, vy], axis=-1).astype(np.int32)   # [n, 4, 2]
+    for number, quad in enumerate(vertices, start=1):
+        cv2.fillPoly(full_score, quad[None], 1.0)
+        cv2.fillPoly(full_ids, quad[None], number)
+    small = (w // 4, h // 4)                        # Python-2 integer division in the reference (:56-57)
+    return (cv2.resize(full_score, small, interpolation=cv2.INTER_NEAREST),
+            cv2.resize(full_ids, small, interpolation=cv2.INTER_NEAREST))
+
+
 def generate_rbox(h, w, xs, ys, bboxes, ignored):
     """tool/pixellink_fn.py:53-111.  Same arguments and returns (res_score_map [h/4,w/4] fp32,
     res_link_map [h/4,w/4,8] fp32, show_bboxes [200,4] fp32) as numpy arrays.
 
-    The polygon rasterisation and the nearest-neighbour resize stay on the host with the same OpenCV
-    calls as the reference (:72-79, a few polygons per image); the per-pixel link-label loop — the part
-    that is O(pixels x 8) interpreted Python in the reference — runs on the GPU."""
-    import cv2
+    The polygon rasterisation stays on the host (`rasterize_polygons`); the per-pixel link-label loop —
+    O(pixels x 8) interpreted Python in the reference — runs on the GPU (`plh_link_labels`)."""
     if len(xs) != len(ignored):
         raise AssertionError("the length of xs and ignored must be the same, but got %s and %s" % (len(xs), len(ignored)))
-    h, w = int(h), int(w)
-    new_h, new_w = h // 4, w // 4          # Python-2 integer division in the reference (:56-57)
-    score_map = np.zeros((h, w), dtype=np.float32)
-    poly_mask = np.zeros((h, w), dtype=np.uint8)
-    show_bboxes = np.zeros((200, 4), dtype=np.float32)
-    xs = np.asarray(xs, dtype=np.float32)
-    ys = np.asarray(ys, dtype=np.float32)
-    bboxes = np.asarray(bboxes)
-    for idx in range(xs.shape[0]):
-        points = list(zip(xs[idx, :] * w, ys[idx, :] * h))
-        show_bboxes[idx, :] = bboxes[idx, :]
-        draw_poly = np.array([points], np.int32)
-        cv2.fillPoly(score_map, draw_poly, 1.0)
-        cv2.fillPoly(poly_mask, draw_poly, idx + 1)
-    res_score_map = cv2.resize(score_map, (new_w, new_h), interpolation=cv2.INTER_NEAREST)
-    poly_mask = cv2.resize(poly_mask, (new_w, new_h), interpolation=cv2.INTER_NEAREST)
-    res_link_map = link_labels_from_ids(poly_mask)
-    return res_score_map, res_link_map, show_bboxes
+    n = len(xs)
+    show_bboxes = np.zeros((200, 4), dtype=np.float32)   # fixed 200 rows (:65)
+    show_bboxes[:n] = np.asarray(bboxes)[:n]
+    res_score_map, ids = rasterize_polygons(h, w, xs, ys)
+    return res_score_map, link_labels_from_ids(ids), show_bboxes
 
 
 def tf_pixellink_get_rbox(img_size, xs, ys, bboxes, ignored):
