@@ -18,6 +18,19 @@
  *    error (PLH_E_*); positive = cudaError_t from a launch.  Nothing throws.
  *  - Outputs are written in full (never accumulated into).
  *  - NaN produced by empty link classes is DATA, not an error (nets/model.py:252-253).
+ *
+ * Numerical contract (what tests/ assert against the reference-executed goldens and the oracle)
+ *  - Decisions are bit-exact: OHEM masks, integer normalisers, threshold flags, component labels
+ *    (minimum pixel index), integer box corners, restore_rectangle's row order.
+ *  - Loss scalars: |a - b| <= 1e-5 * |b|.
+ *  - Gradients, ELEMENTWISE: |a - b| <= 1e-5 * |b| + 4 * 2^-24 * w, where w is that element's weight
+ *    (gradient = w * (softmax - onehot); w = 2*M/n_seg_pos for pixel logits, M*(1/sum_Wp or 1/sum_Wn) for
+ *    link logits).  The absolute term is the fp32 rounding of `softmax - onehot` that the reference itself
+ *    (TF autodiff) carries on saturated pixels; the kernels evaluate the same quantity as a sigmoid of the
+ *    logit difference, which has no cancellation.  tests/util.py:grad_close states this check; the
+ *    max-norm check |a - b|_inf <= 1e-5 * |b|_inf (tests/util.py:rel_err) is asserted as well.
+ *  - One host thread per device at a time per (stream, workspace); several devices may be driven from one
+ *    process (kernel attributes are set per device).
  */
 #ifndef PLHEAD_H_
 #define PLHEAD_H_
@@ -225,6 +238,13 @@ PLH_API int plh_pixel_detect(const float* score, const float* link, int H, int W
  */
 PLH_API int plh_restore_rectangle(const float* origin, const float* geometry, int N, double* out, int32_t* out_index,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* Same with either input in float64 (numpy computes the distance sums and cos/sin in geometry's dtype and the
+ * rest in float64; a float64 origin enters the final translation only).  fp32/fp32 is bit-exact against
+ * numpy; with a float64 geometry the device cos/sin may differ from the host libm in the last bit. */
+PLH_API int plh_restore_rectangle_ex(const void* origin, int origin_is_f64, const void* geometry, int geometry_is_f64,
+                             int N, double* out, int32_t* out_index, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 
 /*
  * EAST RBOX loss fwd+bwd — NOT in the reference; restated

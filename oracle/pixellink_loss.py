@@ -204,6 +204,7 @@ def loss_model(y_true_pixel, y_pred_pixel, y_true_link, y_pred_link, training_ma
     link_pred = yl.reshape(B, N, 8, 2)
     link_lab = np.asarray(y_true_link, f32).reshape(B, N, 8).astype(np.int32)     # :242
     grad_link = np.zeros((B, N, 8, 2), f32)
+    w_link = np.zeros((B, N, 8), f32)
     L_link = np.zeros(8, f32)
     sum_wp = np.zeros(8, f32)
     sum_wn = np.zeros(8, f32)
@@ -225,6 +226,7 @@ def loss_model(y_true_pixel, y_pred_pixel, y_true_link, y_pred_link, training_ma
             gl1 = (w * g1).astype(f32)
         grad_link[:, :, d, 1] = gl1
         grad_link[:, :, d, 0] = -gl1
+        w_link[:, :, d] = w
     with np.errstate(invalid="ignore"):
         link_total = f32(np.sum(L_link.astype(np.float64)))                        # :256
         total = f32(link_total + f32(2) * L_pix)                                   # :261
@@ -232,7 +234,11 @@ def loss_model(y_true_pixel, y_pred_pixel, y_true_link, y_pred_link, training_ma
                 n_seg_pos=n_seg_pos, sum_wp=sum_wp, sum_wn=sum_wn,
                 s_pix=s_pix, s_pos=s_pos, s_neg=s_neg, thr=thr,
                 ohem_mask=M.reshape(yp.shape[:-1]).astype(f32),
-                grad_pixel=grad_pixel, grad_link=grad_link.reshape(yl.shape))
+                grad_pixel=grad_pixel, grad_link=grad_link.reshape(yl.shape),
+                # per-element gradient weights (gradient = weight * (softmax - onehot)): the scale the
+                # elementwise tolerance of tests/util.py:grad_close is stated against
+                w_pixel=(M * pix_scale).astype(f32).reshape(yp.shape[:-1]),
+                w_link=w_link.reshape(yl.shape[:-1] + (8,)))
 
 
 def ohem_loss_vgg16(y_true_pixel, y_pred_pixel, y_true_link, y_pred_link, training_mask=None):

@@ -47,6 +47,7 @@ SIGNATURES = {
     "plh_min_area_boxes": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "plh_pixel_detect": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     "plh_restore_rectangle": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "plh_restore_rectangle_ex": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "plh_east_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _sz, _vp]),
     "plh_lanms": (_i, [_vp, _vp, _i, _i, C.c_double, _vp, _vp, _vp, _sz, _vp]),
     "plh_link_labels": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -251,13 +251,14 @@ east_grad_kernel(const float* __restrict__ sg, const float* __restrict__ gg, con
 // a stable partition, done with a block-count / scan / scatter triple.
 constexpr int kRRBlock = 1024;
 
+template <typename TG>
 __global__ void __launch_bounds__(kRRBlock)
-rr_count_kernel(const float* __restrict__ geometry, int N, int* __restrict__ blockcnt) {
+rr_count_kernel(const TG* __restrict__ geometry, int N, int* __restrict__ blockcnt) {
   __shared__ int s_c;
   if (threadIdx.x == 0) s_c = 0;
   __syncthreads();
   const int i = blockIdx.x * kRRBlock + threadIdx.x;
-  const bool nn = i < N && geometry[(size_t)i * 5 + 4] >= 0.f;
+  const bool nn = i < N && geometry[(size_t)i * 5 + 4] >= (TG)0;
   const unsigned m = __ballot_sync(0xffffffffu, nn);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_c, __popc(m));
   __syncthreads();
@@ -302,20 +303,28 @@ __global__ void __launch_bounds__(1024) rr_scan_kernel(int* __restrict__ blockcn
   if (tid == 0) *total = s_base;
 }
 
+// TG / TO: dtype of geometry / origin.  numpy computes the distance sums and cos / sin in geometry's dtype,
+// everything else in float64 (np.zeros is float64); a float64 origin only enters the final translation.
+__device__ __forceinline__ double rr_cos(float a) { return (double)(float)cos((double)a); }
+__device__ __forceinline__ double rr_cos(double a) { return cos(a); }
+__device__ __forceinline__ double rr_sin(float a) { return (double)(float)sin((double)a); }
+__device__ __forceinline__ double rr_sin(double a) { return sin(a); }
+
+template <typename TG, typename TO>
 __global__ void __launch_bounds__(kRRBlock)
-rr_scatter_kernel(const float* __restrict__ origin, const float* __restrict__ geometry, int N,
+rr_scatter_kernel(const TO* __restrict__ origin, const TG* __restrict__ geometry, int N,
                   const int* __restrict__ blockoff, const int* __restrict__ total_nn, double* __restrict__ out,
                   int32_t* __restrict__ out_index) {
   __shared__ int s_w[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = blockIdx.x * kRRBlock + tid;
   const bool valid = i < N;
-  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, th = -1.f;
+  TG d0 = 0, d1 = 0, d2 = 0, d3 = 0, th = -1;
   if (valid) {
-    const float* g = geometry + (size_t)i * 5;
+    const TG* g = geometry + (size_t)i * 5;
     d0 = g[0], d1 = g[1], d2 = g[2], d3 = g[3], th = g[4];
   }
-  const bool nn = valid && th >= 0.f;
+  const bool nn = valid && th >= (TG)0;
   const unsigned m = __ballot_sync(0xffffffffu, nn);
   if (lane == 0) s_w[warp] = __popc(m);
   __syncthreads();
@@ -333,23 +342,23 @@ rr_scatter_kernel(const float* __restrict__ origin, const float* __restrict__ ge
   if (!valid) return;
   const int nn_before = blockoff[blockIdx.x] + s_w[warp] + __popc(m & ((1u << lane) - 1u));
   const int row = nn ? nn_before : *total_nn + (i - nn_before);
-  // fp32 sums of the distances (numpy fp32 arithmetic), fp32 cos/sin of the fp32 angle,
+  // sums of the distances and cos/sin of the angle in geometry's dtype (numpy arithmetic of that dtype),
   // products and sums in fp64 (numpy upcasts: np.zeros is float64), icdar.py:417-443 / :450-476
-  const float hh = -d0 - d2;
+  const TG hh = -d0 - d2;
   double px[5], py[5];
   double c, s_;
   if (nn) {
-    const float ww = d1 + d3;
+    const TG ww = d1 + d3;
     px[0] = 0.0, py[0] = hh; px[1] = ww, py[1] = hh; px[2] = ww, py[2] = 0.0; px[3] = 0.0, py[3] = 0.0;
     px[4] = d3, py[4] = -d2;
-    c = (double)(float)cos((double)th), s_ = (double)(float)sin((double)th);
+    c = rr_cos(th), s_ = rr_sin(th);
     // rotate_matrix_x = [cos, sin], rotate_matrix_y = [-sin, cos]
   } else {
-    const float ww = -d1 - d3;
+    const TG ww = -d1 - d3;
     px[0] = ww, py[0] = hh; px[1] = 0.0, py[1] = hh; px[2] = 0.0, py[2] = 0.0; px[3] = ww, py[3] = 0.0;
     px[4] = -d1, py[4] = -d2;
-    const float nth = -th;
-    c = (double)(float)cos((double)nth), s_ = -(double)(float)sin((double)nth);
+    const TG nth = -th;
+    c = rr_cos(nth), s_ = -rr_sin(nth);
     // rotate_matrix_x = [cos(-a), -sin(-a)], rotate_matrix_y = [sin(-a), cos(-a)]
   }
   double rx[5], ry[5];
@@ -449,23 +458,41 @@ extern "C" int plh_east_loss(const float* score_gt, const float* score_pred, con
   return rc;
 }
 
-extern "C" int plh_restore_rectangle(const float* origin, const float* geometry, int N, double* out,
-                                     int32_t* out_index, void* workspace, size_t workspace_bytes, void* stream) {
-  if (N == 0) return PLH_OK;
-  if (!origin || !geometry || !out) return PLH_E_NULL;
-  if (N < 0) return PLH_E_SHAPE;
+template <typename TG, typename TO>
+static int restore_rectangle_impl(const TO* origin, const TG* geometry, int N, double* out, int32_t* out_index,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t s) {
   const int nb = (N + kRRBlock - 1) / kRRBlock;
   if (!workspace || workspace_bytes < (size_t)(nb + 1) * 4 + 256) return PLH_E_WORKSPACE;
   int* blockcnt = (int*)workspace;
   int* total = blockcnt + nb;
-  cudaStream_t s = (cudaStream_t)stream;
-  rr_count_kernel<<<nb, kRRBlock, 0, s>>>(geometry, N, blockcnt);
+  rr_count_kernel<TG><<<nb, kRRBlock, 0, s>>>(geometry, N, blockcnt);
   int rc = launch_status();
   if (rc) return rc;
   rr_scan_kernel<<<1, 1024, 0, s>>>(blockcnt, nb, total);
   if ((rc = launch_status())) return rc;
-  rr_scatter_kernel<<<nb, kRRBlock, 0, s>>>(origin, geometry, N, blockcnt, total, out, out_index);
+  rr_scatter_kernel<TG, TO><<<nb, kRRBlock, 0, s>>>(origin, geometry, N, blockcnt, total, out, out_index);
   return launch_status();
+}
+
+extern "C" int plh_restore_rectangle_ex(const void* origin, int origin_is_f64, const void* geometry, int geometry_is_f64,
+                                        int N, double* out, int32_t* out_index, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (N == 0) return PLH_OK;
+  if (!origin || !geometry || !out) return PLH_E_NULL;
+  if (N < 0) return PLH_E_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (geometry_is_f64 && origin_is_f64)
+    return restore_rectangle_impl((const double*)origin, (const double*)geometry, N, out, out_index, workspace, workspace_bytes, s);
+  if (geometry_is_f64)
+    return restore_rectangle_impl((const float*)origin, (const double*)geometry, N, out, out_index, workspace, workspace_bytes, s);
+  if (origin_is_f64)
+    return restore_rectangle_impl((const double*)origin, (const float*)geometry, N, out, out_index, workspace, workspace_bytes, s);
+  return restore_rectangle_impl((const float*)origin, (const float*)geometry, N, out, out_index, workspace, workspace_bytes, s);
+}
+
+extern "C" int plh_restore_rectangle(const float* origin, const float* geometry, int N, double* out,
+                                     int32_t* out_index, void* workspace, size_t workspace_bytes, void* stream) {
+  return plh_restore_rectangle_ex(origin, 0, geometry, 0, N, out, out_index, workspace, workspace_bytes, stream);
 }
 
 extern "C" int plh_link_labels(const uint8_t* ids, int B, int H, int W, float* link_lab, float* pix_lab, void* stream) {

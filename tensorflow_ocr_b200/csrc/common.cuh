@@ -92,6 +92,27 @@ __device__ __forceinline__ void pdl_wait_and_release() {
 __device__ __forceinline__ void pdl_wait() { cudaGridDependencySynchronize(); }
 __device__ __forceinline__ void pdl_release() { cudaTriggerProgrammaticLaunchCompletion(); }
 
+// Dynamic shared memory above 48 KB is an opt-in per (kernel, DEVICE): one process may drive several
+// devices (one host thread each), so the bookkeeping is per device, not per process.  `state` is one
+// static object per launch site; the largest size granted so far is remembered per device.
+struct SmemOptIn {
+  std::atomic<int> granted[64];
+  SmemOptIn() { for (auto& g : granted) g.store(0, std::memory_order_relaxed); }
+};
+template <typename K>
+inline int ensure_dynamic_smem(SmemOptIn& state, K kern, size_t bytes) {
+  if (bytes <= 48 * 1024) return PLH_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && state.granted[dev].load(std::memory_order_acquire) >= (int)bytes) return PLH_OK;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);  // idempotent; benign if raced
+  if (e != cudaSuccess) return (int)e;
+  if (tracked) state.granted[dev].store((int)bytes, std::memory_order_release);
+  return PLH_OK;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -562,6 +562,14 @@ min_area_boxes_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict
   RectSmem S = rect_carve(smem, npad);
   const int s = blockIdx.x;
   const int o0 = offsets[s], total = offsets[s + 1] - o0;
+  if (total > npad) {  // more points than the shared-memory carve holds: sentinel box, no out-of-bounds write
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 8; ++i) boxes[(size_t)s * 8 + i] = INT32_MIN;
+      if (rects)
+        for (int i = 0; i < 5; ++i) rects[(size_t)s * 5 + i] = __int_as_float(0x7fc00000);
+    }
+    return;
+  }
   int nsort = 32;
   while (nsort < total) nsort <<= 1;
   for (int i = threadIdx.x; i < nsort; i += blockDim.x)
@@ -653,12 +661,8 @@ rects:
   {
     const int npad = next_pow2(std::max(2 * H, 32));
     const size_t smem = rect_smem_bytes(npad);
-    static size_t attr_bytes = 0;
-    if (smem > 48 * 1024 && smem > attr_bytes) {
-      cudaError_t e = cudaFuncSetAttribute(decode_rects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      attr_bytes = smem;
-    }
+    static SmemOptIn optin;
+    if ((rc = ensure_dynamic_smem(optin, decode_rects_kernel, smem))) return rc;
     const int rect_grid = (int)std::min<long long>((long long)B * K, kNumSMs * 8);
     rc = launch(decode_rects_kernel, rect_grid, 256, smem, s, n_boxes, comp_root, comp_size, nrec, recs, B, H, W, K,
                                                       p->scale_x, p->scale_y, npad, boxes, rects, comp);
@@ -710,12 +714,8 @@ extern "C" int plh_min_area_boxes(const int32_t* pts, const int32_t* offsets, in
   if (n_sets <= 0) return PLH_E_SHAPE;
   const int npad = 2048;  // max points per set
   const size_t smem = rect_smem_bytes(npad);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(min_area_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(optin, min_area_boxes_kernel, smem)) return rc;
   min_area_boxes_kernel<<<n_sets, 256, smem, (cudaStream_t)stream>>>(pts, offsets, npad, boxes, rects);
   return launch_status();
 }

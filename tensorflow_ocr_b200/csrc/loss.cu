@@ -1067,12 +1067,8 @@ float prob_to_logit_threshold(float t) {
 template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
 static int launch_main_one(int grid, cudaStream_t s, const MainArgs& a, int B, int N) {
   auto kern = loss_main_kernel<VARIANT, TERM, GRAD, FLAGS>;
-  static bool attr_set = false;  // idempotent; benign if raced
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMainSmem);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(optin, kern, kMainSmem)) return rc;
   return launch(kern, grid, kMainBlock, kMainSmem, s, a, B, N);
 }
 
@@ -1102,12 +1098,8 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
     auto kern = fused ? ohem_select_cluster_kernel<KEYMODE, FROM_SCORES, KPT, !FROM_SCORES>                      \
                       : ohem_select_cluster_kernel<KEYMODE, FROM_SCORES, KPT, false>;                            \
     const size_t smem = fused ? (size_t)(KPT < 8 ? KPT : 8) * kClThreads * 32 : 0;                               \
-    static bool attr_set = false; /* idempotent; benign if raced */                                              \
-    if (smem > 48 * 1024 && !attr_set) {                                                                         \
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-      if (e != cudaSuccess) return (int)e;                                                                       \
-      attr_set = true;                                                                                           \
-    }                                                                                                            \
+    static SmemOptIn optin; /* only the fused kernel asks for more than 48 KB */                               \
+    if ((rc = ensure_dynamic_smem(optin, kern, smem))) return rc;                                                \
     /* first kernel of the chain: plain stream order unless the caller vouches for the predecessor (its CTAs   \
        parked under a foreign kernel only get in that kernel's way) */                                        \
     rc = head_pdl ? launch(kern, B * kClusterSize, kClThreads, smem, s, pix_logits, pix_lab, link_lab, scores, pos, neg, \
@@ -1127,13 +1119,8 @@ static int launch_keys_and_select(const float* pix_logits, const float* pix_lab,
               scores, pos, neg, N, keys, counts);
   if (rc) return rc;
   const bool use_smem = (size_t)N * 4 <= kSmemKeysMaxBytes;
-  static bool attr_set = false;  // idempotent; benign if raced
-  if (use_smem && !attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ohem_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemKeysMaxBytes);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  if (use_smem && (rc = ensure_dynamic_smem(optin, ohem_select_kernel, kSmemKeysMaxBytes))) return rc;
   return launch(ohem_select_kernel, B, kSelectThreads, use_smem ? (size_t)N * 4 : 0, s, keys, counts, per_image,
                 n_pos_override, N, ratio, KEYMODE, use_smem ? 1 : 0, info, thr_out, hdr);
 }

@@ -26,6 +26,13 @@ def decode_pixellink(pixel_logits, link_logits, pixel_thresh=0.8, link_thresh=0.
              ascending label order (np.int0(cv2.boxPoints(cv2.minAreaRect(pts))))
       counts list of B int32 arrays [n_b]: pixel count of each component
     numpy in -> numpy out; CUDA tensors in -> CUDA tensors (one sync to read n_boxes).
+
+    Deviation from the script (quirk Q10): the reference groups pixels by a DIRECTED depth-first search whose
+    result depends on Python-2 dict order when link decisions are asymmetric; this function returns the
+    weakly-connected components of the same edge set.  Identical whenever link decisions are symmetric
+    (tests/golden/link_graph.npz pins that against the script's own lines); with asymmetric links every
+    group of the script lies inside one component returned here, i.e. components are never split, only
+    merged (tests/test_gpu_decode.py::test_decode_asymmetric_links_vs_literal_dfs quantifies it).
     """
     pl, np_in = head.to_device(pixel_logits)
     ll, _ = head.to_device(link_logits, device=pl.device)

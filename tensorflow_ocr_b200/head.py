@@ -87,22 +87,30 @@ def to_device(x, dtype=torch.float32, device=None):
     return t.contiguous(), False
 
 
-_ws_cache = {}
+_ws_cache = {}      # key -> [tensor, pinned]; insertion order = age
+_WS_CACHE_MAX = 64
 
 
 def _workspace(op: int, B: int, H: int, W: int, K: int, device: torch.device) -> torch.Tensor:
-    """Caller-owned workspace, cached per (device, stream, op, shape): the library keeps no state."""
+    """Caller-owned workspace, cached per (device, stream, op, shape): the library keeps no state.
+
+    A workspace handed out while the stream is being captured into a CUDA graph is baked into that graph
+    and is therefore pinned for the life of the process; only unpinned entries are ever evicted (oldest
+    first), so a replayed graph never points at freed memory."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream, op, B, H, W, K)
-    ws = _ws_cache.get(key)
-    if ws is None:
+    capturing = torch.cuda.is_current_stream_capturing()
+    ent = _ws_cache.get(key)
+    if ent is None:
         n = _lib.load().plh_workspace_bytes(op, B, H, W, K)
         if n == 0:
             raise ValueError("bad shape for workspace query: op=%d B=%d H=%d W=%d" % (op, B, H, W))
-        ws = torch.empty(n, dtype=torch.uint8, device=device)
-        if len(_ws_cache) > 64:
-            _ws_cache.clear()
-        _ws_cache[key] = ws
-    return ws
+        if len(_ws_cache) >= _WS_CACHE_MAX:
+            for k in [k for k, e in _ws_cache.items() if not e[1]][: len(_ws_cache) - _WS_CACHE_MAX + 1]:
+                del _ws_cache[k]
+        ent = _ws_cache[key] = [torch.empty(n, dtype=torch.uint8, device=device), capturing]
+    elif capturing:
+        ent[1] = True
+    return ent[0]
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -417,9 +425,13 @@ def lanms_raw(polys: torch.Tensor, offsets: torch.Tensor, thres: float = 0.3):
 
 
 def restore_rectangle_raw(origin, geometry, want_index=False):
+    """plh_restore_rectangle_ex: origin [N,2], geometry [N,5], each float32 or float64 (CUDA) -> [N,4,2] float64."""
     lib = _lib.load()
     dev = origin.device
     _require_gpu(dev)
+    for t in (origin, geometry):
+        if t.dtype not in (torch.float32, torch.float64):
+            raise TypeError("restore_rectangle takes float32 / float64 tensors, got %s" % t.dtype)
     N = origin.shape[0]
     outp = torch.empty((N, 4, 2), dtype=torch.float64, device=dev)
     idx = torch.empty((N,), dtype=torch.int32, device=dev) if want_index else None
@@ -427,7 +439,8 @@ def restore_rectangle_raw(origin, geometry, want_index=False):
         return outp, idx
     ws = torch.empty((N // 1024 + 2) * 4 + 256, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.plh_restore_rectangle(_p(origin), _p(geometry), N, _p(outp), _p(idx), _p(ws), ws.numel(),
-                                       _stream(dev))
-    _lib.check(rc, "plh_restore_rectangle")
+        rc = lib.plh_restore_rectangle_ex(_p(origin), int(origin.dtype == torch.float64), _p(geometry),
+                                          int(geometry.dtype == torch.float64), N, _p(outp), _p(idx), _p(ws),
+                                          ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_restore_rectangle_ex")
     return outp, idx

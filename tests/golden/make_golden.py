@@ -287,13 +287,151 @@ def golden_generate_rbox():
     save("generate_rbox", n_cases=3, **cases)
 
 
+# ----------------------------------------------------------------------------- D2/D3: link graph + DFS + boxes
+def cut_lines(path, lo, hi):
+    """Lines lo..hi (1-based, inclusive) of a reference file, dedented."""
+    lines = open(os.path.join(REF, path)).read().split("\n")
+    return textwrap.dedent("\n".join(lines[lo - 1:hi]))
+
+
+def _py3(src):
+    """The only edits made to the inline decode blocks: Python-2 `print x` statements dropped, dict.has_key ->
+    `in`, and np.int0 (removed in numpy 2) -> np.intp.  Returns (patched source, number of edits)."""
+    n = 0
+    out = []
+    for l in src.split("\n"):
+        if re.match(r"^\s*print\s+[^(]", l):
+            l = l[: len(l) - len(l.lstrip())] + "pass"
+            n += 1
+        if "graph.has_key(v)" in l:
+            l = l.replace("graph.has_key(v)", "(v in graph)")
+            n += 1
+        if "np.int0(" in l:
+            l = l.replace("np.int0(", "np.intp(")
+            n += 1
+        out.append(l)
+    return "\n".join(out), n
+
+
+def _symmetric_flag_maps(seed, H, W, rects, min_side=3):
+    """P [H,W] bool, L [H,W,8] bool with symmetric link decisions (L[v,d] == L[u,opp(d)]) and no positive on
+    the map border: on such maps the reference's directed, seed-order dependent DFS is order independent
+    (quirk Q10), so its Python-3 execution is THE reference result."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    P = np.zeros((H, W), np.uint8)
+    keep = np.zeros((H, W), np.float32)          # per-pixel edge survival probability
+    for (cx, cy, lw, lh, ang, p_edge) in rects:
+        c, s = np.cos(ang), np.sin(ang)
+        pts = (np.array([[-lw, -lh], [lw, -lh], [lw, lh], [-lw, lh]]) / 2.0) @ np.array([[c, -s], [s, c]]).T + (cx, cy)
+        m = np.zeros((H, W), np.uint8)
+        cv2.fillPoly(m, [np.round(pts).astype(np.int32)], 1)
+        P |= m
+        keep[m > 0] = p_edge
+    P[0, :] = P[-1, :] = 0
+    P[:, 0] = P[:, -1] = 0
+    P = P.astype(bool)
+    P &= rng.uniform(size=(H, W)) > 0.03         # pinholes
+    L = np.zeros((H, W, 8), bool)
+    for d in (3, 4, 5, 7):                       # each undirected pair once
+        dy, dx = synth.NEIGHBOURS[d]
+        o = synth.OPPOSITE[d]
+        on = rng.uniform(size=(H, W)) < keep
+        ys, xs = np.nonzero(on)
+        ok = (ys + dy >= 0) & (ys + dy < H) & (xs + dx >= 0) & (xs + dx < W)
+        ys, xs = ys[ok], xs[ok]
+        L[ys, xs, d] = True
+        L[ys + dy, xs + dx, o] = True
+    # link decisions of background pixels are arbitrary (the graph never reads them): noise
+    # (kept to a 2-pixel band around the text so that the packed fixture stays small)
+    band = cv2.dilate(P.astype(np.uint8), np.ones((5, 5), np.uint8)).astype(bool) & ~P
+    L |= band[:, :, None] & (rng.uniform(size=(H, W, 8)) < 0.3)
+    return P, L
+
+
+def _run_inline_decode(path, spans, H, W, P, L, hi_score, lo_score, flags):
+    """exec the inline decode block of a reference script on score maps built from (P, L)."""
+    import cv2
+    src = "\n".join(cut_lines(path, lo, hi) for lo, hi in spans)
+    src, nedit = _py3(src)
+    assert ("%d" % W) in src and ("%d" % H) in src, "map-size literals of the script"
+    pixel_score = np.where(P, hi_score, lo_score).astype(np.float32)
+    ns = dict(np=np, cv2=cv2, FLAGS=flags, pixel_score=pixel_score,
+              link_score_set=[np.where(L[:, :, d], hi_score, lo_score).astype(np.float32) for d in range(8)],
+              im_ori=np.zeros((8, 8, 3), np.uint8), boxes=[])
+    exec(src, ns)
+    assert np.array_equal(ns["pixel_seg"], P)
+    return ns, nedit
+
+
+def golden_link_graph():
+    """test_pixellink_fast.py:111,115-178,191-202 (192x320 maps, > 10 px, scale 4.0 / 3.75) and
+    test_pixellink.py:113,117-181,206-217 (720x1280, > 200 px, unscaled), executed by line range."""
+    flags = types.SimpleNamespace(pixel_conf_threshold=0.8, link_conf_threshold=0.9)
+    out = {}
+    # ---- 4s script
+    H, W = 192, 320
+    rng = np.random.default_rng(5)
+    rects = []
+    for i in range(14):
+        rects.append((rng.uniform(20, W - 20), rng.uniform(15, H - 15), rng.uniform(8, 70), rng.uniform(2, 12),
+                      rng.uniform(-0.8, 0.8), [1.0, 0.7, 0.45, 0.3][i % 4]))
+    P, L = _symmetric_flag_maps(41, H, W, rects)
+    ns, nedit = _run_inline_decode("test_pixellink_fast.py", [(111, 111), (115, 178), (191, 202)], H, W, P, L,
+                                   0.95, 0.05, flags)
+    print("test_pixellink_fast.py inline decode: %d groups, %d py3 edits" % (ns["gid"] - 1, nedit))
+    out.update(_pack_case("fast", H, W, P, L, ns, 10, (1280.0 / 320, 720.0 / 192)))
+    # the ICDAR result-file format, test_pixellink_fast.py:209-217, written by the script's own lines
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        ns["FLAGS"].output_dir = td
+        ns["image_name"] = "/some/dir/img_7.jpg"
+        ns["os"] = os
+        exec(_py3(cut_lines("test_pixellink_fast.py", 209, 217))[0], ns)
+        out["fast_res_txt"] = np.frombuffer(open(os.path.join(td, "res_img_7.txt"), "rb").read(), np.uint8)
+    # ---- full-resolution script (small components only: its DFS is quadratic in the component size)
+    H, W = 720, 1280
+    rng = np.random.default_rng(6)
+    rects = []
+    for i in range(12):
+        rects.append((rng.uniform(60, W - 60), rng.uniform(40, H - 40), rng.uniform(20, 110), rng.uniform(4, 22),
+                      rng.uniform(-0.8, 0.8), [1.0, 0.6, 0.4][i % 3]))
+    P, L = _symmetric_flag_maps(42, H, W, rects)
+    ns, nedit = _run_inline_decode("test_pixellink.py", [(113, 113), (117, 181), (206, 217)], H, W, P, L,
+                                   0.95 * 255, 0.05 * 255, flags)
+    print("test_pixellink.py inline decode: %d groups, %d py3 edits" % (ns["gid"] - 1, nedit))
+    out.update(_pack_case("full", H, W, P, L, ns, 200, (1.0, 1.0)))
+    save("link_graph", **out)
+
+
+def _pack_case(tag, H, W, P, L, ns, min_size, scale):
+    """Canonicalise the script's result: gid g -> the group's minimum pixel index; boxes in ascending-label order."""
+    group = np.asarray(ns["group_idx"]).reshape(H, W)
+    gid = int(ns["gid"])
+    labels = np.full((H, W), -1, np.int32)
+    mins = []
+    for g in range(1, gid):
+        idx = np.flatnonzero(group.reshape(-1) == g)
+        mins.append(int(idx.min()))
+        labels.reshape(-1)[idx] = idx.min()
+    order = np.argsort(mins)
+    boxes = np.stack([np.asarray(ns["boxes"][i]) for i in order]).astype(np.int64) if mins else np.zeros((0, 4, 2), np.int64)
+    return {tag + "_H": H, tag + "_W": W, tag + "_P": np.packbits(P), tag + "_L": np.packbits(L),
+            tag + "_labels": labels, tag + "_boxes": boxes, tag + "_min_size": min_size,
+            tag + "_scale": np.asarray(scale, np.float64), tag + "_n_groups": gid - 1}
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    if len(sys.argv) > 1 and sys.argv[1] == "rbox":
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "rbox":
         golden_generate_rbox()
-        sys.exit(0)
-    golden_model_loss()
-    golden_vgg16()
-    golden_pixellink_build_loss()
-    golden_numpy_pieces()
-    golden_generate_rbox()
+    elif only == "link_graph":
+        golden_link_graph()
+    else:
+        golden_model_loss()
+        golden_vgg16()
+        golden_pixellink_build_loss()
+        golden_numpy_pieces()
+        golden_generate_rbox()
+        golden_link_graph()

@@ -90,6 +90,30 @@ def test_restore_rectangle(golden_dir, cuda_dev):
     assert np.allclose(icdar.restore_rectangle(origin, geom), ref, rtol=1e-6, atol=1e-4)
 
 
+@pytest.mark.parametrize("o64,g64", [(False, True), (True, False), (True, True)])
+def test_restore_rectangle_float64_inputs(golden_dir, o64, g64, cuda_dev):
+    """float64 inputs are computed in float64 like numpy does (not silently downcast): origins above 2^24 and a
+    float64 geometry keep their digits.  Checked against the reference function itself (executed on the float64
+    inputs by the oracle restatement, which numpy evaluates in the input dtype)."""
+    from oracle import east as E
+    from tensorflow_ocr_b200.datasets import icdar
+    rng = np.random.default_rng(4)
+    N = 3000
+    origin = rng.uniform(0, 5e7, (N, 2)).astype(np.float64 if o64 else np.float32)
+    geom = np.concatenate([rng.uniform(1, 80, (N, 4)), rng.uniform(-0.7, 0.7, (N, 1))], 1)
+    geom = geom.astype(np.float64 if g64 else np.float32)
+    ref = E.restore_rectangle_rbox(origin, geom)
+    out = icdar.restore_rectangle(origin, geom)
+    assert out.dtype == np.float64
+    if g64:      # fp64 trig: device libm vs host libm, last-bit differences only
+        assert np.allclose(out, ref, rtol=1e-13, atol=1e-9)
+    else:        # fp32 trig differs by an ulp between libms (same bound as the fp32 test above)
+        assert np.allclose(out, ref, rtol=1e-6, atol=1e-4)
+    if o64:      # the origin's low digits survive: a float32 round trip of the origin would be off by > 1
+        bad = icdar.restore_rectangle(origin.astype(np.float32), geom)
+        assert np.abs(bad - ref).max() > 0.5 and np.abs(out - ref).max() < 1e-3
+
+
 def _east_boxes(rng, n_groups, per_group):
     """Row-major-like stream of slightly jittered boxes: consecutive boxes of a group overlap."""
     polys = []

@@ -77,6 +77,21 @@ def test_decode_variants(cuda_dev):
     _check(inp, out, min_size=0, scale=(2.0, 1.875), pixel_thresh=0.7, link_thresh=0.7)
 
 
+@pytest.mark.parametrize("tag", ["fast", "full"])
+def test_decode_link_graph_golden(golden_dir, tag, cuda_dev):
+    """D2/D3 against the reference scripts' own graph + DFS + minAreaRect lines, executed by line range
+    (tests/golden/make_golden.py:golden_link_graph): 192x320 / > 10 px / scale (4, 3.75) of
+    test_pixellink_fast.py:111-202 and 720x1280 / > 200 px / unscaled of test_pixellink.py:113-217."""
+    from util import link_graph_case
+    c = link_graph_case(golden_dir, tag)
+    inp = {"pix_logits": c["pix_logits"][None], "link_logits": c["link_logits"][None]}
+    out = _decode(inp, min_size=c["min_size"], scale=c["scale"], max_boxes=64)
+    n = c["n_groups"]
+    assert out["n_boxes"][0] == n
+    assert np.array_equal(out["labels"][0], c["labels"])
+    assert np.array_equal(out["boxes"][0, :n], c["boxes"])
+
+
 def test_decode_literal_dfs_crosscheck():
     """Oracle-only: on symmetric links without positive border pixels the canonical
     components equal the reference's literal DFS grouping."""
@@ -94,6 +109,48 @@ def test_decode_literal_dfs_crosscheck():
             px = np.argwhere(g == gid)
             r = lab[px[0][0], px[0][1]]
             assert r >= 0 and np.array_equal(lab == r, g == gid)
+
+
+def test_decode_asymmetric_links_vs_literal_dfs(cuda_dev):
+    """Quirk Q10, quantified: on ASYMMETRIC link maps the reference's directed, seed-order dependent DFS
+    (test_pixellink_fast.py:151-178, here with ascending seeds) and the canonical weakly-connected components
+    this library returns are different groupings.  What always holds, and is asserted: every literal group
+    lies inside ONE canonical component (a directed reachability set is weakly connected), so the canonical
+    grouping never splits what the reference joins; the reverse merges are counted and reported."""
+    from oracle import decode as D
+    from tensorflow_ocr_b200 import synth
+    n_lit = n_can = 0
+    for i in range(3):
+        im = synth.make_image(31, i, 48, 64, "G")          # independent link logits per direction: asymmetric
+        P, L = D.thresholds(im["pix_logits"], im["link_logits"], 0.6, 0.6)
+        out = _decode({"pix_logits": im["pix_logits"][None], "link_logits": im["link_logits"][None]},
+                      pixel_thresh=0.6, link_thresh=0.6, min_size=0, max_boxes=2048)
+        lab = out["labels"][0]
+        g, n = D.link_components_literal(P, L, 0)
+        for gid in range(1, n + 1):
+            inside = np.unique(lab[g == gid])
+            assert len(inside) == 1 and inside[0] >= 0, "a literal group straddles two canonical components"
+        n_lit += n
+        n_can += len(np.unique(lab[lab >= 0]))
+    assert n_can <= n_lit
+    print("asymmetric links: %d literal DFS groups -> %d canonical components" % (n_lit, n_can))
+
+
+def test_min_area_boxes_point_limit(cuda_dev):
+    """More than 2048 points in one explicit set: sentinel box instead of a shared-memory overrun."""
+    import torch
+    from tensorflow_ocr_b200 import head
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 500, (3000, 2)).astype(np.int32)
+    b = rng.integers(0, 500, (100, 2)).astype(np.int32)
+    b = np.array(sorted(b.tolist(), key=lambda t: (t[1], t[0])), np.int32)
+    offs = np.array([0, 3000, 3100], np.int32)
+    boxes, rects = head.min_area_boxes_raw(torch.as_tensor(np.concatenate([a, b])).to(cuda_dev),
+                                           torch.as_tensor(offs).to(cuda_dev))
+    boxes = boxes.cpu().numpy()
+    import cv2
+    assert (boxes[0] == np.iinfo(np.int32).min).all()
+    assert np.array_equal(boxes[1], np.intp(cv2.boxPoints(cv2.minAreaRect(b))))
 
 
 def test_min_area_boxes_vs_cv2(cuda_dev):
@@ -159,6 +216,25 @@ def test_pixel_detect(golden_dir, cuda_dev):
     g = np.load(golden_dir + "/pixel_detect.npz")
     assert np.array_equal(pixellink_fn.pixel_detect(g["score"], g["geo"]), g["res"])
     assert np.array_equal(pixellink_fn.pixel_detect(g["score"], g["geo"], 0.75, 0.7), g["res_075_07"])
+
+
+def test_pixel_detect_test_py_layout(golden_dir, cuda_dev):
+    """`decode.pixel_detect` keeps the name and input layout of test.py:45-74 (score [1,H,W,1], geo [1,H,W,16],
+    channel 2i+1 = link_i score) with the semantics of tool/pixellink_fn.py:120-154 (quirk Q8: the twin in
+    test.py clears two cells instead of every failing pixel); pinned on the reference-executed golden of the
+    latter, re-laid-out."""
+    import torch
+    from tensorflow_ocr_b200.decode import pixel_detect
+    g = np.load(golden_dir + "/pixel_detect.npz")
+    geo = g["geo"]                                                  # [8,1,H,W,2]
+    H, W = geo.shape[2], geo.shape[3]
+    geo16 = np.ascontiguousarray(np.transpose(geo[:, 0], (1, 2, 0, 3)).reshape(1, H, W, 16))
+    assert np.array_equal(pixel_detect(g["score"], geo16), g["res"])
+    assert np.array_equal(pixel_detect(g["score"], geo16, 0.75, 0.7), g["res_075_07"])
+    t = pixel_detect(torch.as_tensor(g["score"]).to(cuda_dev), torch.as_tensor(geo16).to(cuda_dev))
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), g["res"])
+    with pytest.raises(ValueError):
+        pixel_detect(g["score"], geo16[..., :8])
 
 
 def test_fused_loss_decode_flags(cuda_dev):

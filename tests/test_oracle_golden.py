@@ -142,3 +142,39 @@ def test_generate_rbox_matches_reference_execution(golden_dir):
         assert np.array_equal(show, g["show%d" % ci])
         assert link.sum() > 0
         assert np.array_equal(OL.link_labels_from_ids(pm), OL.link_labels_from_ids_loop(pm))
+
+
+import pytest
+
+
+@pytest.mark.parametrize("tag", ["fast", "full"])
+def test_link_graph_golden(golden_dir, tag):
+    """D2/D3 pin: the reference scripts' own graph + DFS + box lines (test_pixellink_fast.py:111-202,
+    test_pixellink.py:113-217), executed by line range on symmetric-link maps, against the canonical
+    weakly-connected-component labelling and the cv2 boxes of the oracle."""
+    from oracle import decode as D
+    from util import link_graph_case
+    c = link_graph_case(golden_dir, tag)
+    assert c["n_groups"] >= 8
+    P, L = D.thresholds(c["pix_logits"], c["link_logits"])
+    assert np.array_equal(P, c["P"]) and np.array_equal(L, c["L"])
+    labels, roots, sizes = D.link_components(c["P"], c["L"], c["min_size"])
+    assert np.array_equal(labels, c["labels"])
+    assert len(roots) == c["n_groups"]
+    boxes, _ = D.component_boxes(labels, roots, c["scale"])
+    assert np.array_equal(boxes, c["boxes"])
+    # some components must have been dropped by the size filter, or the filter is not exercised
+    all_labels, all_roots, _ = D.link_components(c["P"], c["L"], 0)
+    assert len(all_roots) > len(roots)
+
+
+def test_result_txt_golden(golden_dir, tmp_path):
+    """N4: the ICDAR result file exactly as test_pixellink_fast.py:209-217 writes it."""
+    from util import link_graph_case
+    from tensorflow_ocr_b200.decode import write_result_txt
+    c = link_graph_case(golden_dir, "fast")
+    # the script writes boxes in gid (first-seed) order; the golden keeps them in label order, and the
+    # file bytes in the script's order: compare as sets of lines
+    write_result_txt(str(tmp_path / "res.txt"), c["boxes"])
+    mine = open(tmp_path / "res.txt", "rb").read()
+    assert mine.endswith(b"\r\n") and sorted(mine.split(b"\r\n")) == sorted(c["res_txt"].split(b"\r\n"))
