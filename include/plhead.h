@@ -177,7 +177,11 @@ typedef struct plh_decode_params {
                           bit 0: components + label map only (no boxes); bit 1: boxes only, from the workspace
                           of a previous bit-0 call; bit 2: only the first kernel (thresholds + labelling inside
                           32x16 tiles); bit 3: everything after it, on the workspace of a bit-2 call.  Lets a
-                          caller interleave the decode with another pipeline (tensorflow_ocr_b200/head.py). */
+                          caller interleave the decode with another pipeline (tensorflow_ocr_b200/head.py).
+                          Bit 5: use the resident form of the component labelling (one 8-CTA cluster per image,
+                          the map as bit planes in distributed shared memory; PLH_E_SHAPE if a strip of H/8 rows
+                          does not fit in 227 KB) instead of the default tiled form.  Same results either way
+                          (the tests run both); bit 4 is accepted and means the default. */
 } plh_decode_params;
 
 /*
@@ -194,7 +198,7 @@ typedef struct plh_decode_params {
  *          then only K are written)
  *  rects   [B,K,5] float optional: cx, cy, w, h, angle of cv2.minAreaRect
  *  comp    [B,K,2] int32 optional: label (min pixel index) and pixel count per box
- * Limits: H <= 1024 rows, W*scale_x < 32768, H*scale_y < 32768.
+ * Limits: H <= 1024 rows, W <= 2048 columns, W*scale_x < 32768, H*scale_y < 32768.
  */
 PLH_API int plh_decode(const float* pix_logits, const float* link_logits, int B, int H, int W,
                const plh_decode_params* p, int32_t* labels, int32_t* boxes, int32_t* n_boxes, float* rects,

@@ -39,6 +39,12 @@ __constant__ int c_dx[8] = {-1, -1, -1, 1, 1, 1, 0, 0};
 
 constexpr int kFlagP = 1 << 8;
 
+// run-segment record handed to the box kernel: component label | row | first x | last x  (H <= 1024, W <= 2048)
+__device__ __forceinline__ unsigned long long make_rec(int root, int y, int x0, int x1) {
+  return ((unsigned long long)(unsigned)root << 32) | ((unsigned long long)y << 22) | ((unsigned long long)x0 << 11) |
+         (unsigned long long)x1;
+}
+
 struct DecodeWsLayout {
   size_t flags, parent, size, comp_root, comp_size, nrec, recs, total;
 };
@@ -52,7 +58,7 @@ static DecodeWsLayout decode_ws_layout(int B, int H, int W, int K) {
   l.size = off; off = align_up(off + px * 4, 256);
   l.comp_root = off; off = align_up(off + (size_t)B * K * 4, 256);
   l.comp_size = off; off = align_up(off + (size_t)B * K * 4, 256);
-  l.nrec = off; off = align_up(off + (size_t)B * 4, 256);
+  l.nrec = off; off = align_up(off + (size_t)B * 8 * 4, 256);   // one counter per (image, record sub-list)
   l.recs = off; off = align_up(off + px * 8, 256);   // one run-boundary record per pixel at most
   l.total = off;
   return l;
@@ -63,9 +69,14 @@ size_t decode_workspace_bytes(int B, int H, int W, int K) { return decode_ws_lay
 // Work unit = 32 consecutive pixels per warp: four link iterations (lane = pixel-in-iteration x quarter,
 // one 128-bit load of two directions' logits each) and one pixel phase (lane = pixel: its 2 pixel logits,
 // the 16-bit flag word store).  ~3 instructions per pixel: the kernel is bound by the 72 B/px it reads.
+// PLANES: the flag words leave as BIT PLANES for the resident component kernel instead (W % 32 == 0: a unit of
+// 32 consecutive pixels is then one word of a row): planes[b][y][k][w], k = 0..7 link_k passes, k = 8 pixel
+// passes, w = word of the row (rows of a strip are contiguous); 1.125 B/px instead of 2 B/px.
+template <bool PLANES>
 __global__ void __launch_bounds__(256)
 decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restrict__ link_logits, long long total_px,
-                    float tp_logit, float tl_logit, uint16_t* __restrict__ flags, int* __restrict__ n_boxes, int B) {
+                    float tp_logit, float tl_logit, uint16_t* __restrict__ flags, int* __restrict__ n_boxes, int B,
+                    unsigned* __restrict__ planes, int words_per_row) {
   pdl_wait_and_release();
   tl_start(4);
   const int lane = threadIdx.x & 31;
@@ -100,7 +111,19 @@ decode_flags_kernel(const float* __restrict__ pix_logits, const float* __restric
       const unsigned got = __shfl_sync(0xffffffffu, bits, (lane & 7) << 2);
       if ((lane >> 3) == it) mine = got;
     }
-    if (pp < total) flags[pp] = (uint16_t)(mine | ((P.y - P.x) > tp_logit ? kFlagP : 0));
+    const unsigned fl = pp < total ? (mine | ((P.y - P.x) > tp_logit ? kFlagP : 0)) : 0u;
+    if (PLANES) {
+      unsigned out = 0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const unsigned bk = __ballot_sync(0xffffffffu, (fl >> k) & 1u);
+        out = lane == k ? bk : out;
+      }
+      const int row = u / words_per_row;  // global row index b * H + y
+      if (lane < 9) planes[((size_t)row * 9 + lane) * words_per_row + (u - row * words_per_row)] = out;
+    } else if (pp < total) {
+      flags[pp] = (uint16_t)fl;
+    }
   }
   tl_end(4);
 }
@@ -191,7 +214,7 @@ decode_tile_cc_kernel(const float* __restrict__ pix_logits, const float* __restr
   const int tid = threadIdx.x;
   const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH, b = blockIdx.z;
   const size_t base = (size_t)b * H * W;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) n_boxes[b] = 0, nrec[b] = 0;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) n_boxes[b] = 0, nrec[b] = 0;  // (tiled form: one record list per image)
   const int ly = tid / kTW, lx = tid - ly * kTW;
   const int gy = ty0 + ly, gx = tx0 + lx;
   const bool inimg = gy < H && gx < W;
@@ -423,7 +446,7 @@ decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ siz
         const bool run_start = (x == 0) || (parent[g - 1] != r);
         const bool run_end = (x == W - 1) || (parent[g + 1] != r);
         emit = run_start || run_end;
-        rec = ((unsigned long long)(unsigned)rl << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
+        rec = make_rec(rl, y, x, x);
         if (r == (int)g) {
           const int slot = atomicAdd(&n_boxes[b], 1);
           if (slot < K) comp_root[(size_t)b * K + slot] = rl, comp_size[(size_t)b * K + slot] = sz;
@@ -444,6 +467,409 @@ decode_labels_kernel(const int* __restrict__ parent, const int* __restrict__ siz
   tl_end(9);
 }
 
+
+// ------------------------------------------------------------------ resident form: one cluster per image
+// Phases D1a-D4 (component labelling from the threshold bits, sizes, label map, box slots, run records) in
+// ONE launch with the whole map ON CHIP: a thread-block cluster of 8 CTAs owns one image, CTA r holds the
+// strip of rows [r*RS, (r+1)*RS) (+ a 2-row halo of the bit planes) in its shared memory, and the union-find
+// words of the strips form one array in DISTRIBUTED shared memory (every CTA can read / atomicMin any word
+// through the cluster window).  The tiled kernels above spend most of their time in launch / ramp / drain
+// and dependent L2 round trips, and a pixel-per-thread labelling costs ~340 instructions per pixel.  Here
+// the map is held as BIT PLANES (one 32-bit word = 32 pixels of a row; 8 link planes + the pixel plane)
+// and everything that can be is word-wide bit arithmetic, one lane per word:
+//   1. node filter (border pixels no interior neighbour links to are not graph nodes), then the
+//      "continues the run of its left neighbour" mask CL: pixel x joins x-1 iff the pair is linked (either
+//      endpoint emits the edge, same rule as the tiled form).  A run = a maximal stretch of CL; its head is
+//      its first pixel.  Runs, not pixels, are the union-find nodes;
+//   2. row y / row y+1: the edge masks of the three downward directions by shifts and ANDs; an edge is
+//      dropped when the bit to its left is the same edge between the same two runs (or the previous
+//      direction already reaches the same run), which leaves about one union per PAIR OF RUNS.  The edges go
+//      to a list so that all threads share the unions: atomicMin on the run heads (larger index under
+//      smaller: root = minimum pixel index), local or remote shared memory alike;
+//   3. flatten the heads; sizes accumulate IN the root's own word as -(count) - 1 (a root needs no
+//      pointer), one atomic per run segment;
+//   4. label map out (one warp per word, coalesced), kept roots take box slots, kept run segments append
+//      (root, y, x0, x1) records for the box kernel.
+// Cluster barriers (release / acquire) separate the phases that touch other CTAs' words.
+constexpr int kImgCluster = 8;
+#ifndef PLH_IMG_THREADS
+#define PLH_IMG_THREADS 256
+#endif
+constexpr int kImgThreads = PLH_IMG_THREADS;
+constexpr int kImgWarps = kImgThreads / 32;
+constexpr size_t kImgSmemMax = 227 * 1024 - 256;
+constexpr int kImgEdgeCapMax = 2048, kImgEdgeCapMin = 512;
+
+struct ImgGeom {
+  int RS, WW, nl, np, nc, nx;  // rows per strip, words per row, words of: labels / planes / CL (= CH ...) ; cross-edge slots
+};
+__host__ __device__ inline ImgGeom image_geom(int H, int W) {
+  ImgGeom g;
+  g.RS = (H + kImgCluster - 1) / kImgCluster;
+  g.WW = (W + 31) / 32;
+  g.nl = g.RS * W;
+  g.np = ((9 * (g.RS + 4) * g.WW + 3) / 4) * 4;
+  g.nc = (g.RS + 1) * g.WW;
+  g.nx = 3 * W;  // at most three downward edges per pixel of the strip's last row
+  return g;
+}
+__host__ __device__ inline size_t image_smem_base_bytes(int H, int W) {
+  const ImgGeom g = image_geom(H, W);
+  return 4 * ((size_t)g.nl + g.np + 6 * (size_t)g.nc) + 8 + 8 * (size_t)g.nx;
+}
+// capacity of the shared-memory edge list: whatever is left, within [kImgEdgeCapMin, kImgEdgeCapMax]; 0 = does not fit
+inline int image_edge_cap(int H, int W) {
+  const size_t base = image_smem_base_bytes(H, W);
+  if (base + (size_t)kImgEdgeCapMin * 8 > kImgSmemMax) return 0;
+  return (int)std::min<size_t>(kImgEdgeCapMax, (kImgSmemMax - base) / 8);
+}
+
+// bits of word w (pixels 32w .. 32w+31) whose x lies in [lo, hi]
+__device__ __forceinline__ unsigned xmask(int lo, int hi, int w) {
+  const int a = max(lo - (w << 5), 0), b = min(hi - (w << 5), 31);
+  return b < a ? 0u : ((0xffffffffu >> (31 - b)) & (0xffffffffu << a));
+}
+__device__ __forceinline__ void cluster_barrier() {
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// the union-find words of the image, spread over the cluster: word px lives in CTA px / (RS*W)
+struct DLab {
+  int* loc;
+  unsigned long long magic;  // ceil(2^40 / rsw)
+  int rsw;
+  __device__ __forceinline__ uint32_t at(int px) const {  // shared::cluster address of word px
+    const int r = (int)(((unsigned long long)(unsigned)px * magic) >> 40);
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(loc + (px - r * rsw));
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(r));
+    return ra;
+  }
+  __device__ __forceinline__ int ld(int px) const {
+    int v;
+    asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(at(px)) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st(int px, int v) const {
+    asm volatile("st.volatile.shared::cluster.s32 [%0], %1;" ::"r"(at(px)), "r"(v) : "memory");
+  }
+  __device__ __forceinline__ int atom_min(int px, int v) const {
+    int o;
+    asm volatile("atom.relaxed.cluster.shared::cluster.min.s32 %0, [%1], %2;" : "=r"(o) : "r"(at(px)), "r"(v) : "memory");
+    return o;
+  }
+  __device__ __forceinline__ void red_add(int px, int v) const {
+    asm volatile("red.relaxed.cluster.shared::cluster.add.s32 [%0], %1;" ::"r"(at(px)), "r"(v) : "memory");
+  }
+  __device__ __forceinline__ int find(int v) const {  // with path halving
+    int p = ld(v);
+    while (p != v) {
+      const int gp = ld(p);
+      if (gp != p) st(v, gp);
+      v = p;
+      p = gp;
+    }
+    return v;
+  }
+  __device__ __forceinline__ void unite(int a, int c) const {
+    while (true) {
+      a = find(a);
+      c = find(c);
+      if (a == c) return;
+      if (a < c) { const int t = a; a = c; c = t; }  // hook the larger root under the smaller
+      const int old = atom_min(a, c);
+      if (old == a) return;
+      a = old;
+    }
+  }
+};
+
+template <bool FROM_PLANES>
+__global__ void __cluster_dims__(kImgCluster, 1, 1) __launch_bounds__(kImgThreads, 2)
+decode_image_kernel(const uint16_t* __restrict__ flags, const unsigned* __restrict__ planes, int H, int W, int min_size,
+                    int K, int edge_cap, unsigned long long magic, int32_t* __restrict__ labels,
+                    int* __restrict__ comp_root, int* __restrict__ comp_size, int* __restrict__ n_boxes,
+                    int* __restrict__ nrec, unsigned long long* __restrict__ recs) {
+  tl_end(23);  // latest CTA arrival (before the dependency wait)
+  pdl_wait();
+  tl_start(5);
+  tl_end(22);  // latest CTA start
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_nedge, s_nxedge, s_nrec;
+  const ImgGeom g = image_geom(H, W);
+  const int N = H * W, WW = g.WW, RS = g.RS, PR = RS + 4;  // PR: plane rows held (2-row halo each side)
+  int* lab = reinterpret_cast<int*>(smem);                 // [RS*W] this strip's union-find words / root counters
+  unsigned* PL = reinterpret_cast<unsigned*>(lab + g.nl);  // [PR][9][WW] planes: 0..7 link_d passes, 8 pixel passes (then: is a node)
+  unsigned* CL = PL + g.np;                                // [RS+1][WW] continues the run of the left neighbour
+  int* CH = reinterpret_cast<int*>(CL + g.nc);             // [RS+1][WW] head of the run that enters the word at bit 0
+  unsigned* ER = reinterpret_cast<unsigned*>(CH + g.nc);   // [3][RS+1][WW] de-duplicated downward edges per direction
+  int* EO = reinterpret_cast<int*>(ER + 3 * g.nc);         // [RS+1][WW] first edge-list slot of the word
+  int2* EX = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(EO + g.nc) + 7) & ~(uintptr_t)7);  // [3W] edges into the next strip
+  int2* EL = EX + g.nx;                                    // [edge_cap] edges inside the strip
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = blockIdx.x % kImgCluster, b = blockIdx.x / kImgCluster;
+  const size_t base = (size_t)b * N;
+  const int y0 = rank * RS, y1 = min(H, y0 + RS);          // this strip's rows [y0, y1) (may be empty)
+  const int nrows = max(y1 - y0, 0), p00 = y0 * W;         // p00: first pixel of the strip
+  const DLab L{lab, magic, RS * W};
+  auto pl = [&](int k, int y, int w) -> unsigned& { return PL[((y - y0 + 2) * 9 + k) * WW + w]; };
+  if (tid == 0) s_nedge = 0, s_nxedge = 0, s_nrec = 0;
+  if (rank == 0 && tid == 0) n_boxes[b] = 0;
+
+  // ---- bit planes of rows y0-2 .. y1+1 into shared memory (copied: the rows of a strip are contiguous; or built
+  // from the flag words: one warp per word of 32 pixels); union-find initialised to singletons
+  // (strip-relative indices until the strip is flat: the long pointer chains are walked with plain shared-memory loads)
+  for (int i = tid; i < nrows * W; i += kImgThreads) lab[i] = i;
+  if (FROM_PLANES) {
+    const int rw = 9 * WW;                                 // words per row of planes
+    const long long off = ((long long)b * H + (y0 - 2)) * rw;
+    for (int i = tid; i < PR * rw; i += kImgThreads) {
+      const int y = y0 - 2 + i / rw;
+      PL[i] = (y >= 0 && y < H) ? __ldg(planes + (off + i)) : 0u;
+    }
+  } else {
+    for (int j = warp; j < PR * WW; j += kImgWarps) {
+      const int r = j / WW, y = y0 - 2 + r, w = j - r * WW, x = (w << 5) + lane;
+      const unsigned f = (y >= 0 && y < H && x < W) ? flags[base + (size_t)y * W + x] : 0u;
+      unsigned mine = 0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const unsigned bk = __ballot_sync(0xffffffffu, (f >> k) & 1u);
+        mine = lane == k ? bk : mine;
+      }
+      if (lane < 9) PL[(r * 9 + lane) * WW + w] = mine;
+    }
+  }
+  __syncthreads();
+  tl_end(24);
+
+  // ---- 1a. node filter for rows y0-1 .. y1: a border pixel is a graph node only if some interior neighbour links to it
+  {
+    const int ya = max(y0 - 1, 0), yb = min(y1 + 1, H);
+    for (int i = tid; i < max(yb - ya, 0) * WW; i += kImgThreads) {
+      const int y = ya + i / WW, w = i % WW;
+      const unsigned P = pl(8, y, w);
+      const unsigned vin = (y >= 1 && y <= H - 2) ? xmask(1, W - 2, w) : 0u;
+      if (P & ~vin) {
+        unsigned reached = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          const int sy = y - c_dy[d];  // source row: must be interior
+          if (sy < 1 || sy > H - 2) continue;
+          const unsigned S = pl(8, sy, w) & pl(d, sy, w) & xmask(1, W - 2, w);
+          if (c_dx[d] == 0) reached |= S;
+          else if (c_dx[d] > 0) reached |= (S << 1) | (w > 0 ? (pl(8, sy, w - 1) & pl(d, sy, w - 1) & xmask(1, W - 2, w - 1)) >> 31 : 0u);
+          else reached |= (S >> 1) | (w < WW - 1 ? (pl(8, sy, w + 1) & pl(d, sy, w + 1) & xmask(1, W - 2, w + 1)) << 31 : 0u);
+        }
+        pl(8, y, w) = P & (vin | reached);  // only border bits change; the sources read above are interior bits
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 1b. CL for rows y0 .. y1: linked to the left neighbour (v emits "left", plane 0, or the neighbour emits "right", plane 3)
+  const int yc = min(y1 + 1, H);  // CL / CH rows [y0, yc)
+  for (int i = tid; i < max(yc - y0, 0) * WW; i += kImgThreads) {
+    const int y = y0 + i / WW, w = i % WW;
+    const unsigned P = pl(8, y, w);
+    unsigned cl = 0;
+    if (P) {
+      const bool yin = y >= 1 && y <= H - 2;
+      const unsigned Pl = (P << 1) | (w > 0 ? pl(8, y, w - 1) >> 31 : 0u);
+      const unsigned L3l = (pl(3, y, w) << 1) | (w > 0 ? pl(3, y, w - 1) >> 31 : 0u);
+      const unsigned vin = yin ? xmask(1, W - 2, w) : 0u, vinl = yin ? xmask(2, W - 1, w) : 0u;
+      cl = P & Pl & ((vin & pl(0, y, w)) | (vinl & L3l));
+    }
+    CL[i] = cl;
+  }
+  __syncthreads();
+  // ---- 1c. head of the run that enters a word from the left (bit 0 of word 0 is never set in CL)
+  for (int i = tid; i < max(yc - y0, 0) * WW; i += kImgThreads)
+    if (CL[i] & 1u) {
+      const int y = y0 + i / WW;
+      int ii = i - 1;
+      unsigned nz = ~CL[ii];
+      while (nz == 0u) nz = ~CL[--ii];
+      CH[i] = y * W + ((ii % WW) << 5) + 31 - __clz(nz);
+    }
+  __syncthreads();
+  tl_end(17);
+  // run head of pixel `bit` of word w of row y (y in [y0, yc))
+  auto head_of = [&](int y, int w, int bit) -> int {
+    const int i = (y - y0) * WW + w;
+    const unsigned z = ~CL[i] & (0xffffffffu >> (31 - bit));
+    return z ? y * W + (w << 5) + 31 - __clz(z) : CH[i];
+  };
+
+  // ---- 2. edges between the runs of row y and row y+1, y in this strip (the pair y1-1 / y1 reaches into the
+  // next strip).  2a, one lane per word: the three de-duplicated edge masks and the word's slots in the edge list
+  for (int i = tid; i < nrows * WW; i += kImgThreads) {
+    const int y = y0 + i / WW, w = i % WW;
+    unsigned R1 = 0, R7 = 0, R4 = 0;
+    const unsigned P = (y + 1 < H) ? pl(8, y, w) : 0u;
+    if (P) {
+      const bool hasl = w > 0, hasr = w < WW - 1;
+      const unsigned Pd = pl(8, y + 1, w), Pd1 = (Pd << 1) | (hasl ? pl(8, y + 1, w - 1) >> 31 : 0u),
+                     Pd4 = (Pd >> 1) | (hasr ? pl(8, y + 1, w + 1) << 31 : 0u);
+      if (P & (Pd | Pd1 | Pd4)) {
+        const bool yin = y >= 1 && y <= H - 2, y1in = y + 1 <= H - 2;
+        const unsigned vin = yin ? xmask(1, W - 2, w) : 0u;
+        const unsigned vind = y1in ? xmask(1, W - 2, w) : 0u;    // (y+1, x)   interior
+        const unsigned vind1 = y1in ? xmask(2, W - 1, w) : 0u;   // (y+1, x-1) interior
+        const unsigned vind4 = y1in ? xmask(0, W - 3, w) : 0u;   // (y+1, x+1) interior
+        // neighbour's answering link, aligned to this word: left_down 1 <-> right_up 5, down 7 <-> up 6, right_down 4 <-> left_up 2
+        const unsigned L5d1 = (pl(5, y + 1, w) << 1) | (hasl ? pl(5, y + 1, w - 1) >> 31 : 0u);
+        const unsigned L2d4 = (pl(2, y + 1, w) >> 1) | (hasr ? pl(2, y + 1, w + 1) << 31 : 0u);
+        const unsigned E1 = P & Pd1 & ((vin & pl(1, y, w)) | (vind1 & L5d1));
+        const unsigned E7 = P & Pd & ((vin & pl(7, y, w)) | (vind & pl(6, y + 1, w)));
+        const unsigned E4 = P & Pd4 & ((vin & pl(4, y, w)) | (vind4 & L2d4));
+        const int id = i + WW;  // row y+1 in CL / CH
+        const unsigned cl = CL[i], cld = CL[id];
+        const unsigned cld1 = (cld << 1) | (hasl ? CL[id - 1] >> 31 : 0u), cld4 = (cld >> 1) | (hasr ? CL[id + 1] << 31 : 0u);
+        R1 = E1 & ~((E1 << 1) & cl & cld1);
+        R7 = E7 & ~((E7 << 1) & cl & cld) & ~(E1 & cld);
+        R4 = E4 & ~((E4 << 1) & cl & cld4) & ~(E7 & cld4);
+      }
+    }
+    ER[i] = R1, ER[g.nc + i] = R7, ER[2 * g.nc + i] = R4;
+    const int ne = __popc(R1) + __popc(R7) + __popc(R4);
+    // the strip's last row pair goes to the cross list (always large enough), the others to the local list
+    EO[i] = ne ? atomicAdd(y + 1 == y1 ? &s_nxedge : &s_nedge, ne) : 0;
+  }
+  __syncthreads();
+  // 2b, one warp per word, lane = pixel: the (head, head) pair of every edge into its list, so that ALL threads
+  // share the unions afterwards; local edges that do not fit the list are united here (shared-memory atomics)
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i = warp; i < nrows * WW; i += kImgWarps) {
+    const unsigned R1 = ER[i], R7 = ER[g.nc + i], R4 = ER[2 * g.nc + i];
+    if (!(R1 | R7 | R4)) continue;
+    const int y = y0 + i / WW, w = i % WW, x = (w << 5) + lane;
+    const int pos = EO[i];
+    const bool cross = y + 1 == y1;
+    const int hv = head_of(y, w, lane);
+    auto emit = [&](int idx, int c) {
+      if (cross) EX[idx] = make_int2(hv, c);
+      else if (idx < edge_cap) EL[idx] = make_int2(hv, c);
+      else unite_s(lab, hv - p00, c - p00);
+    };
+    if ((R1 >> lane) & 1u) emit(pos + __popc(R1 & lt), head_of(y + 1, (x - 1) >> 5, (x - 1) & 31));
+    if ((R7 >> lane) & 1u) emit(pos + __popc(R1) + __popc(R7 & lt), head_of(y + 1, w, lane));
+    if ((R4 >> lane) & 1u) emit(pos + __popc(R1) + __popc(R7) + __popc(R4 & lt), head_of(y + 1, (x + 1) >> 5, (x + 1) & 31));
+  }
+  __syncthreads();
+  tl_end(18);
+
+  // ---- 3. unions, in two levels so that the long pointer chains stay in LOCAL shared memory.
+  // 3a: edges inside the strip, on strip-relative indices (plain shared-memory loads / atomicMin)
+  {
+    const int ne = min(s_nedge, edge_cap);
+    for (int i = tid; i < ne; i += kImgThreads) unite_s(lab, EL[i].x - p00, EL[i].y - p00);
+  }
+  __syncthreads();
+  // 3b: every head of the strip -> its strip-local root (read-only walks), absolute indices again
+  for (int i = warp; i < nrows * WW; i += kImgWarps) {
+    const int y = y0 + i / WW, w = i % WW;
+    const unsigned P = pl(8, y, w);
+    const int q = (y - y0) * W + (w << 5) + lane;          // strip-relative pixel
+    int r = -1;
+    if ((((P & ~CL[i]) >> lane) & 1u)) {
+      r = q;
+      for (int t = reinterpret_cast<volatile int*>(lab)[r]; t != r; t = reinterpret_cast<volatile int*>(lab)[r]) r = t;
+    }
+    __syncwarp();
+    if (r >= 0) lab[q] = r;                                // (a root's word is only written by its own lane: r == q)
+  }
+  __syncthreads();
+  for (int i = tid; i < nrows * W; i += kImgThreads) lab[i] += p00;
+  cluster_barrier();  // every strip is flat and absolute: heads point at strip-local roots
+  tl_end(19);
+  // 3c: the edges into the next strip, between strip-local roots, through the cluster window (chains: one hop per strip)
+  {
+    const int nx = s_nxedge;
+    for (int i = tid; i < nx; i += kImgThreads) L.unite(lab[EX[i].x - p00], L.ld(EX[i].y));
+  }
+  cluster_barrier();  // all unions of the image are done
+  // 3d: heads -> the image-wide root (their strip-local root, then at most one hop per strip)
+  for (int i = warp; i < nrows * WW; i += kImgWarps) {
+    const int y = y0 + i / WW, w = i % WW;
+    const unsigned hd = pl(8, y, w) & ~CL[i];
+    if ((hd >> lane) & 1u) {
+      const int h = y * W + (w << 5) + lane;
+      int r = lab[h - p00];                                // strip-local root (or already further: pointers only move rootwards)
+      for (int t = L.ld(r); t != r; t = L.ld(r)) r = t;
+      lab[h - p00] = r;
+    }
+  }
+  cluster_barrier();  // nobody walks pointers any more
+  tl_end(20);
+  // roots start counting: -(count) - 1
+  for (int i = warp; i < nrows * WW; i += kImgWarps) {
+    const int y = y0 + i / WW, w = i % WW;
+    const unsigned hd = pl(8, y, w) & ~CL[i];
+    const int h = y * W + (w << 5) + lane;
+    if (((hd >> lane) & 1u) && lab[h - p00] == h) lab[h - p00] = -1;
+  }
+  cluster_barrier();
+  // one atomic per run segment (a run that crosses a word boundary counts once per word)
+  for (int i = warp; i < nrows * WW; i += kImgWarps) {
+    const int y = y0 + i / WW, w = i % WW;
+    const unsigned P = pl(8, y, w);
+    if (!P) continue;
+    const unsigned cl = CL[i];
+    const bool entering = lane == 0 && (cl & 1u);  // its head lives further left in this row, hence in this strip
+    if ((((P & ~cl) >> lane) & 1u) || entering) {
+      const unsigned rest = lane < 31 ? (~cl & (0xffffffffu << (lane + 1))) : 0u;
+      const int h = entering ? CH[i] : y * W + (w << 5) + lane, v = lab[h - p00];
+      L.red_add(v < 0 ? h : v, -((rest ? __ffs(rest) - 1 : 32) - lane));
+    }
+  }
+  cluster_barrier();
+  tl_end(21);
+
+  // ---- 4. label map, box slots, run records (one list per strip): one warp per word, lane = pixel
+  unsigned long long* myrecs = recs + base + (size_t)rank * RS * W;
+  for (int i = warp; i < nrows * WW; i += kImgWarps) {
+    const int y = y0 + i / WW, w = i % WW, x = (w << 5) + lane, px = y * W + x;
+    const unsigned P = pl(8, y, w);
+    if (!P) {
+      if (x < W) labels[base + px] = -1;
+      continue;
+    }
+    const unsigned cl = CL[i];
+    const bool member = (P >> lane) & 1u;
+    const unsigned z = ~cl & (0xffffffffu >> (31 - lane));
+    const int h = z ? y * W + (w << 5) + 31 - __clz(z) : CH[i];
+    int root = -1, cnt = 0, v = 0;
+    if (member) {
+      v = lab[h - p00];
+      root = v < 0 ? h : v;
+      cnt = -(v < 0 ? v : L.ld(root)) - 1;
+    }
+    const bool kept = member && cnt > min_size;  // test_pixellink_fast.py:174 `len(index_list) > 10`
+    if (x < W) labels[base + px] = kept ? root : -1;
+    if (kept && v < 0 && h == px) {
+      const int slot = atomicAdd(&n_boxes[b], 1);
+      if (slot < K) comp_root[(size_t)b * K + slot] = px, comp_size[(size_t)b * K + slot] = cnt;
+    }
+    const bool seg = kept && (lane == 0 || !((cl >> lane) & 1u));  // a head, or the run entering at bit 0
+    const unsigned sm = __ballot_sync(0xffffffffu, seg);
+    if (sm == 0u) continue;
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(&s_nrec, __popc(sm));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (seg) {
+      const unsigned rest = lane < 31 ? (~cl & (0xffffffffu << (lane + 1))) : 0u;
+      const int len = (rest ? __ffs(rest) - 1 : 32) - lane;
+      myrecs[pos + __popc(sm & ((1u << lane) - 1u))] = make_rec(root, y, x, x + len - 1);
+    }
+  }
+  pdl_release();
+  cluster_barrier();  // no CTA retires while a peer may still read its words
+  if (tid == 0) nrec[b * kImgCluster + rank] = s_nrec;
+  tl_end(5);
+}
+
 // ------------------------------------------------------------------ D5: one CTA per component
 // Persistent grid: the components of the whole batch form one work list (image-major); CTA c takes
 // items c, c + gridDim.x, ...  (a grid of B x K CTAs would be ~95% empty CTAs that still have to be
@@ -452,8 +878,8 @@ __global__ void __launch_bounds__(256)
 decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ comp_root,
                     const int* __restrict__ comp_size, const int* __restrict__ nrec,
                     const unsigned long long* __restrict__ recs,
-                    int B, int H, int W, int K, double sx, double sy, int npad, int32_t* __restrict__ boxes,
-                    float* __restrict__ rects, int32_t* __restrict__ comp) {
+                    int B, int H, int W, int K, double sx, double sy, int npad, int nsub, int sub_stride,
+                    int32_t* __restrict__ boxes, float* __restrict__ rects, int32_t* __restrict__ comp) {
   pdl_wait_and_release();
   tl_start(10);
   extern __shared__ __align__(16) unsigned char smem[];
@@ -496,16 +922,16 @@ decode_rects_kernel(const int* __restrict__ n_boxes, const int* __restrict__ com
     const int y0 = root / W;  // the component's first row: its minimum pixel index lives there
     for (int y = y0 + threadIdx.x; y < H; y += blockDim.x) s_rmin[y] = 0x7fffffff, s_rmax[y] = -1;
     __syncthreads();
-    {
-      const int nr = nrec[b];
-      const unsigned long long* rb = recs + (size_t)b * H * W;
+    for (int sub = 0; sub < nsub; ++sub) {  // tiled form: one record list per image; resident form: one per strip
+      const int nr = nrec[b * nsub + sub];
+      const unsigned long long* rb = recs + (size_t)b * H * W + (size_t)sub * sub_stride;
 #pragma unroll 4
       for (int i = threadIdx.x; i < nr; i += blockDim.x) {
         const unsigned long long rc = rb[i];
         if ((int)(rc >> 32) == root) {
-          const int y = (int)(rc >> 16) & 0xffff, x = (int)rc & 0xffff;
-          atomicMin(&s_rmin[y], x);
-          atomicMax(&s_rmax[y], x);
+          const int y = (int)(rc >> 22) & 0x3ff;
+          atomicMin(&s_rmin[y], (int)(rc >> 11) & 0x7ff);
+          atomicMax(&s_rmax[y], (int)rc & 0x7ff);
         }
       }
     }
@@ -608,7 +1034,7 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
                          int W, const plh_decode_params* p, int32_t* labels, int32_t* boxes, int32_t* n_boxes,
                          float* rects, int32_t* comp, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   if (!p || !labels || !boxes || !n_boxes) return PLH_E_NULL;
-  if (B <= 0 || H <= 0 || W <= 0 || H > 1024 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || H > 1024 || W > 2048 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
   if (p->max_boxes <= 0 || p->min_size < 0 || !(p->scale_x >= 1.0) || !(p->scale_y >= 1.0) ||
       W * p->scale_x >= 32768.0 || H * p->scale_y >= 32768.0)
     return PLH_E_PARAM;
@@ -632,7 +1058,59 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   const bool rects_only = (p->reserved[0] & 2) != 0;  // boxes from a workspace prepared by a skip_rects call
   const bool tile_only = (p->reserved[0] & 4) != 0;   // stop after the threshold + tile-labelling kernel
   const bool after_tile = (p->reserved[0] & 8) != 0;  // resume on a workspace a tile_only call prepared
+  // Two forms, same results.  Tiled (default): five launches, the forest in global memory (L2).  Resident (bit 5,
+  // opt-in): three launches — threshold bits as bit planes, components with the map in the shared memory of an
+  // 8-CTA cluster (union-find words in distributed shared memory), boxes.  Measured on B200 at 32 x 128x128
+  // the resident form is NOT faster (61 us vs 50 us alone: its ~10 phases are each bound by the latency of one
+  // warp's dependent shared-memory chain and by the busiest strip of a cluster), so it is
+  // kept as a cross-check of the tiled form in the tests, not as the default.
+  const int edge_cap = image_edge_cap(H, W);
+  const bool fits = edge_cap > 0;
+  const size_t img_smem = image_smem_base_bytes(H, W) + (size_t)edge_cap * 8;
+  const bool planes_ok = !flags_in && (W % 32) == 0;   // the threshold kernel writes bit planes (into the forest's region)
+  unsigned* planes = reinterpret_cast<unsigned*>(parent);
+  const unsigned long long rsw = (unsigned long long)image_geom(H, W).RS * W;
+  const unsigned long long magic = ((1ull << 40) + rsw - 1) / rsw;  // px / rsw == (px * magic) >> 40 for px < 2^31
+  if ((p->reserved[0] & 32) != 0 && !fits) return PLH_E_SHAPE;  // the resident form was demanded
+  const bool legacy = (p->reserved[0] & 32) == 0 || tile_only || after_tile;
   if (rects_only) goto rects;
+  if (!legacy) {
+    if (flags_in) {
+      flags = const_cast<uint16_t*>(flags_in);
+    } else {
+      const int grid = (int)std::min<long long>((total_px / 32 + 7) / 8 + 1, kNumSMs * 8);
+      if (planes_ok)
+        rc = launch_plain(decode_flags_kernel<true>, grid, 256, 0, s, pix_logits, link_logits, total_px,
+                          prob_to_logit_threshold(p->pixel_thresh), prob_to_logit_threshold(p->link_thresh),
+                          (uint16_t*)nullptr, (int*)nullptr, 0, planes, W / 32);
+      else
+        rc = launch_plain(decode_flags_kernel<false>, grid, 256, 0, s, pix_logits, link_logits, total_px,
+                          prob_to_logit_threshold(p->pixel_thresh), prob_to_logit_threshold(p->link_thresh), flags,
+                          (int*)nullptr, 0, (unsigned*)nullptr, 0);
+      if (rc) return rc;
+    }
+    static SmemOptIn optin_p, optin_f;
+    static const bool img_plain = getenv("PLH_IMG_PLAIN") != nullptr;  // A/B: no programmatic early launch
+    if (planes_ok && img_plain) {
+      if ((rc = ensure_dynamic_smem(optin_p, decode_image_kernel<true>, img_smem))) return rc;
+      rc = launch_plain(decode_image_kernel<true>, B * kImgCluster, kImgThreads, img_smem, s, (const uint16_t*)nullptr,
+                  (const unsigned*)planes, H, W, p->min_size, K, edge_cap, magic, labels, comp_root, comp_size, n_boxes,
+                  nrec, recs);
+    } else if (planes_ok) {
+      if ((rc = ensure_dynamic_smem(optin_p, decode_image_kernel<true>, img_smem))) return rc;
+      rc = launch(decode_image_kernel<true>, B * kImgCluster, kImgThreads, img_smem, s, (const uint16_t*)nullptr,
+                  (const unsigned*)planes, H, W, p->min_size, K, edge_cap, magic, labels, comp_root, comp_size, n_boxes,
+                  nrec, recs);
+    } else {
+      if ((rc = ensure_dynamic_smem(optin_f, decode_image_kernel<false>, img_smem))) return rc;
+      rc = launch(decode_image_kernel<false>, B * kImgCluster, kImgThreads, img_smem, s, (const uint16_t*)flags,
+                  (const unsigned*)nullptr, H, W, p->min_size, K, edge_cap, magic, labels, comp_root, comp_size, n_boxes,
+                  nrec, recs);
+    }
+    if (rc) return rc;
+    if (skip_rects) return PLH_OK;
+    goto rects;
+  }
   if (after_tile) goto merge;
   {
     const dim3 tiles((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, B);
@@ -665,7 +1143,8 @@ rects:
     if ((rc = ensure_dynamic_smem(optin, decode_rects_kernel, smem))) return rc;
     const int rect_grid = (int)std::min<long long>((long long)B * K, kNumSMs * 8);
     rc = launch(decode_rects_kernel, rect_grid, 256, smem, s, n_boxes, comp_root, comp_size, nrec, recs, B, H, W, K,
-                                                      p->scale_x, p->scale_y, npad, boxes, rects, comp);
+                p->scale_x, p->scale_y, npad, legacy ? 1 : kImgCluster, legacy ? 0 : image_geom(H, W).RS * W, boxes, rects,
+                comp);
     if (rc) return rc;
   }
   return PLH_OK;
@@ -674,10 +1153,32 @@ rects:
 #ifdef PLH_TIMELINE
 int tl_set_decode(unsigned long long* p) { return tl_set_ptr(p); }
 #endif
+int debug_image_cluster_occupancy(int H, int W) {
+  const int edge_cap = image_edge_cap(H, W);
+  if (!edge_cap) return -1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(32 * kImgCluster);
+  cfg.blockDim = dim3(kImgThreads);
+  cfg.dynamicSmemBytes = image_smem_base_bytes(H, W) + (size_t)edge_cap * 8;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kImgCluster, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  cudaFuncSetAttribute(decode_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+  int n = -2;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, decode_image_kernel<true>, &cfg);
+  return e == cudaSuccess ? n : -1000 - (int)e;
+}
 
 }  // namespace plh
 
 using namespace plh;
+
+#ifdef PLH_TIMELINE
+extern "C" __attribute__((visibility("default"))) int plh_debug_image_cluster_occupancy(int H, int W) {
+  return debug_image_cluster_occupancy(H, W);
+}
+#endif
 
 extern "C" int plh_decode(const float* pix_logits, const float* link_logits, int B, int H, int W,
                           const plh_decode_params* p, int32_t* labels, int32_t* boxes, int32_t* n_boxes, float* rects,
@@ -703,9 +1204,9 @@ extern "C" int plh_decode_flags(const float* pix_logits, const float* link_logit
   if (!aligned16(pix_logits) || !aligned16(link_logits) || !aligned16(flags)) return PLH_E_ALIGN;
   const long long total_px = (long long)B * H * W;
   const int grid = (int)std::min<long long>((total_px / 32 + 7) / 8 + 1, kNumSMs * 8);
-  return launch_plain(decode_flags_kernel, grid, 256, 0, (cudaStream_t)stream, pix_logits, link_logits, total_px,
+  return launch_plain(decode_flags_kernel<false>, grid, 256, 0, (cudaStream_t)stream, pix_logits, link_logits, total_px,
                 prob_to_logit_threshold(p->pixel_thresh), prob_to_logit_threshold(p->link_thresh), flags,
-                (int*)nullptr, 0);
+                (int*)nullptr, 0, (unsigned*)nullptr, 0);
 }
 
 extern "C" int plh_min_area_boxes(const int32_t* pts, const int32_t* offsets, int n_sets, int32_t* boxes, float* rects,

@@ -51,11 +51,12 @@ class DecodeConfig:
     scale: Tuple[float, float] = (4.0, 3.75)  # (1280/320, 720/192) test_pixellink_fast.py:196-197
     max_boxes: int = 128
     phase: int = 0    # plh_decode_params.reserved[0]: 0 whole decode, 4 tile pass only, 8 resume after the tile pass
+    form: str = "auto"  # "auto" = "tiled" (5 launches, forest in L2) | "resident" (one 8-CTA cluster per image, map in shared memory, 3 launches): same results
 
     def c_struct(self):
         p = _lib.DecodeParams(self.pixel_thresh, self.link_thresh, self.min_size, self.max_boxes,
                               float(self.scale[0]), float(self.scale[1]))
-        p.reserved[0] = self.phase
+        p.reserved[0] = self.phase | {"auto": 0, "tiled": 16, "resident": 32}[self.form]
         return p
 
 
@@ -278,12 +279,15 @@ def _aux_stream(dev: torch.device) -> torch.cuda.Stream:
 
 def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossConfig = LossConfig(),
                         dcfg: DecodeConfig = DecodeConfig(), out: Optional[dict] = None,
-                        want_rects: bool = False, parallel: bool = True) -> dict:
+                        want_rects: bool = False, parallel: bool = True, schedule: Optional[str] = None) -> dict:
     """The head step: loss fwd+bwd and decode of the same logits.
 
-    parallel=True (default): the two pipelines are independent chains of small kernels, so after the
-    decode's first kernel they run on two streams (fork/join with events; under CUDA-graph capture
-    this becomes two parallel branches).
+    parallel=True (default): the two pipelines are independent chains of kernels and run on two streams
+    (fork/join with events; under CUDA-graph capture this becomes two parallel branches).
+      schedule "fork" (default): both chains start at once — decode (flags, components, boxes) on
+        the auxiliary stream, loss (selection, main pass) on the caller's.
+      schedule "tile_first": the round-1 interleaving for the tiled decode — its threshold + tile-labelling
+        kernel runs first and alone, the selection kernel launches programmatically under its tail.
     parallel=False: one stream; the loss kernel emits the 2 B/px threshold flags and the decode
     starts from them (one read of the logits instead of two).
     """
@@ -294,20 +298,25 @@ def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossCo
     out = {} if out is None else out
     cur = torch.cuda.current_stream(dev)
     aux = _aux_stream(dev)
-    aux.wait_stream(cur)
-    # The decode's threshold + tile-labelling kernel and the loss's selection kernel are both bound by
-    # integer issue and only slow each other down, so the tile pass runs first, alone (13 us); the
-    # selection kernel launches programmatically under its tail (chain_pdl), and the loss chain then runs
-    # beside the decode's latency-bound merge / flatten / label kernels.
     B, H, W = pix_logits.shape[:3]
     with torch.cuda.device(dev):
         ws = _workspace(_lib.OP_DECODE, B, H, W, dcfg.max_boxes, dev)
-    decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=4), out, want_rects, ws)
+    if schedule is None:
+        schedule = "fork" if dcfg.form == "resident" else "tile_first"
+    if schedule == "fork":
+        aux.wait_stream(cur)
+        with torch.cuda.stream(aux):
+            decode_raw(pix_logits, link_logits, dcfg, out, want_rects, ws)
+        pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg, True, False, None, out)
+        cur.wait_stream(aux)
+        return out
+    aux.wait_stream(cur)
+    decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=4, form="tiled"), out, want_rects, ws)
     aux.wait_stream(cur)
     pixellink_loss_raw(pix_logits, link_logits, pix_lab, link_lab, dataclasses.replace(lcfg, chain_pdl=True), True, False,
                        None, out)
     with torch.cuda.stream(aux):
-        decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=8), out, want_rects, ws)
+        decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=8, form="tiled"), out, want_rects, ws)
     cur.wait_stream(aux)
     return out
 

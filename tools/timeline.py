@@ -9,6 +9,10 @@ B, H, W = 32, 128, 128
 dev = torch.device("cuda", 0)
 lib = _lib.load()
 lib.plh_timeline_read.argtypes = [ctypes.c_void_p]
+try:
+    print("max active clusters of the resident component kernel:", lib.plh_debug_image_cluster_occupancy(H, W))
+except AttributeError:
+    pass
 base = synth.make_batch(2, B, H, W, "C")
 sets = []
 for s in range(6):
@@ -17,7 +21,7 @@ for s in range(6):
     sets.append(d)
 ms = torch.cuda.Stream(dev, priority=int(os.environ.get('BENCH_MAIN_PRIO', '0')))
 torch.cuda.set_stream(ms)
-lcfg, dcfg = head.LossConfig(), head.DecodeConfig(max_boxes=128)
+lcfg, dcfg = head.LossConfig(), head.DecodeConfig(max_boxes=128, form=os.environ.get("TL_FORM", "auto"))
 def step(i):
     d = sets[i % 6]
     if os.environ.get("TL_MODE", "fused") == "decode":
@@ -40,8 +44,8 @@ torch.cuda.set_stream(ms)
 for i in range(30):
     graphs[i % 6].replay()
 torch.cuda.synchronize()
-names = ["K0 keys (general path)", "K1 select", "K2 counts (split/general)", "K3 main", "D0 flags (standalone)", "D1a tile_cc", "D1b cross", "D2 flatten", "(unused)", "D4 labels", "D5 rects", "K1 preamble", "K1 loop", "K1 counted", "K1 posted"]
-acc = np.zeros((15, 2))
+names = ["K0 keys (general path)", "K1 select", "K2 counts (split/general)", "K3 main", "D0 flags (standalone)", "D1a tile_cc / cluster A", "D1b cross / cluster B", "D2 flatten / cluster C", "(unused)", "D4 labels / cluster D", "D5 rects", "K1 preamble", "K1 loop", "K1 counted", "K1 posted", "(15)", "img planes loaded", "img runs (CL/CH)", "img edges listed", "img unions", "img flattened", "img sizes", "img latest CTA start", "img latest CTA arrival", "img planes copied"]
+acc = np.zeros((len(names), 2))
 reps = 20
 for r in range(reps):
     lib.plh_timeline_reset()
@@ -49,7 +53,7 @@ for r in range(reps):
     torch.cuda.synchronize()
     buf = np.zeros(64, np.uint64)
     lib.plh_timeline_read(buf.ctypes.data_as(ctypes.c_void_p))
-    t = buf.astype(np.int64).reshape(32, 2)[:15]
+    t = buf.astype(np.int64).reshape(32, 2)[:len(names)]
     used = t[:, 1] > 0
     t0 = t[used & (t[:, 0] > 0) & (t[:, 0] < 2**62), 0].min()
     acc += np.where(used[:, None], (t - t0) / 1e3, 0.0)
