@@ -84,6 +84,14 @@ constexpr int kKeysMaxCTAsPerImage = 64;  // K0 writes one (n_pos, n_neg) pair p
 #ifndef PLH_K3_STAGES
 #define PLH_K3_STAGES 4
 #endif
+// Gradients through shared memory + bulk async stores (shared -> global) instead of per-lane streaming stores.
+// Measured on B200 (32 x 128x128): no gain alone (20.57 vs 20.6 us per launch: the main pass is not limited by
+// the LSU / issue cost of its stores) and 2.6 us slower inside the loss chain (a stage is held one tile longer),
+// so it is off by default and kept for A/B runs (-DPLH_K3_BULK_STORE=1).
+#ifndef PLH_K3_BULK_STORE
+#define PLH_K3_BULK_STORE 0
+#endif
+constexpr bool kBulkStore = PLH_K3_BULK_STORE != 0;
 constexpr int kMainThreads = 32 * PLH_K3_WARPS;   // consumer threads
 constexpr int kMainCTAsPerSM = PLH_K3_CTAS_PER_SM;
 constexpr int kMainMaxCTAs = kNumSMs * kMainCTAsPerSM;
@@ -671,10 +679,13 @@ __device__ __forceinline__ void term_and_grad(float x0, float x1, bool lab1, flo
   }
 }
 
+// model.py:213 casts the labels to int32 (truncation) before `== 1` / `== 0` (:199-202).  Same decisions from float
+// compares, which keeps the quarter-rate conversion unit out of the main pass: (int)l == 1 <=> 1 <= l < 2;
+// (int)l == 0 <=> |l| < 1, or l is NaN (the device cast gives 0 for NaN; +-inf saturate and match neither).
 template <int VARIANT>
 __device__ __forceinline__ void classify(float l, bool& p, bool& n) {
   if (VARIANT == PLH_VARIANT_PIXELLINK) p = l > 0.f, n = !p;
-  else { const int li = (int)l; p = li == 1, n = li == 0; }
+  else p = l >= 1.f && l < 2.f, n = !(fabsf(l) >= 1.f);
 }
 
 // ---- CTA totals -> header (fp64 atomics), last CTA -> the scalars.  s_red holds the consumer warps' sums.
@@ -785,11 +796,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 // one 16-pixel unit, operands already in registers (see loss_main_kernel for the lane mapping)
+// sgl / sgp: when non-null the gradients of the unit go to shared memory (the unit's own slots of its stage: the
+// gradient has the layout of the logits it was computed from) and leave with bulk async stores; else straight to
+// global memory with streaming stores.
 template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
 __device__ __forceinline__ void main_unit(const MainArgs& a, int px0, int total_px, const float4 (&L)[2],
                                           const float2 (&LB)[2], float2 P, float PLB, float MF, float pix_scale,
                                           const float (&invP)[2], const float (&invN)[2], int lane, float (&sp)[2],
-                                          float (&sn)[2], float& spx) {
+                                          float (&sn)[2], float& spx, float4* sgl = nullptr, float2* sgp = nullptr) {
   const int j = lane & 3, q_pix = lane >> 2, pl_lane = lane & 15;
   const int pp = px0 + pl_lane;
   {
@@ -801,7 +815,8 @@ __device__ __forceinline__ void main_unit(const MainArgs& a, int px0, int total_
       spx += t * MF;
       if (GRAD) {
         const float gp = (MF * pix_scale) * g1;
-        stg_stream2(reinterpret_cast<float2*>(a.grad_pix) + pp, make_float2(-gp, gp));
+        if (sgp) sgp[pl_lane] = make_float2(-gp, gp);
+        else stg_stream2(reinterpret_cast<float2*>(a.grad_pix) + pp, make_float2(-gp, gp));
       }
     }
   }
@@ -823,7 +838,8 @@ __device__ __forceinline__ void main_unit(const MainArgs& a, int px0, int total_
       if (GRAD) {
         const float a0 = (Mf * (p0 ? invP[0] : (n0 ? invN[0] : 0.f))) * g0;
         const float a1 = (Mf * (p1 ? invP[1] : (n1 ? invN[1] : 0.f))) * g1;
-        stg_stream4(reinterpret_cast<float4*>(a.grad_link) + ((size_t)px * 4 + j), make_float4(-a0, a0, -a1, a1));
+        if (sgl) sgl[it * 32 + lane] = make_float4(-a0, a0, -a1, a1);
+        else stg_stream4(reinterpret_cast<float4*>(a.grad_link) + ((size_t)px * 4 + j), make_float4(-a0, a0, -a1, a1));
       }
     }
     if (FLAGS) {
@@ -845,7 +861,9 @@ __device__ __forceinline__ void main_unit(const MainArgs& a, int px0, int total_
 template <int VARIANT, int TERM, bool GRAD, bool FLAGS>
 __global__ void __launch_bounds__(kMainBlock, kMainCTAsPerSM)
 loss_main_kernel(const MainArgs a, const int B, const int N) {
-  pdl_wait_and_release();
+  // No dependency wait at the top: the logits and labels are not written by the preceding kernel (the selection
+  // kernel, or this kernel's previous launch), so the producer fetches the first tiles of them BEFORE it waits;
+  // only the selected mask and the normalisers are the predecessor's, and they are read after the wait.
   tl_start(3);
   if (a.ts && threadIdx.x == 0) {
     unsigned long long t;
@@ -885,26 +903,37 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
     __syncwarp();
     asm volatile("bar.arrive 1, %0;" ::"r"(kMainBlock) : "memory");  // barriers are live
     if (lane == 0) {
-      for (int k = 0; k < ntiles; ++k) {
+      auto fetch = [&](int k, bool inputs, bool mask_too) {
         const int st = k % kStages;
-        mbar_wait(smem_u32(&s_empty[st]), ((k / kStages) & 1) ^ 1);  // passes at once on the first lap
         const int nu = min(kTileUnits, u_count - k * kTileUnits);
         const size_t px0 = (size_t)(u_begin + k * kTileUnits) << 4;
         const uint32_t npx = (uint32_t)nu * 16u;
         const uint32_t bar = smem_u32(&s_full[st]);
         const uint32_t base = smem_u32(stages + (size_t)st * kStageBytes);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                     "r"(npx * (kNeedMask ? 109u : 108u))
-                     : "memory");
-        bulk_g2s(base + kOffLL, a.link_logits + px0 * 16, npx * 64u, bar);
-        bulk_g2s(base + kOffLB, a.link_lab + px0 * 8, npx * 32u, bar);
-        bulk_g2s(base + kOffPL, a.pix_logits + px0 * 2, npx * 8u, bar);
-        bulk_g2s(base + kOffPB, a.pix_lab + px0, npx * 4u, bar);
-        if (kNeedMask) bulk_g2s(base + kOffMK, a.mask + px0, npx, bar);
+        if (inputs) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                       "r"(npx * (kNeedMask ? 109u : 108u))
+                       : "memory");
+          bulk_g2s(base + kOffLL, a.link_logits + px0 * 16, npx * 64u, bar);
+          bulk_g2s(base + kOffLB, a.link_lab + px0 * 8, npx * 32u, bar);
+          bulk_g2s(base + kOffPL, a.pix_logits + px0 * 2, npx * 8u, bar);
+          bulk_g2s(base + kOffPB, a.pix_lab + px0, npx * 4u, bar);
+        }
+        if (kNeedMask && mask_too) bulk_g2s(base + kOffMK, a.mask + px0, npx, bar);
+      };
+      const int nearly = min(ntiles, kStages);
+      for (int k = 0; k < nearly; ++k) fetch(k, true, false);  // the ring is empty: no wait
+      pdl_wait();                                               // the mask is the predecessor's
+      pdl_release();
+      for (int k = 0; k < nearly; ++k) fetch(k, false, true);
+      for (int k = nearly; k < ntiles; ++k) {
+        mbar_wait(smem_u32(&s_empty[k % kStages]), ((k / kStages) & 1) ^ 1);
+        fetch(k, true, true);
       }
     }
   } else {
     // ---- normalisers (final: the selection/count kernels completed before this launch)
+    pdl_wait();
     if (warp == 0) {
       const int c = batch_count(a.info, B, lane);
       if (lane < HC_COUNT) s_cnt[lane] = c;
@@ -930,15 +959,20 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
     }
   }
 
-  // ---- consumers: operands of this warp's unit from the stage, stage back to the producer, compute
+  // ---- consumers: operands of this warp's unit from the stage, stage back to the producer, compute; gradients
+  // leave through streaming 128-bit stores.  (kBulkStore: the gradients are written back INTO the unit's slots of
+  // the stage — same layout as the logits — and leave through two bulk async stores, shared -> global, 1024 +
+  // 128 B per unit, issued by lane 0; the stage then goes back to the producer one tile later, once the bulk
+  // stores of the tile have read their source.)
   float sp[2] = {0.f, 0.f}, sn[2] = {0.f, 0.f}, spx = 0.f;
   if (!producer) {
     const int pl_lane = lane & 15;
+    int held = -1;  // stage whose bulk stores are still reading shared memory
     for (int k = 0; k < ntiles; ++k) {
       const int st = k % kStages;
       const int nu = min(kTileUnits, u_count - k * kTileUnits);
       mbar_wait(smem_u32(&s_full[st]), (k / kStages) & 1);
-      const unsigned char* sb = stages + (size_t)st * kStageBytes;
+      unsigned char* sb = stages + (size_t)st * kStageBytes;
       float4 L[2];
       float2 LB[2], P;
       float PLB, MF;
@@ -954,12 +988,40 @@ loss_main_kernel(const MainArgs a, const int B, const int N) {
         MF = kNeedMask ? (float)sb[kOffMK + warp * 16 + pl_lane] : 1.f;
       }
       __syncwarp();
-      if (lane == 0)  // the stage goes back to the producer as soon as this warp holds its operands
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[st])) : "memory");
-      if (mine)
-        main_unit<VARIANT, TERM, GRAD, FLAGS>(a, (u_begin + k * kTileUnits + warp) << 4, total_px, L, LB, P, PLB, MF,
-                                              pix_scale, invP, invN, lane, sp, sn, spx);
+      if (GRAD && kBulkStore) {
+        // the previous tile's bulk stores have read their source by now: hand that stage back
+        if (held >= 0 && lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[held])) : "memory");
+        }
+        held = st;
+        if (mine) {
+          const int px0 = (u_begin + k * kTileUnits + warp) << 4;
+          float4* sgl = reinterpret_cast<float4*>(sb + kOffLL + warp * 1024);
+          float2* sgp = reinterpret_cast<float2*>(sb + kOffPL + warp * 128);
+          main_unit<VARIANT, TERM, GRAD, FLAGS>(a, px0, total_px, L, LB, P, PLB, MF, pix_scale, invP, invN, lane, sp, sn,
+                                                spx, sgl, sgp);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.grad_link + (size_t)px0 * 16),
+                         "r"(smem_u32(sgl)), "r"(1024)
+                         : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.grad_pix + (size_t)px0 * 2),
+                         "r"(smem_u32(sgp)), "r"(128)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
+        if (lane == 0)  // the stage goes back to the producer as soon as this warp holds its operands
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[st])) : "memory");
+        if (mine)
+          main_unit<VARIANT, TERM, GRAD, FLAGS>(a, (u_begin + k * kTileUnits + warp) << 4, total_px, L, LB, P, PLB, MF,
+                                                pix_scale, invP, invN, lane, sp, sn, spx);
+      }
     }
+    if (GRAD && kBulkStore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all gradient stores complete
     // the ragged last unit of the batch (total_px % 16 pixels): guarded global loads, one warp
     if ((total_px & 15) && blockIdx.x == gridDim.x - 1 && warp == 0) {
       const int px0 = nfull << 4;

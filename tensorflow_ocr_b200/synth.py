@@ -166,24 +166,58 @@ def make_batch(config: int, B: int, H: int, W: int, family: str = "G",
     return out
 
 
-def make_east_batch(config: int, B: int, H: int, W: int, first_image: int = 0):
+def make_east_batch(config: int, B: int, H: int, W: int, first_image: int = 0, consistent: bool = False):
     """EAST RBOX head inputs (config 4): score [B,H,W,1] prob, geo [B,H,W,5]
-    (4 distances + angle) for prediction and ground truth, plus training mask."""
+    (4 distances + angle) for prediction and ground truth, plus training mask.
+
+    consistent=True: the geometry of a text pixel is the distances (top, right, bottom, left, in input pixels =
+    4 x map pixels) to the sides of ITS rotated rectangle and the rectangle's angle, as the EAST label generator
+    produces them, and the prediction is that plus a few percent of noise — so that the pixels of one instance
+    restore to nearly the same quadrilateral and locality-aware NMS has its usual work.  Otherwise uniform noise."""
+    import cv2
+
     outs = dict(score_gt=[], score_pred=[], geo_gt=[], geo_pred=[], training_mask=[])
     for i in range(B):
         rng = _rng(config, first_image + i)
-        ids = make_id_map(rng, H, W)
+        if consistent:
+            ids = np.zeros((H, W), np.int32)
+            d_gt = np.ones((H, W, 4), np.float32)
+            th_gt = np.zeros((H, W, 1), np.float32)
+            yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+            scale = min(H, W) / 128.0
+            for k in range(int(rng.integers(3, 13))):
+                cx, cy = rng.uniform(0, W), rng.uniform(0, H)
+                long_side = rng.uniform(8.0, 60.0) * scale
+                hx, hy = long_side / 2.0, max(long_side / rng.uniform(2.0, 8.0) / 2.0, 0.75)
+                ang = np.deg2rad(rng.uniform(-30.0, 30.0))
+                c, s_ = np.cos(ang), np.sin(ang)
+                pts = np.array([[-hx, -hy], [hx, -hy], [hx, hy], [-hx, hy]]) @ np.array([[c, -s_], [s_, c]]).T + (cx, cy)
+                m = np.zeros((H, W), np.uint8)
+                cv2.fillPoly(m, [np.round(pts).astype(np.int32)], 1)
+                m = m > 0
+                ids[m] = k + 1
+                u = (xx - cx) * c + (yy - cy) * s_          # along the rectangle's width / height
+                v = -(xx - cx) * s_ + (yy - cy) * c
+                d = np.stack([hy + v, hx - u, hy - v, hx + u], -1) * 4.0     # top, right, bottom, left
+                d_gt[m] = np.maximum(d[m], 0.5)
+                th_gt[m] = -ang                                # image y points down
+        else:
+            ids = make_id_map(rng, H, W)
+            d_gt = rng.uniform(1.0, 40.0, (H, W, 4)).astype(np.float32)
+            th_gt = rng.uniform(-np.pi / 4, np.pi / 4, (H, W, 1)).astype(np.float32)
         gt = (ids > 0).astype(np.float32)[..., None]
         z = (2.0 * gt - 1.0) * 2.0 + 1.5 * rng.standard_normal(gt.shape)
         pred = (1.0 / (1.0 + np.exp(-z))).astype(np.float32)
-        d_gt = rng.uniform(1.0, 40.0, (H, W, 4)).astype(np.float32)
-        th_gt = rng.uniform(-np.pi / 4, np.pi / 4, (H, W, 1)).astype(np.float32)
-        d_pr = (d_gt * rng.uniform(0.6, 1.4, (H, W, 4))).astype(np.float32)
-        th_pr = (th_gt + 0.2 * rng.standard_normal((H, W, 1))).astype(np.float32)
+        if consistent:
+            d_pr = (d_gt * rng.uniform(0.97, 1.03, (H, W, 4))).astype(np.float32)
+            th_pr = (th_gt + 0.02 * rng.standard_normal((H, W, 1))).astype(np.float32)
+        else:
+            d_pr = (d_gt * rng.uniform(0.6, 1.4, (H, W, 4))).astype(np.float32)
+            th_pr = (th_gt + 0.2 * rng.standard_normal((H, W, 1))).astype(np.float32)
         tm = (rng.uniform(size=(H, W, 1)) > 0.05).astype(np.float32)
         outs["score_gt"].append(gt)
         outs["score_pred"].append(pred)
-        outs["geo_gt"].append(np.concatenate([d_gt, th_gt], -1))
-        outs["geo_pred"].append(np.concatenate([d_pr, th_pr], -1))
+        outs["geo_gt"].append(np.concatenate([d_gt, th_gt], -1).astype(np.float32))
+        outs["geo_pred"].append(np.concatenate([d_pr, th_pr], -1).astype(np.float32))
         outs["training_mask"].append(tm)
     return {k: np.ascontiguousarray(np.stack(v)) for k, v in outs.items()}
