@@ -597,8 +597,6 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     wl = get_workload(args.config)
@@ -659,6 +657,9 @@ def run_gpu(args):
 
     # ---- one CUDA graph per input set, and one graph holding a whole round of NSETS consecutive steps (a graph
     # launch costs the host ~10-20 us and the device a ~2.5 us gap, a visible fraction of a ~60 us step)
+    # (with the per-step collective a round is two passes over the sets: the side branch has to rejoin at the end
+    # of a captured graph, and that one wait is then shared by 12 steps)
+    ROUND = NSETS * (2 if use_coll else 1)
     graphs, round_graph = None, None
     if not args.no_graphs:
         graphs = []
@@ -672,17 +673,17 @@ def run_gpu(args):
         if not os.environ.get("BENCH_STEP_GRAPHS"):
             round_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(round_graph, stream=main_stream):
-                for i in range(NSETS):
-                    step(i, join=(i == NSETS - 1))
+                for i in range(ROUND):
+                    step(i, join=(i == ROUND - 1))
             torch.cuda.synchronize()
             torch.cuda.set_stream(main_stream)
 
     def run_steps(first, n):
         i = first
         while i < first + n:
-            if round_graph is not None and i % NSETS == 0 and i + NSETS <= first + n:
+            if round_graph is not None and i % NSETS == 0 and i + ROUND <= first + n:
                 round_graph.replay()
-                i += NSETS
+                i += ROUND
             else:
                 if graphs is not None:
                     graphs[i % NSETS].replay()
@@ -825,7 +826,7 @@ def run_gpu(args):
             "cuda_graphs": graphs is not None,
             "us_per_step_per_rank": [round(t / args.steps * 1e3, 2) for t in per_rank_ms],
             "host_enqueue_us_per_step": round(host_us_per_step, 2),
-            "steps_per_graph_launch": NSETS if round_graph is not None else 1,
+            "steps_per_graph_launch": ROUND if round_graph is not None else 1,
             "launches_per_step": launches_per_step,
             "collective": ("NCCL all-reduce of the 64 loss scalars EVERY step, captured inside the step's CUDA graph "
                            "(side branch)") if use_coll else "none"})
@@ -846,7 +847,20 @@ def run_gpu(args):
                                               "one process, %.1f s)" % (sample, nsteps, dt)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear down in order: graphs that hold captured NCCL work first, then the process group.  A watchdog ends
+        # the process if the communicator teardown does not return (seen with captured collectives): the line above
+        # is already out.
+        sys.stdout.flush()
+        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        del round_graph, graphs
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 def main():

@@ -210,6 +210,28 @@ PLH_API int plh_decode_from_flags(const uint16_t* flags, int B, int H, int W, co
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Contour path of the decode, test.py:182-218: cv2.findContours(mask, RETR_TREE, CHAIN_APPROX_SIMPLE) — hole
+ * borders included (quirk Q14) — then per contour cv2.minAreaRect -> cv2.boxPoints -> np.int0, x4, /ratio_w,
+ * /ratio_h (assigned into an integer array: truncation, test.py:193-200) and order_points (test.py:24-35, :217).
+ *  mask      [B,H,W] uint8 (device), nonzero = text (the output of plh_pixel_detect)
+ *  boxes     [B,K,4,2] int32: the ordered box of contour slot k (tl, tr, br, bl)
+ *  raw_boxes [B,K,4,2] int32 optional: the box before order_points (what test.py draws)
+ *  info      [B,K,6] int32 per slot: scan position y*W+x at which OpenCV's raster scan finds the border, hole
+ *            flag, own key, parent key (-1 = top level), first point in `points`, number of points.  Slots are
+ *            in arrival order; OpenCV's output order is the pre-order of the border tree with siblings in
+ *            reverse scan order (tensorflow_ocr_b200/decode.py:contour_boxes puts them in that order).
+ *  n_contours [B] int32: number of borders found (may exceed K: then only K slots are written)
+ *  points    [B, 2*H*W, 2] int32 optional: the CHAIN_APPROX_SIMPLE points (x, y) of every border (else they
+ *            live in the workspace).  Limits: H <= 1020, W <= 2044; a border with more than 2048 points gets
+ *            the sentinel box INT32_MIN.
+ *  workspace: plh_contour_workspace_bytes(B, H, W).
+ */
+PLH_API size_t plh_contour_workspace_bytes(int B, int H, int W);
+PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double ratio_w, double ratio_h, int K,
+                      int32_t* boxes, int32_t* raw_boxes, int32_t* info, int32_t* n_contours, int32_t* points,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * The threshold pass of the decode alone (test_pixellink_fast.py:120-128): flags[b,y,x] = bit 8: pixel
  * score > pixel_thresh, bits 0..7: link d score > link_thresh, for plh_decode_from_flags.  Lets a caller
  * schedule this bandwidth-bound pass separately from the latency-bound component labelling.

@@ -1053,7 +1053,9 @@ static int decode_common(const uint16_t* flags_in, const float* pix_logits, cons
   const long long total_px = (long long)B * H * W;
   const int N = H * W;
   int rc;
-  const int grid_px = (int)std::min<long long>((total_px + 255) / 256, kNumSMs * 16);
+  // pixel-parallel passes: a thread's grid-stride iterations are dependent L2 round trips in sequence, so large
+  // batches get more CTAs rather than more iterations (at most ~2 pixels per thread)
+  const int grid_px = (int)std::min<long long>((total_px + 255) / 256, std::max<long long>(kNumSMs * 16, (total_px + 511) / 512));
   const bool skip_rects = (p->reserved[0] & 1) != 0;  // components + label map only
   const bool rects_only = (p->reserved[0] & 2) != 0;  // boxes from a workspace prepared by a skip_rects call
   const bool tile_only = (p->reserved[0] & 4) != 0;   // stop after the threshold + tile-labelling kernel
@@ -1148,6 +1150,17 @@ rects:
     if (rc) return rc;
   }
   return PLH_OK;
+}
+
+// Component labels of ready-made flag maps, nothing else (the contour path labels the foreground and the
+// background of a binary mask with it): tiled form, every component kept, no boxes.
+int decode_labels_only(const uint16_t* flags, int B, int H, int W, int32_t* labels, int32_t* n_boxes, int32_t* scratch_boxes,
+                       void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  plh_decode_params p = {};
+  p.pixel_thresh = 0.5f, p.link_thresh = 0.5f, p.min_size = 0, p.max_boxes = 1, p.scale_x = 1.0, p.scale_y = 1.0;
+  p.reserved[0] = 1;  // components + label map only
+  return decode_common(flags, nullptr, nullptr, B, H, W, &p, labels, scratch_boxes, n_boxes, nullptr, nullptr, workspace,
+                       workspace_bytes, s);
 }
 
 #ifdef PLH_TIMELINE

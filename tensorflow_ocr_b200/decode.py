@@ -12,7 +12,8 @@ import torch
 from . import head
 from .tool.pixellink_fn import pixel_detect as _pixel_detect_fn
 
-__all__ = ["decode_pixellink", "pixel_detect", "order_points", "sort_poly", "write_result_txt"]
+__all__ = ["decode_pixellink", "pixel_detect", "contour_boxes", "cv_contour_order", "order_points", "sort_poly",
+           "write_result_txt"]
 
 
 def decode_pixellink(pixel_logits, link_logits, pixel_thresh=0.8, link_thresh=0.9, min_size=10,
@@ -70,6 +71,65 @@ def pixel_detect(score_map, geo_map, score_map_thresh=0.8, link_thresh=0.8):
     g = gm[0].reshape(H, W, 8, 2).permute(2, 0, 1, 3).unsqueeze(1).contiguous()  # [8,1,H,W,2]
     out = _pixel_detect_fn(sm, g, score_map_thresh, link_thresh)
     return out.cpu().numpy() if np_in else out
+
+
+def cv_contour_order(info):
+    """OpenCV's output order of cv2.findContours(..., RETR_TREE, ...) for the borders of one image, from the
+    `info` rows of plh_contour_boxes (scan position, hole flag, own key, parent key, ...): pre-order of the border
+    tree, siblings in REVERSE order of discovery by the raster scan.  Returns (order, parents): indices into
+    `info`, and each contour's hierarchy parent as a position in that order (-1 = top level)."""
+    info = np.asarray(info)
+    disc = np.argsort(info[:, 0], kind="stable")          # discovery order = scan position
+    slot_of_key = {int(info[k, 2]): int(k) for k in disc}
+    children = {}
+    for k in disc:
+        children.setdefault(slot_of_key.get(int(info[k, 3]), -1) if info[k, 3] >= 0 else -1, []).append(int(k))
+    order = []
+    stack = [(-1, iter(reversed(children.get(-1, []))))]
+    while stack:
+        try:
+            k = next(stack[-1][1])
+        except StopIteration:
+            stack.pop()
+            continue
+        order.append(k)
+        stack.append((k, iter(reversed(children.get(k, [])))))
+    pos = {k: n for n, k in enumerate(order)}
+    parents = [(-1 if info[k, 3] < 0 else pos[slot_of_key[int(info[k, 3])]]) for k in order]
+    return order, parents
+
+
+def contour_boxes(mask, ratio_w=1.0, ratio_h=1.0, max_contours=1024, ordered=True, return_contours=False):
+    """The contour path of test.py:182-218 on the GPU: cv2.findContours(mask, RETR_TREE, CHAIN_APPROX_SIMPLE)
+    (hole borders included, quirk Q14) -> per contour np.int0(cv2.boxPoints(cv2.minAreaRect(.))) -> x4 ->
+    /ratio_w, /ratio_h (truncating) -> order_points (the form test.py:217 writes; ordered=False: the box as
+    test.py:193-201 leaves it).
+
+    mask uint8 [H,W] or [B,H,W] (numpy or CUDA tensor; the output of pixel_detect).  Returns, per image, an
+    int32 array [n,4,2] in OpenCV's contour order — and with return_contours=True also the list of contours
+    (int32 [m,1,2], CHAIN_APPROX_SIMPLE points) like cv2.findContours returns them."""
+    m, np_in = head.to_device(mask, torch.uint8)
+    single = m.dim() == 2
+    if single:
+        m = m.unsqueeze(0)
+    out = head.contour_boxes_raw(m, ratio_w, ratio_h, max_contours, want_points=return_contours)
+    n = out["n_contours"].cpu().numpy()
+    if (n > max_contours).any():
+        raise ValueError("an image has %d contours; raise max_contours (=%d)" % (int(n.max()), max_contours))
+    info = out["info"].cpu().numpy()
+    boxes = out["boxes" if ordered else "raw_boxes"].cpu().numpy()
+    pts = out["points"].cpu().numpy() if return_contours else None
+    res_b, res_c = [], []
+    for b in range(len(n)):
+        order, _ = cv_contour_order(info[b, : n[b]])
+        res_b.append(boxes[b, order].reshape(-1, 4, 2))
+        if return_contours:
+            res_c.append([pts[b, info[b, k, 4]: info[b, k, 4] + info[b, k, 5]].reshape(-1, 1, 2).copy() for k in order])
+    if not np_in:
+        res_b = [torch.as_tensor(x, device=m.device) for x in res_b]
+    if single:
+        return (res_b[0], res_c[0]) if return_contours else res_b[0]
+    return (res_b, res_c) if return_contours else res_b
 
 
 def order_points(pts):

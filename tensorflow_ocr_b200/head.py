@@ -21,7 +21,7 @@ from . import _lib
 
 __all__ = ["DecodeConfig", "LossConfig", "pixellink_loss_raw", "decode_raw", "loss_and_decode_raw",
            "ohnm_batch_raw", "dice_raw", "dice_head_raw", "east_loss_raw", "restore_rectangle_raw",
-           "pixel_detect_raw", "min_area_boxes_raw", "lanms_raw", "to_device", "launch_count"]
+           "pixel_detect_raw", "min_area_boxes_raw", "lanms_raw", "contour_boxes_raw", "to_device", "launch_count"]
 
 
 # ----------------------------------------------------------------------------- configuration
@@ -318,6 +318,35 @@ def loss_and_decode_raw(pix_logits, link_logits, pix_lab, link_lab, lcfg: LossCo
     with torch.cuda.stream(aux):
         decode_raw(pix_logits, link_logits, dataclasses.replace(dcfg, phase=8, form="tiled"), out, want_rects, ws)
     cur.wait_stream(aux)
+    return out
+
+
+def contour_boxes_raw(mask: torch.Tensor, ratio_w: float = 1.0, ratio_h: float = 1.0, max_contours: int = 1024,
+                      want_points: bool = False) -> dict:
+    """plh_contour_boxes: mask uint8 [B,H,W] (CUDA) -> boxes / raw_boxes int32 [B,K,4,2], info int32 [B,K,6],
+    n_contours int32 [B] (slots in arrival order), points int32 [B,2*H*W,2] if asked for."""
+    lib = _lib.load()
+    if mask.dtype != torch.uint8 or mask.dim() != 3:
+        raise ValueError("mask must be uint8 [B,H,W]")
+    dev = mask.device
+    _require_gpu(dev)
+    mask = mask.contiguous()
+    B, H, W = mask.shape
+    K = int(max_contours)
+    out = {"boxes": torch.empty((B, K, 4, 2), dtype=torch.int32, device=dev),
+           "raw_boxes": torch.empty((B, K, 4, 2), dtype=torch.int32, device=dev),
+           "info": torch.empty((B, K, 6), dtype=torch.int32, device=dev),
+           "n_contours": torch.empty((B,), dtype=torch.int32, device=dev),
+           "points": torch.empty((B, 2 * H * W, 2), dtype=torch.int32, device=dev) if want_points else None}
+    n = lib.plh_contour_workspace_bytes(B, H, W)
+    if n == 0:
+        raise ValueError("bad shape for the contour workspace: B=%d H=%d W=%d" % (B, H, W))
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_contour_boxes(_p(mask), B, H, W, float(ratio_w), float(ratio_h), K, _p(out["boxes"]),
+                                   _p(out["raw_boxes"]), _p(out["info"]), _p(out["n_contours"]), _p(out["points"]),
+                                   _p(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "plh_contour_boxes")
     return out
 
 

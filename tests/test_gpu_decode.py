@@ -334,3 +334,57 @@ def test_decode_phase_bits_compose(cuda_dev):
     assert np.array_equal(out["labels"].cpu().numpy(), whole["labels"].cpu().numpy())
     for b in range(3):
         assert np.array_equal(out["boxes"][b, :nb[b]].cpu().numpy(), whole["boxes"][b, :nb[b]].cpu().numpy())
+
+
+def test_contour_path_vs_cv2(cuda_dev):
+    """N2 / D4: the contour path of test.py:182-218 on the GPU against OpenCV itself: the CHAIN_APPROX_SIMPLE point
+    sequence of every border (outer and hole) in cv2's output order, and the boxes after minAreaRect / boxPoints
+    / int0 / x4 / truncating division by the ratios, before and after order_points."""
+    import cv2
+    from oracle import decode as D
+    from tensorflow_ocr_b200.decode import contour_boxes
+    from test_contours import random_masks
+    nc = 0
+    for t, m in enumerate(random_masks(60, seed=7, hmax=70, wmax=90)):
+        rw, rh = [(1.0, 1.0), (0.8, 0.75), (1.6, 1.28)][t % 3]
+        cs, _ = cv2.findContours(m.copy(), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        raw, conts = contour_boxes(m, rw, rh, max_contours=4096, ordered=False, return_contours=True)
+        assert len(conts) == len(cs)
+        for a, b in zip(conts, cs):
+            assert np.array_equal(a, b)
+        ref = D.contour_boxes(m, rw, rh)                    # test.py:182-201 with the container's cv2
+        assert len(ref) == len(raw)
+        for a, b in zip(raw, ref):
+            assert np.array_equal(a, b), (t, a.tolist(), b.tolist())
+        ordered = contour_boxes(m, rw, rh, max_contours=4096)
+        for a, b in zip(ordered, ref):
+            assert np.array_equal(a, D.order_points(b))     # test.py:217
+        nc += len(cs)
+    assert nc > 1000
+
+
+def test_contour_path_batched_text_masks(cuda_dev):
+    """Batched, on masks shaped like the path's real input: pixel_detect outputs of synthetic PixelLink maps."""
+    import cv2
+    import torch
+    from oracle import decode as D
+    from oracle.pixellink_loss import softmax2
+    from tensorflow_ocr_b200 import synth
+    from tensorflow_ocr_b200.decode import contour_boxes
+    B, H, W = 4, 128, 128
+    inp = synth.make_batch(33, B, H, W, "G")
+    masks = []
+    for b in range(B):
+        score = softmax2(inp["pix_logits"][b])[None, :, :, 1:2]
+        link = softmax2(inp["link_logits"][b].reshape(H, W, 8, 2)).transpose(2, 0, 1, 3)[:, None]
+        masks.append(D.pixel_detect(score, link, 0.6, 0.3))
+    masks = np.stack(masks)
+    got = contour_boxes(torch.as_tensor(masks).to(cuda_dev), 0.9, 0.8, max_contours=4096)
+    n = 0
+    for b in range(B):
+        ref = D.contour_boxes(masks[b], 0.9, 0.8)
+        assert len(ref) == len(got[b])
+        for a, r in zip(got[b].cpu().numpy(), ref):
+            assert np.array_equal(a, D.order_points(r))
+        n += len(ref)
+    assert n > 20
