@@ -595,7 +595,21 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = None
     if world > 1:
+        # pin the rank to the CPUs NVML reports as local to its GPU before any pinned host buffer is allocated
+        # (first touch then places the staging buffers on the GPU's NUMA node)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa_note = "cpus %d-%d" % (min(cpus), max(cpus))
+        except Exception as e:      # not fatal: the box may hide the topology
+            numa_note = "affinity not set (%s)" % type(e).__name__
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -828,6 +842,7 @@ def run_gpu(args):
             "host_enqueue_us_per_step": round(host_us_per_step, 2),
             "steps_per_graph_launch": ROUND if round_graph is not None else 1,
             "launches_per_step": launches_per_step,
+            "cpu_affinity_rank0": numa_note,
             "collective": ("NCCL all-reduce of the 64 loss scalars EVERY step, captured inside the step's CUDA graph "
                            "(side branch)") if use_coll else "none"})
         line = {

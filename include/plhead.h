@@ -210,6 +210,19 @@ PLH_API int plh_decode_from_flags(const uint16_t* flags, int B, int H, int W, co
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Link labels of the EAST-fork generator, datasets/icdar.py:83-105 valid_link + :486-539 generate_rbox (the one
+ * train.sh uses), with its quirks kept (Q17: direction names move the other axis, x is tested against h-1,
+ * index -1 wraps, a link asks "is the neighbour text so far", polygons filled in order).
+ *  last_ids / first_ids [B,H,W] int32: 1-based index of the last / first polygon covering the pixel (0 =
+ *            background); H == W (the reference indexes out of range otherwise)
+ *  stride    1, or 4 for the [::4, ::4] subsample of icdar.py:632-634 (outputs are [B, ceil(H/stride), ceil(W/stride), .])
+ *  link_lab  [B,Ho,Wo,8] float: left, left_down, left_up, right, right_down, right_up, up, down
+ *  score     [B,Ho,Wo] float optional: score_map (1 where some polygon covers the pixel)
+ */
+PLH_API int plh_link_labels_icdar(const int32_t* last_ids, const int32_t* first_ids, int B, int H, int W, int stride,
+                          float* link_lab, float* score, void* stream);
+
+/*
  * Contour path of the decode, test.py:182-218: cv2.findContours(mask, RETR_TREE, CHAIN_APPROX_SIMPLE) — hole
  * borders included (quirk Q14) — then per contour cv2.minAreaRect -> cv2.boxPoints -> np.int0, x4, /ratio_w,
  * /ratio_h (assigned into an integer array: truncation, test.py:193-200) and order_points (test.py:24-35, :217).

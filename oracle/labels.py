@@ -68,3 +68,47 @@ def generate_rbox(h, w, xs, ys, bboxes, ignored):
     res_score = cv2.resize(score_map, (new_w, new_h), interpolation=cv2.INTER_NEAREST)
     pm = cv2.resize(poly_mask, (new_w, new_h), interpolation=cv2.INTER_NEAREST)
     return res_score, link_labels_from_ids(pm), show_bboxes, pm
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# datasets/icdar.py:83-105 valid_link + :486-539 generate_rbox — the EAST-fork generator (quirk Q17), pinned by
+# tests/golden/icdar_generate_rbox.npz (the reference's own source executed).
+ICDAR_DIRS = [(0, -1), (1, -1), (-1, -1), (0, 1), (1, 1), (-1, 1), (-1, 0), (1, 0)]   # (dx, dy) AS THE CODE MOVES
+
+
+def icdar_link_labels(last_ids, first_ids):
+    """Link labels from the last-cover / first-cover polygon index maps (see csrc/aux.cu for why these two maps
+    state the order-dependent loop of generate_rbox exactly).  Square maps."""
+    L = np.asarray(last_ids)
+    F = np.asarray(first_ids)
+    h, w = L.shape
+    assert h == w
+    out = np.zeros((h, w, 8), np.float32)
+    ys, xs = np.nonzero(L)
+    k = L[ys, xs]
+    edge = (xs == h - 1) | (ys == w - 1)
+    for d, (dx, dy) in enumerate(ICDAR_DIRS):
+        qx, qy = (xs + dx) % w, (ys + dy) % h          # -1 wraps like numpy; the far side never occurs (edge rule)
+        f = F[qy, qx]
+        out[ys, xs, d] = np.where(edge, 1.0, ((f != 0) & (f <= k)).astype(np.float32))
+    return out
+
+
+def icdar_generate_rbox(im_size, polys, tags, min_text_size=10):
+    """datasets/icdar.py:486-539 restated with the two-map form."""
+    import cv2
+    h, w = im_size
+    last = np.zeros((h, w), np.int32)
+    first = np.zeros((h, w), np.int32)
+    training_mask = np.ones((h, w), np.uint8)
+    polys = np.asarray(polys)
+    quads = [np.asarray(p).astype(np.int32)[np.newaxis] for p in polys]
+    for k, (poly, tag) in enumerate(zip(polys, tags)):
+        cv2.fillPoly(last, quads[k], k + 1)
+        poly_h = min(np.linalg.norm(poly[0] - poly[3]), np.linalg.norm(poly[1] - poly[2]))
+        poly_w = min(np.linalg.norm(poly[0] - poly[1]), np.linalg.norm(poly[2] - poly[3]))
+        if min(poly_h, poly_w) < min_text_size or tag:
+            cv2.fillPoly(training_mask, quads[k], 0)
+    for k in range(len(quads) - 1, -1, -1):
+        cv2.fillPoly(first, quads[k], k + 1)
+    return (last > 0).astype(np.uint8), icdar_link_labels(last, first), training_mask

@@ -51,6 +51,7 @@ SIGNATURES = {
     "plh_east_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _sz, _vp]),
     "plh_lanms": (_i, [_vp, _vp, _i, _i, C.c_double, _vp, _vp, _vp, _sz, _vp]),
     "plh_link_labels": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "plh_link_labels_icdar": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "plh_contour_workspace_bytes": (_sz, [_i, _i, _i]),
     "plh_contour_boxes": (_i, [_vp, _i, _i, _i, C.c_double, C.c_double, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "plh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

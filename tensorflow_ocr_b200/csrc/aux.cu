@@ -411,9 +411,69 @@ link_labels_kernel(const uint8_t* __restrict__ ids, int H, int W, long long tota
   }
 }
 
+// ------------------------------------------------------------------ link labels, EAST-fork generator
+// datasets/icdar.py:83-105 valid_link + :486-539 generate_rbox (the generator train.sh actually uses), as the
+// code stands (quirk Q17): the direction names move the OTHER axis ('up' is x-1, 'left' is y-1, ...), the
+// early return tests x against h-1 and y against w-1 (square maps only), an index of -1 wraps to the far side,
+// and a link asks whether the neighbour is text in score_map AS IT IS when the pixel's polygon is processed:
+// polygons are filled in order and a pixel is (re)labelled by every polygon that covers it, so the value that
+// stays is the one of its LAST covering polygon k, for which the neighbour counts iff some polygon <= k covers
+// it.  Inputs: last[y][x] = 1-based index of the last polygon covering the pixel (poly_mask), first[y][x] = of
+// the first one (0 = background); outputs at every `stride`-th pixel (icdar.py:632-634 keeps [::4, ::4]).
+// Channel order: left, left_down, left_up, right, right_down, right_up, up, down — as (dx, dy) of the code:
+__constant__ int c_idx[8] = {0, 1, -1, 0, 1, -1, -1, 1};
+__constant__ int c_idy[8] = {-1, -1, -1, 1, 1, 1, 0, 0};
+
+__global__ void __launch_bounds__(256)
+link_labels_icdar_kernel(const int32_t* __restrict__ last, const int32_t* __restrict__ first, int B, int H, int W,
+                         int stride, float* __restrict__ link_lab, float* __restrict__ score) {
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const long long total = (long long)B * Ho * Wo;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / ((long long)Ho * Wo));
+    const int r = (int)(g - (long long)b * Ho * Wo);
+    const int y = (r / Wo) * stride, x = (r % Wo) * stride;
+    const int32_t* L = last + (size_t)b * H * W;
+    const int32_t* F = first + (size_t)b * H * W;
+    const int k = L[(size_t)y * W + x];
+    float l[8];
+    if (k == 0) {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) l[d] = 0.f;
+    } else if (x == H - 1 || y == W - 1) {   // icdar.py:84 `point[0] == h - 1 or point[1] == w - 1`
+#pragma unroll
+      for (int d = 0; d < 8; ++d) l[d] = 1.f;
+    } else {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        int qx = x + c_idx[d], qy = y + c_idy[d];
+        qx = qx < 0 ? qx + W : qx, qy = qy < 0 ? qy + H : qy;   // numpy's negative index
+        const int f = F[(size_t)qy * W + qx];
+        l[d] = (f != 0 && f <= k) ? 1.f : 0.f;
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(link_lab) + g * 2;
+    stg_stream4(o, make_float4(l[0], l[1], l[2], l[3]));
+    stg_stream4(o + 1, make_float4(l[4], l[5], l[6], l[7]));
+    if (score) score[g] = k != 0 ? 1.f : 0.f;
+  }
+}
+
 }  // namespace plh
 
 using namespace plh;
+
+extern "C" int plh_link_labels_icdar(const int32_t* last_ids, const int32_t* first_ids, int B, int H, int W, int stride,
+                                     float* link_lab, float* score, void* stream) {
+  if (!last_ids || !first_ids || !link_lab) return PLH_E_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || stride <= 0 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
+  if (H != W) return PLH_E_SHAPE;   // the reference indexes out of range on non-square maps (quirk Q17)
+  if (!aligned16(link_lab)) return PLH_E_ALIGN;
+  const long long total = (long long)B * ((H + stride - 1) / stride) * ((W + stride - 1) / stride);
+  const int grid = (int)std::min<long long>((total + 255) / 256, kNumSMs * 16);
+  link_labels_icdar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(last_ids, first_ids, B, H, W, stride, link_lab, score);
+  return launch_status();
+}
 
 extern "C" int plh_dice(const float* y_true, const float* y_pred, const float* mask, long long M, float* out,
                         float* grad, void* workspace, size_t workspace_bytes, void* stream) {

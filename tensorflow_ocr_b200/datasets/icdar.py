@@ -3,7 +3,7 @@ from __future__ import annotations
 
 from .. import head
 
-__all__ = ["restore_rectangle_rbox", "restore_rectangle"]
+__all__ = ["restore_rectangle_rbox", "restore_rectangle", "rasterize_polygons", "generate_rbox", "generate_rbox_4s"]
 
 
 def _float_dtype(x):
@@ -33,3 +33,49 @@ def restore_rectangle_rbox(origin, geometry, return_index=False):
 def restore_rectangle(origin, geometry):
     """datasets/icdar.py:482-483."""
     return restore_rectangle_rbox(origin, geometry)
+
+
+def rasterize_polygons(im_size, polys, tags, min_text_size=10):
+    """Host part of generate_rbox (datasets/icdar.py:486-514): cv2.fillPoly of every polygon, in order, with the
+    same float -> int32 truncation of the vertices.  Returns last_ids (poly_mask: index of the LAST polygon
+    covering a pixel), first_ids (index of the FIRST one: which pixels are text once polygons 0..k are in) and
+    training_mask (0 inside polygons that are tagged or smaller than min_text_size, FLAGS.min_text_size :25)."""
+    import cv2
+    import numpy as np
+    h, w = int(im_size[0]), int(im_size[1])
+    last = np.zeros((h, w), np.int32)
+    first = np.zeros((h, w), np.int32)
+    training_mask = np.ones((h, w), np.uint8)
+    polys = np.asarray(polys)
+    quads = [np.asarray(p).astype(np.int32)[np.newaxis, :, :] for p in polys]
+    for k, (poly, tag) in enumerate(zip(polys, tags)):
+        cv2.fillPoly(last, quads[k], k + 1)
+        poly_h = min(np.linalg.norm(poly[0] - poly[3]), np.linalg.norm(poly[1] - poly[2]))
+        poly_w = min(np.linalg.norm(poly[0] - poly[1]), np.linalg.norm(poly[2] - poly[3]))
+        if min(poly_h, poly_w) < min_text_size or tag:
+            cv2.fillPoly(training_mask, quads[k], 0)
+    for k in range(len(quads) - 1, -1, -1):          # earliest polygon wins
+        cv2.fillPoly(first, quads[k], k + 1)
+    return last, first, training_mask
+
+
+def _generate(im_size, polys, tags, min_text_size, stride):
+    import numpy as np
+    import torch
+    last, first, training_mask = rasterize_polygons(im_size, polys, tags, min_text_size)
+    dev = head._require_gpu()
+    link, score = head.link_labels_icdar_raw(torch.as_tensor(last[None]).to(dev), torch.as_tensor(first[None]).to(dev), stride)
+    return score[0].cpu().numpy().astype(np.uint8), link[0].cpu().numpy(), training_mask[::stride, ::stride]
+
+
+def generate_rbox(im_size, polys, tags, min_text_size=10):
+    """datasets/icdar.py:486-539: (score_map uint8 [h,w], geo_map float32 [h,w,8] = the 8 link labels,
+    training_mask uint8 [h,w]).  The per-pixel valid_link loop (~10^5 interpreted calls per image) runs on the
+    GPU; quirks of the original kept (Q17), square maps only."""
+    return _generate(im_size, polys, tags, min_text_size, 1)
+
+
+def generate_rbox_4s(im_size, polys, tags, min_text_size=10):
+    """What the batch generator keeps of it (datasets/icdar.py:632-634): score_map[::4, ::4], geo_map[::4, ::4, :],
+    training_mask[::4, ::4] — computed at those pixels only."""
+    return _generate(im_size, polys, tags, min_text_size, 4)

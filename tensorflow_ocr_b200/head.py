@@ -367,6 +367,26 @@ def link_labels_raw(ids: torch.Tensor, want_pixel: bool = True):
     return link, pix
 
 
+def link_labels_icdar_raw(last_ids: torch.Tensor, first_ids: torch.Tensor, stride: int = 1):
+    """plh_link_labels_icdar: id maps int32 [B,H,W] (CUDA) -> (link fp32 [B,Ho,Wo,8], score fp32 [B,Ho,Wo])."""
+    lib = _lib.load()
+    if last_ids.dtype != torch.int32 or first_ids.dtype != torch.int32 or last_ids.dim() != 3 or last_ids.shape != first_ids.shape:
+        raise ValueError("id maps must be int32 [B,H,W] of the same shape")
+    dev = last_ids.device
+    _require_gpu(dev)
+    B, H, W = last_ids.shape
+    if H != W:
+        raise ValueError("datasets/icdar.py valid_link indexes out of range on non-square maps (quirk Q17)")
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    link = torch.empty((B, Ho, Wo, 8), dtype=torch.float32, device=dev)
+    score = torch.empty((B, Ho, Wo), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_link_labels_icdar(_p(last_ids.contiguous()), _p(first_ids.contiguous()), B, H, W, int(stride), _p(link),
+                                       _p(score), _stream(dev))
+    _lib.check(rc, "plh_link_labels_icdar")
+    return link, score
+
+
 def min_area_boxes_raw(pts: torch.Tensor, offsets: torch.Tensor, want_rects=True):
     """plh_min_area_boxes: pts int32 [total,2], offsets int32 [n+1] -> boxes int32 [n,4,2], rects [n,5]."""
     lib = _lib.load()

@@ -421,6 +421,35 @@ def _pack_case(tag, H, W, P, L, ns, min_size, scale):
             tag + "_scale": np.asarray(scale, np.float64), tag + "_n_groups": gid - 1}
 
 
+def golden_icdar_generate_rbox():
+    """datasets/icdar.py valid_link (:83-105) and generate_rbox (:486-539) executed as written (FLAGS.min_text_size
+    = 10, :25), on overlapping polygons (the loop is order dependent) that touch all four borders (index -1 wraps;
+    x == h-1 / y == w-1 return early), plus the [::4, ::4] subsample of :632-634."""
+    import cv2
+    ns = dict(np=np, cv2=cv2, FLAGS=types.SimpleNamespace(min_text_size=10))
+    for fn in ("valid_link", "generate_rbox"):
+        src, span = cut("datasets/icdar.py", fn)
+        print("datasets/icdar.py", fn, span)
+        exec(src, ns)
+    rng = np.random.default_rng(21)
+    out = {}
+    for ci, (size, n) in enumerate([(64, 5), (96, 9), (128, 12)]):
+        polys = []
+        for i in range(n):
+            c = rng.uniform(-0.05, 1.05, 2) * size
+            a = rng.uniform(-0.7, 0.7)
+            hw, hh = rng.uniform(0.05, 0.35) * size, rng.uniform(0.02, 0.15) * size
+            R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+            polys.append((np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T + c).astype(np.float32))
+        polys = np.stack(polys)
+        tags = rng.uniform(size=n) < 0.3
+        score, geo, tm = ns["generate_rbox"]((size, size), polys, tags)
+        out.update({"size%d" % ci: size, "polys%d" % ci: polys, "tags%d" % ci: tags, "score%d" % ci: score,
+                    "geo%d" % ci: geo, "tmask%d" % ci: tm, "geo4s%d" % ci: geo[::4, ::4, :].astype(np.float32),
+                    "score4s%d" % ci: score[::4, ::4].astype(np.float32), "tmask4s%d" % ci: tm[::4, ::4].astype(np.float32)})
+    save("icdar_generate_rbox", n_cases=3, **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     only = sys.argv[1] if len(sys.argv) > 1 else None
@@ -428,6 +457,8 @@ if __name__ == "__main__":
         golden_generate_rbox()
     elif only == "link_graph":
         golden_link_graph()
+    elif only == "icdar":
+        golden_icdar_generate_rbox()
     else:
         golden_model_loss()
         golden_vgg16()
@@ -435,3 +466,4 @@ if __name__ == "__main__":
         golden_numpy_pieces()
         golden_generate_rbox()
         golden_link_graph()
+        golden_icdar_generate_rbox()

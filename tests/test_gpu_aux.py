@@ -177,3 +177,32 @@ def test_link_labels_vs_oracle_and_golden(cuda_dev):
         assert np.array_equal(score, g["score%d" % ci])
         assert np.array_equal(link, g["link%d" % ci])
         assert np.array_equal(show, g["show%d" % ci])
+
+
+def test_icdar_generate_rbox(golden_dir, cuda_dev):
+    """N1: datasets/icdar.py generate_rbox (the generator train.sh uses) and its [::4, ::4] subsample against the
+    reference-executed golden, and the kernel against the oracle on random id maps."""
+    import torch
+    from oracle import labels as OL
+    from tensorflow_ocr_b200 import head
+    from tensorflow_ocr_b200.datasets import icdar
+    g = np.load(golden_dir + "/icdar_generate_rbox.npz")
+    for ci in range(int(g["n_cases"])):
+        s = int(g["size%d" % ci])
+        score, geo, tm = icdar.generate_rbox((s, s), g["polys%d" % ci], g["tags%d" % ci])
+        assert score.dtype == np.uint8 and geo.dtype == np.float32 and tm.dtype == np.uint8
+        assert np.array_equal(score, g["score%d" % ci]) and np.array_equal(geo, g["geo%d" % ci])
+        assert np.array_equal(tm, g["tmask%d" % ci])
+        score4, geo4, tm4 = icdar.generate_rbox_4s((s, s), g["polys%d" % ci], g["tags%d" % ci])
+        assert np.array_equal(geo4, g["geo4s%d" % ci]) and np.array_equal(score4.astype(np.float32), g["score4s%d" % ci])
+        assert np.array_equal(tm4.astype(np.float32), g["tmask4s%d" % ci])
+    rng = np.random.default_rng(8)
+    B, S = 3, 80
+    first = rng.integers(0, 4, (B, S, S)).astype(np.int32)
+    last = np.where(first > 0, first + rng.integers(0, 3, (B, S, S)), 0).astype(np.int32)
+    link, score = head.link_labels_icdar_raw(torch.as_tensor(last).to(cuda_dev), torch.as_tensor(first).to(cuda_dev))
+    for b in range(B):
+        assert np.array_equal(link[b].cpu().numpy(), OL.icdar_link_labels(last[b], first[b]))
+        assert np.array_equal(score[b].cpu().numpy(), (last[b] > 0).astype(np.float32))
+    with pytest.raises(ValueError):
+        icdar.generate_rbox((64, 96), g["polys0"], g["tags0"])

@@ -178,3 +178,17 @@ def test_result_txt_golden(golden_dir, tmp_path):
     write_result_txt(str(tmp_path / "res.txt"), c["boxes"])
     mine = open(tmp_path / "res.txt", "rb").read()
     assert mine.endswith(b"\r\n") and sorted(mine.split(b"\r\n")) == sorted(c["res_txt"].split(b"\r\n"))
+
+
+def test_icdar_generate_rbox_golden(golden_dir):
+    """N1, the EAST-fork generator (datasets/icdar.py:83-105, 486-539, executed by make_golden.py): the oracle's
+    two-map restatement (last / first covering polygon) reproduces the order-dependent loop exactly."""
+    from oracle import labels as OL
+    g = np.load(golden_dir + "/icdar_generate_rbox.npz")
+    for ci in range(int(g["n_cases"])):
+        s = int(g["size%d" % ci])
+        score, geo, tm = OL.icdar_generate_rbox((s, s), g["polys%d" % ci], g["tags%d" % ci])
+        assert np.array_equal(score, g["score%d" % ci])
+        assert np.array_equal(geo, g["geo%d" % ci])
+        assert np.array_equal(tm, g["tmask%d" % ci])
+        assert geo.sum() > 1000 and (geo[:, 0].sum() > 0 or geo[0].sum() > 0)   # the wrap-around borders are exercised
