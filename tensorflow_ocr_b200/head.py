@@ -270,10 +270,13 @@ _aux_streams = {}
 
 
 def _aux_stream(dev: torch.device) -> torch.cuda.Stream:
-    st = _aux_streams.get(dev.index)
+    """The second stream of the head step, one per (device, calling stream): two callers that drive the step on
+    two streams of one device (batches in flight) must not share their decode branch."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    st = _aux_streams.get(key)
     if st is None:
         st = torch.cuda.Stream(dev)
-        _aux_streams[dev.index] = st
+        _aux_streams[key] = st
     return st
 
 
