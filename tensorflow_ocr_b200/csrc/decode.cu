@@ -259,22 +259,50 @@ decode_tile_cc_kernel(const float* __restrict__ pix_logits, const float* __restr
     }
   }
   __syncthreads();
+  // Run-based labelling inside the tile.  A warp is one tile row: pixel x continues the run of x-1 iff the pair
+  // is linked (either endpoint emits the edge) — one ballot gives every lane its run head; the union-find nodes
+  // are the RUN HEADS, and only the three downward directions need unions, at most one per pair of runs (an
+  // edge is dropped when the lane to its left has the same edge between the same two runs, or when the
+  // previous direction already reaches the same run below).  A per-pixel union-find did up to four unions
+  // per pixel, and the tile's barrier waited for the thread with the longest chain.
+  __shared__ unsigned s_cl[kTH];
+  static_assert(kTW == 32, "one warp per tile row");
+  const int lane = tid & 31;
   const unsigned f = sf[ly + 1][lx + 1];
   const bool P = inimg && (f & kFlagP);
-  slab[tid] = P ? tid : -1;
+  const bool yin = gy >= 1 && gy <= H - 2;
+  const bool vin = yin && gx >= 1 && gx <= W - 2;
+  const unsigned fl = sf[ly + 1][lx];   // left neighbour (for lx == 0 it lies in the next tile: decode_cross_kernel)
+  const bool lin = yin && gx >= 2 && gx <= W - 1;
+  const bool cl = P && lx > 0 && (fl & kFlagP) && ((vin && (f & 1u)) || (lin && (fl & 8u)));
+  const unsigned m = __ballot_sync(0xffffffffu, cl);
+  const int hv = ly * kTW + 31 - __clz(~m & (0xffffffffu >> (31 - lane)));   // bit 0 of m is never set
+  slab[tid] = P ? hv : -1;
+  if (lane == 0) s_cl[ly] = m;
   __syncthreads();
-  if (P) {
-    const bool vin = gx >= 1 && gx <= W - 2 && gy >= 1 && gy <= H - 2;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int d = c_fwd[k];
-      const int uy = ly + c_dy[d], ux = lx + c_dx[d];
-      if (uy < 0 || uy >= kTH || ux < 0 || ux >= kTW) continue;  // cross-tile: decode_cross_kernel
-      const unsigned fu = sf[uy + 1][ux + 1];
-      if (!(fu & kFlagP)) continue;
-      const int ugx = gx + c_dx[d], ugy = gy + c_dy[d];
-      const bool uin = ugx >= 1 && ugx <= W - 2 && ugy >= 1 && ugy <= H - 2;
-      if ((vin && (f & (1u << d))) || (uin && (fu & (1u << c_opp[k])))) unite_s(slab, tid, uy * kTW + ux);
+  {
+    // downward edges (all lanes take part in the ballots): left_down 1 <-> right_up 5, down 7 <-> up 6, right_down 4 <-> left_up 2
+    const bool row = ly + 1 < kTH;      // the row below is in this tile, else decode_cross_kernel
+    const bool y1in = gy + 1 <= H - 2;
+    const unsigned fu1 = (P && row && lx >= 1) ? sf[ly + 2][lx] : 0u;
+    const unsigned fu7 = (P && row) ? sf[ly + 2][lx + 1] : 0u;
+    const unsigned fu4 = (P && row && lx + 1 < kTW) ? sf[ly + 2][lx + 2] : 0u;
+    const bool u1in = y1in && gx - 1 >= 1 && gx - 1 <= W - 2, u7in = y1in && gx >= 1 && gx <= W - 2, u4in = y1in && gx + 1 <= W - 2;
+    const bool e1 = (fu1 & kFlagP) && ((vin && (f & (1u << 1))) || (u1in && (fu1 & (1u << 5))));
+    const bool e7 = (fu7 & kFlagP) && ((vin && (f & (1u << 7))) || (u7in && (fu7 & (1u << 6))));
+    const bool e4 = (fu4 & kFlagP) && ((vin && (f & (1u << 4))) || (u4in && (fu4 & (1u << 2))));
+    const unsigned E1 = __ballot_sync(0xffffffffu, e1), E7 = __ballot_sync(0xffffffffu, e7), E4 = __ballot_sync(0xffffffffu, e4);
+    if (E1 | E7 | E4) {
+      const unsigned md = row ? s_cl[ly + 1] : 0u;                  // run continuation bits of the row below
+      const bool cu1 = lane >= 1 && ((md >> (lane - 1)) & 1u), cu7 = (md >> lane) & 1u, cu4 = lane < 31 && ((md >> (lane + 1)) & 1u);
+      const bool prev = lane > 0 && cl;
+      const bool s1 = prev && ((E1 >> (lane - 1)) & 1u) && cu1;
+      const bool s7 = (prev && ((E7 >> (lane - 1)) & 1u) && cu7) || (e1 && cu7);
+      const bool s4 = (prev && ((E4 >> (lane - 1)) & 1u) && cu4) || (e7 && cu4);
+      auto head_below = [&](int x) { return (ly + 1) * kTW + 31 - __clz(~md & (0xffffffffu >> (31 - x))); };
+      if (e1 && !s1) unite_s(slab, hv, head_below(lane - 1));
+      if (e7 && !s7) unite_s(slab, hv, head_below(lane));
+      if (e4 && !s4) unite_s(slab, hv, head_below(lane + 1));
     }
   }
   __syncthreads();
@@ -282,7 +310,7 @@ decode_tile_cc_kernel(const float* __restrict__ pix_logits, const float* __restr
     const size_t g = base + (size_t)gy * W + gx;
     int root = -1;
     if (P) {
-      const int r = find_root_s(slab, tid);
+      const int r = find_root_s(slab, hv);
       const int ry = r / kTW, rx = r - ry * kTW;
       root = (int)(base + (size_t)(ty0 + ry) * W + tx0 + rx);
     }
