@@ -692,12 +692,40 @@ def run_gpu(args):
             torch.cuda.synchronize()
             torch.cuda.set_stream(main_stream)
 
+    # The timed run is `steps` consecutive steps.  Short runs (the driver's 20 steps) are captured WHOLE into one
+    # graph: a graph launch costs the device a ~2.5 us gap, and with the per-step collective a graph has to wait for
+    # its last all-reduce before it ends — once per run instead of once per round.  Long runs replay round graphs
+    # and one tail graph for the remainder.
+    run_graph, tail_graph, n_tail = None, None, 0
+    if round_graph is not None and args.steps <= 96:
+        run_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(run_graph, stream=main_stream):
+            for i in range(args.steps):
+                step(i, join=(i == args.steps - 1))
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(main_stream)
+    elif round_graph is not None and use_coll and args.steps % ROUND > 1:
+        n_tail = args.steps % ROUND
+        t0 = args.steps - n_tail
+        tail_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(tail_graph, stream=main_stream):
+            for i in range(t0, t0 + n_tail):
+                step(i, join=(i == t0 + n_tail - 1))
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(main_stream)
+
     def run_steps(first, n):
+        if run_graph is not None and first == 0 and n == args.steps:
+            run_graph.replay()
+            return
         i = first
         while i < first + n:
             if round_graph is not None and i % NSETS == 0 and i + ROUND <= first + n:
                 round_graph.replay()
                 i += ROUND
+            elif tail_graph is not None and first == 0 and n == args.steps and i == args.steps - n_tail:
+                tail_graph.replay()
+                i += n_tail
             else:
                 if graphs is not None:
                     graphs[i % NSETS].replay()
@@ -717,6 +745,8 @@ def run_gpu(args):
     launches_per_step = int(lib.plh_launch_count() - c0)
 
     run_steps(0, args.warmup)
+    if run_graph is not None:        # one untimed replay of the whole-run graph (first launch of a graph is slower)
+        run_graph.replay()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -879,7 +909,7 @@ def run_gpu(args):
             "cuda_graphs": graphs is not None,
             "us_per_step_per_rank": [round(t / args.steps * 1e3, 2) for t in per_rank_ms],
             "host_enqueue_us_per_step": round(host_us_per_step, 2),
-            "steps_per_graph_launch": ROUND if round_graph is not None else 1,
+            "steps_per_graph_launch": args.steps if run_graph is not None else (ROUND if round_graph is not None else 1),
             "launches_per_step": launches_per_step,
             "cpu_affinity_rank0": numa_note,
             "two_batches_in_flight": two_in_flight,
@@ -909,7 +939,7 @@ def run_gpu(args):
         killer = threading.Timer(30.0, lambda: os._exit(0))
         killer.daemon = True
         killer.start()
-        del round_graph, graphs
+        del round_graph, graphs, tail_graph, run_graph
         import gc
         gc.collect()
         torch.cuda.synchronize()
