@@ -123,7 +123,7 @@ class Workload:
     total_batch = None          # strong scaling: the batch is split over the ranks
     batch_per_gpu = 32
     bytes_per_px = 0            # algorithmic bytes of the whole step
-    cpu_s_per_image = 0.12      # for sizing the bounded CPU sample
+    cpu_s_per_image = 0.03      # one core, for sizing the bounded CPU sample (~20 s)
     collective = False          # a per-step all-reduce of the loss scalars at N > 1
 
     def batch(self, world):
@@ -293,7 +293,7 @@ class DecodeOnly(Workload):
     scaling = "strong"
     total_batch = 64
     bytes_per_px = 76           # 72 B/px logits + 4 B/px label map
-    cpu_s_per_image = 0.5
+    cpu_s_per_image = 0.14
 
     def __init__(self, cid):
         self.cid = cid
@@ -373,7 +373,7 @@ class EastHead(Workload):
     workload = ("EAST RBOX head: dice + IoU/angle loss fwd+bwd (1 score + 5 geometry channels at 1/4 res), restore_rectangle "
                 "+ locality-aware NMS of the pixels with score > 0.8, batch 32 at 512x512 (128x128 maps), per GPU")
     bytes_per_px = 76
-    cpu_s_per_image = 1.0
+    cpu_s_per_image = 0.85
     THRESH = 0.8
 
     def host_sets(self, B, rank):
@@ -483,7 +483,7 @@ class LossAblation(Workload):
                 "fwd+bwd each, batch 256 at 768x768 (192x192 maps) over 8 GPUs = 32 per GPU, NCCL all-reduce of the loss scalars")
     bytes_per_px = 180 + 180 + 184      # CE 180, focal 180, dice head 108 + 4 (mask) + 72
     collective = True
-    cpu_s_per_image = 0.5
+    cpu_s_per_image = 0.11
 
     def host_sets(self, B, rank):
         sets = _pixellink_sets(self.cid, B, self.H, self.W, rank)
