@@ -77,10 +77,21 @@ def get_pos_and_neg_masks(labels):
     return labels == 1, labels == 0
 
 
+def _check_scores(sc):
+    """The selection kernel ranks the fp32 bit patterns of the scores, which orders them only on [0, 1] (they are
+    softmax probabilities in the reference, nets/model.py:216-217).  Anything else — negative, above 1, NaN —
+    would silently give a wrong threshold, so it is rejected here (one reduction; the fused loss computes its own
+    scores and does not come through this check)."""
+    lo, hi = torch.aminmax(sc)
+    if not (float(lo) >= 0.0 and float(hi) <= 1.0):     # NaN fails both comparisons
+        raise ValueError("OHNM scores must be probabilities in [0, 1] (got min %r, max %r)" % (float(lo), float(hi)))
+
+
 def OHNM_batch(batch_size, neg_conf, pos_mask, neg_mask):
     """nets/model.py:186-197 — ``float(pos_mask) + selected_neg_mask`` with the per-image
     radix-select kernel.  ``batch_size`` is accepted; the real batch is ``pos_mask.shape[0]``."""
     sc, np_in = head.to_device(neg_conf)
+    _check_scores(sc)
     shape = tuple(sc.shape)
     B = shape[0]
     pm, _ = head.to_device(pos_mask, torch.uint8, sc.device)
@@ -93,6 +104,7 @@ def OHNM_batch(batch_size, neg_conf, pos_mask, neg_mask):
 def OHNM_single_image(scores, n_pos, neg_mask):
     """nets/model.py:161-184 — mask of the selected negatives of ONE image."""
     sc, np_in = head.to_device(scores)
+    _check_scores(sc)
     shape = tuple(sc.shape)
     nm, _ = head.to_device(neg_mask, torch.uint8, sc.device)
     npos = torch.as_tensor([int(n_pos)], dtype=torch.int32, device=sc.device)

@@ -206,3 +206,19 @@ def test_icdar_generate_rbox(golden_dir, cuda_dev):
         assert np.array_equal(score[b].cpu().numpy(), (last[b] > 0).astype(np.float32))
     with pytest.raises(ValueError):
         icdar.generate_rbox((64, 96), g["polys0"], g["tags0"])
+
+
+def test_east_loss_at_config4_shape(cuda_dev):
+    """E2 at BASELINE config 4's shape (32 x 128x128, geometry consistent per instance like the bench's) against
+    the oracle — parity unpinned (the EAST geometry loss is not in the reference)."""
+    import torch
+    from oracle import east as E
+    from tensorflow_ocr_b200 import head, synth
+    d = synth.make_east_batch(4, 32, 128, 128, consistent=True)
+    ref = E.east_loss(d["score_gt"], d["score_pred"], d["geo_gt"], d["geo_pred"], d["training_mask"])
+    t = {k: torch.as_tensor(v).to(cuda_dev) for k, v in d.items()}
+    outv, gs, gg = head.east_loss_raw(t["score_gt"], t["score_pred"], t["geo_gt"], t["geo_pred"], t["training_mask"])
+    torch.cuda.synchronize()
+    assert rel_err(outv[0].item(), ref["loss"]) <= TOL
+    assert rel_err(gs.cpu().numpy(), ref["grad_score"]) <= TOL
+    assert rel_err(gg.cpu().numpy(), ref["grad_geo"]) <= 5e-5   # cosf/sinf/logf vs numpy: a few ulp on tiny terms

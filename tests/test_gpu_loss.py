@@ -235,3 +235,45 @@ def test_loss_select_path_boundaries(hw, cuda_dev):
     inp = synth.make_batch(123 + H, 2, H, W, "G", edge_images=False)
     ref = O.loss_model(inp["pix_lab"], inp["pix_logits"], inp["link_lab"], inp["link_logits"])
     _compare(_run(inp, head.LossConfig()), ref, 2)
+
+
+def test_ohnm_rejects_scores_outside_unit_interval(cuda_dev):
+    """The standalone OHNM ranks fp32 bit patterns: only probabilities in [0, 1] are ordered by them."""
+    from tensorflow_ocr_b200.nets import model
+    sc = np.random.default_rng(0).uniform(size=(2, 64)).astype(np.float32)
+    pos = np.zeros((2, 64), bool)
+    pos[:, :5] = True
+    neg = ~pos
+    model.OHNM_batch(14, sc, pos, neg)
+    for bad in (-0.25, 1.5, np.nan):
+        s2 = sc.copy()
+        s2[1, 7] = bad
+        with pytest.raises(ValueError):
+            model.OHNM_batch(14, s2, pos, neg)
+        with pytest.raises(ValueError):
+            model.OHNM_single_image(s2[1], 5, neg[1])
+
+
+def test_loss_terms_at_config5_shape(cuda_dev):
+    """BASELINE config 5's per-GPU shape (32 x 192x192: the 32-keys-per-thread tier of the selection kernel, inputs
+    larger than half of L2): CE+OHEM, focal (parity unpinned) and the dice head against the oracle, gradients
+    elementwise."""
+    import torch
+    from oracle import pixellink_loss as O
+    from tensorflow_ocr_b200 import _lib, head, synth
+    B, H, W = 32, 192, 192
+    inp = synth.make_batch(5, B, H, W, "G", edge_images=True)
+    a = (inp["pix_lab"], inp["pix_logits"], inp["link_lab"], inp["link_logits"])
+    _compare(_run(inp), O.loss_model(*a), B)
+    _compare(_run(inp, head.LossConfig(term=_lib.TERM_FOCAL)), O.loss_model(*a, term="focal"), B)
+    pl, ll = inp["pix_logits"], inp["link_logits"].reshape(B, H, W, 8, 2)
+    pp = (1.0 / (1.0 + np.exp(-(pl[..., 1:2] - pl[..., 0:1])))).astype(np.float32)
+    lp = (1.0 / (1.0 + np.exp(-(ll[..., 1] - ll[..., 0])))).astype(np.float32)
+    m = (np.random.default_rng(1).uniform(size=(B, H, W, 1)) > 0.1).astype(np.float32)
+    ref = O.loss_vgg16_dice(inp["pix_lab"], pp, inp["link_lab"], lp, m)
+    t = lambda x: torch.as_tensor(x).to(cuda_dev)
+    outv, gp, gl = head.dice_head_raw(t(inp["pix_lab"]), t(pp), t(inp["link_lab"]), t(lp), t(m))
+    torch.cuda.synchronize()
+    assert rel_err(outv[0].item(), ref["loss"]) <= TOL
+    assert rel_err(gp.cpu().numpy(), ref["grad_pixel"]) <= TOL
+    assert rel_err(gl.cpu().numpy(), ref["grad_link"]) <= TOL
