@@ -245,6 +245,29 @@ PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double r
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Detection evaluation.
+ * plh_quad_jaccard — tool/bboxes.py:252-282 np_bboxes_jaccard for every (detection, ground truth) pair of every
+ * image: both quadrilaterals rasterised as cv2.drawContours(thickness = -1) draws them (outline by cv::line +
+ * scan-line interior, cv2 4.13; no mask is materialised) and iou = (float)((double)|A & B| / (double)|A | B|).
+ *  dets      [sum D_b, 4, 2] int32 (x, y), gts [sum G_b, 4, 2] int32; coordinates in [0, 2^20) — a pair with a
+ *            negative coordinate gets NaN (cv2 would clip the polygon against its mask; not restated)
+ *  det_off / gt_off [B+1] int32 (device): first detection / ground truth of image b
+ *  pair_off  [B+1] int64 (device): pair_off[b] = sum_{i<b} D_i * G_i; total_pairs = pair_off[B]
+ *  jaccard   [total_pairs] float: image b's D_b x G_b matrix, row-major, at pair_off[b]
+ * plh_bboxes_matching — tool/bboxes.py:158-246: detections of an image in the given (score) order, each against
+ * the FIRST maximum of its Jaccard row: match = iou > matching_threshold; true positive = matched, not ignored,
+ * ground truth not matched before; false positive = not ignored and (unmatched or already matched).
+ *  gignored  [sum G_b] uint8; gmatch [sum G_b] uint8 scratch; tp / fp [sum D_b] uint8;
+ *  n_gbboxes [B] int32 = number of not-ignored ground truths.  An image without ground truth gets tp = fp = 0
+ *            (the reference raises on it).
+ */
+PLH_API int plh_quad_jaccard(const int32_t* dets, const int32_t* gts, const int32_t* det_off, const int32_t* gt_off,
+                     const int64_t* pair_off, int B, long long total_pairs, float* jaccard, void* stream);
+PLH_API int plh_bboxes_matching(const float* jaccard, const int32_t* det_off, const int32_t* gt_off, const int64_t* pair_off,
+                        int B, const uint8_t* gignored, float matching_threshold, uint8_t* gmatch, uint8_t* tp,
+                        uint8_t* fp, int32_t* n_gbboxes, void* stream);
+
+/*
  * The threshold pass of the decode alone (test_pixellink_fast.py:120-128): flags[b,y,x] = bit 8: pixel
  * score > pixel_thresh, bits 0..7: link d score > link_thresh, for plh_decode_from_flags.  Lets a caller
  * schedule this bandwidth-bound pass separately from the latency-bound component labelling.

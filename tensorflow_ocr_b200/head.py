@@ -353,6 +353,49 @@ def contour_boxes_raw(mask: torch.Tensor, ratio_w: float = 1.0, ratio_h: float =
     return out
 
 
+def bboxes_matching_raw(dets: torch.Tensor, gts: torch.Tensor, det_counts, gt_counts, gignored: torch.Tensor,
+                        matching_threshold: float = 0.5) -> dict:
+    """plh_quad_jaccard + plh_bboxes_matching over a batch of images (tool/bboxes.py:158-282).
+
+    dets int32 [sum D_b,4,2], gts int32 [sum G_b,4,2], gignored uint8 [sum G_b] (CUDA); det_counts / gt_counts:
+    per-image counts (host sequences).  -> jaccard fp32 [sum D_b*G_b] (image b's D_b x G_b matrix at
+    pair_off[b]), tp / fp uint8 [sum D_b], n_gbboxes int32 [B], pair_off (host list)."""
+    lib = _lib.load()
+    dev = dets.device
+    _require_gpu(dev)
+    if dets.dtype != torch.int32 or gts.dtype != torch.int32 or gignored.dtype != torch.uint8:
+        raise ValueError("dets / gts must be int32, gignored uint8")
+    det_counts = [int(v) for v in det_counts]
+    gt_counts = [int(v) for v in gt_counts]
+    B = len(det_counts)
+    if B == 0 or len(gt_counts) != B:
+        raise ValueError("det_counts and gt_counts must name the same (non-zero) number of images")
+    if dets.numel() != 8 * sum(det_counts) or gts.numel() != 8 * sum(gt_counts) or gignored.numel() != sum(gt_counts):
+        raise ValueError("counts do not add up to the box arrays")
+    det_off, gt_off, pair_off = [0], [0], [0]
+    for d, g in zip(det_counts, gt_counts):
+        det_off.append(det_off[-1] + d), gt_off.append(gt_off[-1] + g), pair_off.append(pair_off[-1] + d * g)
+    dets, gts, gignored = dets.contiguous(), gts.contiguous(), gignored.contiguous()
+    d_off = torch.tensor(det_off, dtype=torch.int32).to(dev, non_blocking=True)
+    g_off = torch.tensor(gt_off, dtype=torch.int32).to(dev, non_blocking=True)
+    p_off = torch.tensor(pair_off, dtype=torch.int64).to(dev, non_blocking=True)
+    out = {"jaccard": torch.empty((max(pair_off[-1], 1),), dtype=torch.float32, device=dev)[:pair_off[-1]],
+           "tp": torch.empty((det_off[-1],), dtype=torch.uint8, device=dev),
+           "fp": torch.empty((det_off[-1],), dtype=torch.uint8, device=dev),
+           "n_gbboxes": torch.empty((B,), dtype=torch.int32, device=dev), "pair_off": pair_off,
+           "det_off": det_off, "gt_off": gt_off}
+    gmatch = torch.empty((max(gt_off[-1], 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.plh_quad_jaccard(_p(dets), _p(gts), _p(d_off), _p(g_off), _p(p_off), B, pair_off[-1], _p(out["jaccard"]),
+                                  _stream(dev))
+        _lib.check(rc, "plh_quad_jaccard")
+        rc = lib.plh_bboxes_matching(_p(out["jaccard"]), _p(d_off), _p(g_off), _p(p_off), B, _p(gignored),
+                                     float(matching_threshold), _p(gmatch), _p(out["tp"]), _p(out["fp"]),
+                                     _p(out["n_gbboxes"]), _stream(dev))
+        _lib.check(rc, "plh_bboxes_matching")
+    return out
+
+
 def link_labels_raw(ids: torch.Tensor, want_pixel: bool = True):
     """plh_link_labels: ids uint8 [B,H,W] (CUDA) -> (link_lab fp32 [B,H,W,8], pix_lab fp32 [B,H,W] or None)."""
     lib = _lib.load()

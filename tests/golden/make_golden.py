@@ -450,6 +450,134 @@ def golden_icdar_generate_rbox():
     save("icdar_generate_rbox", n_cases=3, **out)
 
 
+# ----------------------------------------------------------------------------- tool/bboxes.py + tool/metrics.py (N4)
+class _NpTensor(np.ndarray):
+    def set_shape(self, _shape):
+        pass
+
+
+class _NpTensorArray:
+    def __init__(self, dtype, size, dynamic_size=False, infer_shape=True):
+        self.items = [None] * int(size)
+
+    def write(self, i, v):
+        self.items[int(i)] = np.asarray(v)
+        return self
+
+    def stack(self):
+        return np.stack(self.items) if self.items else np.zeros((0,), bool)
+
+
+def _np_tf():
+    """Eager numpy stand-in for the handful of TF ops tool/bboxes.py::bboxes_matching and tool/metrics.py use."""
+    import contextlib
+
+    t = types.SimpleNamespace()
+    t.bool, t.int32, t.int64, t.float32 = np.bool_, np.int32, np.int64, np.float32
+    t.name_scope = lambda *a, **k: contextlib.nullcontext()
+    t.cast = lambda x, dtype=None: np.asarray(x).astype(dtype)
+    t.count_nonzero = lambda x: np.int64(np.count_nonzero(x))
+    t.logical_not, t.logical_and, t.logical_or = np.logical_not, np.logical_and, np.logical_or
+    t.zeros = lambda shape, dtype=np.float32: np.zeros(tuple(int(v) for v in np.atleast_1d(shape)), dtype)
+    t.zeros_like = np.zeros_like
+    t.shape = lambda x: np.asarray(np.shape(x), np.int32)
+    t.size = lambda x: np.int32(np.size(x))
+    t.range = lambda n, dtype=np.int32: np.arange(int(n), dtype=dtype)
+    t.TensorArray = _NpTensorArray
+    t.less = np.less
+    t.greater = np.greater
+    t.equal = np.equal
+    t.divide = lambda a, b: np.divide(a, b, out=np.zeros_like(np.asarray(a, np.float32)), where=np.asarray(b) != 0)
+    t.argmax = lambda x, axis=0: np.int64(np.argmax(x, axis=axis))
+    t.reshape = lambda x, shp: np.reshape(x, tuple(int(v) for v in shp))
+    t.reduce_sum = lambda x, axis=None: np.sum(x, axis=axis, dtype=np.asarray(x).dtype)
+    t.where = lambda c, a, b, name=None: np.where(c, a, b)
+    t.tuple = lambda xs: tuple(xs)
+
+    def py_func(fn, inputs, _tout):
+        return np.asarray(fn(*[np.asarray(v) for v in inputs])).view(_NpTensor)
+
+    def while_loop(cond, body, loop_vars, parallel_iterations=1, back_prop=False):
+        vs = list(loop_vars)
+        while cond(*vs):
+            vs = list(body(*vs))
+        return vs
+
+    t.py_func, t.while_loop = py_func, while_loop
+    return t
+
+
+def golden_evaluation():
+    """tool/bboxes.py np_bboxes_jaccard (:252-282), bboxes_jaccard (:247-250), bboxes_matching (:158-246) and
+    tool/metrics.py precision_recall (:66-80), fmean (:82-85) with tool/math.py safe_divide (:27-41), executed as
+    written.  `util.img` (un-vendored dengdan/pylib) is its three one-line cv2/numpy wrappers."""
+    import cv2
+
+    util = types.SimpleNamespace(img=types.SimpleNamespace(
+        points_to_contours=lambda pts: [np.asarray(pts, np.int32).reshape(-1, 1, 2)],
+        black=lambda shape: np.zeros(tuple(int(v) for v in shape), np.uint8),
+        draw_contours=lambda img, contours, idx=-1, color=1, border_width=1: cv2.drawContours(img, contours, idx, color, border_width)))
+    tfn = _np_tf()
+    ns = dict(np=np, cv2=cv2, util=util, tf=tfn, zip=lambda *a: list(zip(*a)))
+    for fn in ("np_bboxes_jaccard", "bboxes_jaccard", "bboxes_matching"):
+        src, span = cut("tool/bboxes.py", fn)
+        print("tool/bboxes.py", fn, span)
+        exec(src, ns)
+    mns = dict(tf=tfn, math_ops=tfn)
+    src, span = cut("tool/math.py", "safe_divide")
+    print("tool/math.py safe_divide", span)
+    exec(src, mns)
+    mns["tfe_math"] = types.SimpleNamespace(safe_divide=mns["safe_divide"])
+    for fn in ("precision_recall", "fmean"):
+        src, span = cut("tool/metrics.py", fn)
+        print("tool/metrics.py", fn, span)
+        exec(src, mns)
+
+    rng = np.random.default_rng(44)
+
+    def quad(c, w, h, a):
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        return np.maximum((np.array([[-w, -h], [w, -h], [w, h], [-w, h]]) / 2 @ R.T + c), 0).astype(np.int32)
+
+    out = {}
+    n_cases = 6
+    for ci in range(n_cases):
+        G = int(rng.integers(1, 14))
+        size = (160, 90) if ci % 2 else (1280, 720)
+        gts = []
+        for g in range(G):
+            c = rng.uniform(0.1, 0.9, 2) * size
+            gts.append(quad(c, rng.uniform(0.03, 0.3) * size[0], rng.uniform(0.02, 0.12) * size[1], rng.uniform(-0.6, 0.6)))
+        gts = np.stack(gts)
+        dets = []
+        for g in range(G):          # detections: jittered copies (some twice: the second one is a false positive), plus strays
+            for rep in range(int(rng.integers(0, 3))):
+                j = rng.normal(0, 0.006 * size[0] * (1 + 5 * (rng.uniform() < 0.3)), (4, 2))
+                dets.append(np.maximum(gts[g] + j, 0).astype(np.int32))
+        for k in range(int(rng.integers(1, 5))):
+            dets.append(quad(rng.uniform(0.1, 0.9, 2) * size, rng.uniform(0.03, 0.2) * size[0],
+                             rng.uniform(0.02, 0.1) * size[1], rng.uniform(-1.5, 1.5)))
+        if ci == 0:                  # degenerate shapes: a segment, a point, a bow-tie
+            dets += [np.array([[5, 5], [40, 9], [40, 9], [5, 5]], np.int32), np.array([[7, 7]] * 4, np.int32),
+                     np.array([[10, 10], [60, 40], [60, 10], [10, 40]], np.int32)]
+        order = rng.permutation(len(dets))
+        dets = np.stack([dets[i] for i in order])
+        gign = (rng.uniform(size=G) < 0.25).astype(np.int32)
+        gxs, gys = gts[:, :, 0].copy(), gts[:, :, 1].copy()
+        bboxes = dets.reshape(-1, 8)
+        jac = np.stack([ns["np_bboxes_jaccard"](bboxes[i], gxs, gys) for i in range(len(bboxes))])
+        n_g, tp, fp = ns["bboxes_matching"](bboxes, gxs, gys, gign, matching_threshold=0.5)
+        pre, rec = mns["precision_recall"](n_g, tp, fp)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            fm = mns["fmean"](pre, rec)
+        out.update({"bboxes%d" % ci: bboxes, "gxs%d" % ci: gxs, "gys%d" % ci: gys, "gignored%d" % ci: gign,
+                    "jaccard%d" % ci: jac.astype(np.float32), "n_gbboxes%d" % ci: np.int64(n_g), "tp%d" % ci: tp,
+                    "fp%d" % ci: fp, "precision%d" % ci: np.float32(pre), "recall%d" % ci: np.float32(rec),
+                    "fmean%d" % ci: np.float32(fm)})
+        print("case", ci, "G", G, "D", len(bboxes), "tp", int(tp.sum()), "fp", int(fp.sum()), "n_g", int(n_g), "P/R/F", pre, rec, fm)
+    save("evaluation", n_cases=n_cases, **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     only = sys.argv[1] if len(sys.argv) > 1 else None
@@ -459,6 +587,8 @@ if __name__ == "__main__":
         golden_link_graph()
     elif only == "icdar":
         golden_icdar_generate_rbox()
+    elif only == "evaluation":
+        golden_evaluation()
     else:
         golden_model_loss()
         golden_vgg16()
@@ -467,3 +597,4 @@ if __name__ == "__main__":
         golden_generate_rbox()
         golden_link_graph()
         golden_icdar_generate_rbox()
+        golden_evaluation()

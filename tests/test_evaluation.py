@@ -1,0 +1,84 @@
+"""N4 evaluation code on the CPU: the oracle against the reference-executed golden (tests/golden/evaluation.npz,
+make_golden.py::golden_evaluation), the interval statement of cv2's filled contour against cv2 itself, and the
+host-side metrics mirror."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import evaluation as oe
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "evaluation.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_oracle_jaccard_and_matching_equal_the_reference(gold):
+    for ci in range(int(gold["n_cases"])):
+        bboxes, gxs, gys, gi = gold["bboxes%d" % ci], gold["gxs%d" % ci], gold["gys%d" % ci], gold["gignored%d" % ci]
+        jac = np.stack([oe.np_bboxes_jaccard(b, gxs, gys) for b in bboxes])
+        assert jac.dtype == np.float32 and np.array_equal(jac, gold["jaccard%d" % ci])
+        n_g, tp, fp = oe.bboxes_matching(bboxes, gxs, gys, gi, 0.5)
+        assert n_g == int(gold["n_gbboxes%d" % ci])
+        assert np.array_equal(tp, gold["tp%d" % ci]) and np.array_equal(fp, gold["fp%d" % ci])
+        pre, rec = oe.precision_recall(n_g, tp, fp)
+        assert pre == gold["precision%d" % ci] and rec == gold["recall%d" % ci]
+        np.testing.assert_array_equal(oe.fmean(pre, rec), gold["fmean%d" % ci])
+
+
+def test_interval_statement_equals_the_reference_jaccard(gold):
+    """quad_jaccard_rows (no cv2: what the CUDA kernel computes) is bit-identical to the reference's mask path."""
+    for ci in range(int(gold["n_cases"])):
+        bboxes, gxs, gys = gold["bboxes%d" % ci], gold["gxs%d" % ci], gold["gys%d" % ci]
+        if bboxes[:, 0::2].max() > 400:   # the big canvases are covered on the GPU; keep the CPU suite short
+            bboxes = bboxes[:3]
+        jac = np.stack([oe.quad_jaccard_rows(b, gxs, gys) for b in bboxes])
+        assert np.array_equal(jac, gold["jaccard%d" % ci][:len(bboxes)])
+
+
+def test_filled_polygon_rows_vs_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for t in range(3000):
+        kind = t % 5
+        if kind == 0:
+            pts = rng.integers(0, 60, (4, 2))
+        elif kind == 1:
+            pts = rng.integers(0, 12, (4, 2))          # many degenerate shapes: repeated points, segments
+        elif kind == 2:
+            c, w, h, a = rng.uniform(20, 200, 2), rng.uniform(1, 80), rng.uniform(1, 30), rng.uniform(-3.2, 3.2)
+            R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+            pts = np.maximum((np.array([[-w, -h], [w, -h], [w, h], [-w, h]]) / 2 @ R.T + c), 0)
+        elif kind == 3:
+            pts = rng.integers(0, 300, (4, 2))         # self-intersecting quadrilaterals
+        else:
+            pts = rng.integers(0, 40, (int(rng.integers(3, 9)), 2))
+        pts = np.asarray(pts).astype(np.int32)
+        shape = (int(pts[:, 1].max()) + 10, int(pts[:, 0].max()) + 10)
+        ref = np.zeros(shape, np.uint8)
+        cv2.drawContours(ref, [pts.reshape(-1, 1, 2)], -1, 1, -1)
+        got = oe.mask_from_rows(oe.filled_quad_rows([tuple(int(v) for v in p) for p in pts]), shape)
+        assert np.array_equal(ref, got), pts.tolist()
+
+
+def test_metrics_mirror_equals_the_reference(gold):
+    from tensorflow_ocr_b200.tool import metrics
+    state = None
+    tot_n, tot_tp, tot_fp = 0, [], []
+    for ci in range(int(gold["n_cases"])):
+        n_g, tp, fp = gold["n_gbboxes%d" % ci], gold["tp%d" % ci], gold["fp%d" % ci]
+        pre, rec = metrics.precision_recall(n_g, tp, fp)
+        assert pre.dtype == np.float32 and pre == gold["precision%d" % ci] and rec == gold["recall%d" % ci]
+        np.testing.assert_array_equal(metrics.fmean(pre, rec), gold["fmean%d" % ci])
+        (v_n, v_tp, v_fp), state = metrics.streaming_tp_fp_arrays(n_g, tp, fp, state=state)
+        tot_n += int(n_g)
+        tot_tp.append(tp), tot_fp.append(fp)
+        assert v_n == tot_n and np.array_equal(v_tp, np.concatenate(tot_tp)) and np.array_equal(v_fp, np.concatenate(tot_fp))
+    # the streaming arrays feed precision_recall at the end of an evaluation (tool/metrics.py:31-80)
+    pre, rec = metrics.precision_recall(*state.value())
+    o_pre, o_rec = oe.precision_recall(tot_n, np.concatenate(tot_tp), np.concatenate(tot_fp))
+    assert pre == o_pre and rec == o_rec
+    assert metrics.precision_recall(0, np.zeros(0, bool), np.zeros(0, bool)) == (0.0, 0.0)   # safe_divide
