@@ -210,6 +210,28 @@ PLH_API int plh_decode_from_flags(const uint16_t* flags, int B, int H, int W, co
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Polygon rasterisation of the ground-truth generators: tool/pixellink_fn.py:66-79 (cv2.fillPoly of every
+ * quadrilateral in order, then cv2.resize(INTER_NEAREST) to (w/4, h/4)) and datasets/icdar.py:486-514 (cv2.fillPoly
+ * at full resolution, training mask cleared inside flagged polygons).  Bit-identical to cv2 4.13 (outline by
+ * cv::line, scan-line interior, clipping of polygons that leave the canvas); nothing is drawn at full resolution,
+ * every output pixel looks at the source pixel it samples.
+ *  quads     [sum n_b, 4, 2] int32 (x, y) canvas coordinates (the caller truncates the float vertices like
+ *            np.array(points, np.int32) does); quad_off [B+1] int32 (device): first polygon of image b
+ *  zero_flags [sum n_b] uint8 optional: polygons that clear the training mask
+ *  H, W      canvas; Ho, Wo output grid (Wo <= 2048)
+ *  mode 0    output (oy, ox) = canvas (oy*stride, ox*stride)  (stride 1: the canvas itself; 4: [::4, ::4])
+ *  mode 1    output = cv2.resize(canvas, (Wo, Ho), INTER_NEAREST)
+ *  last_ids  [B,Ho,Wo] int32: 1-based index of the LAST polygon covering the pixel (0 = none) — what cv2 leaves
+ *  first_ids [B,Ho,Wo] int32 optional: index of the FIRST polygon covering it (plh_link_labels_icdar)
+ *  ids_u8    [B,Ho,Wo] uint8 optional: min(last, 255), the reference's uint8 poly_mask (plh_link_labels)
+ *  score     [B,Ho,Wo] float optional: 1.0 where any polygon covers the pixel
+ *  training_mask [B,Ho,Wo] uint8 optional: 0 where a flagged polygon covers the pixel, else 1
+ */
+PLH_API int plh_fill_quads(const int32_t* quads, const int32_t* quad_off, const uint8_t* zero_flags, int B, int H, int W,
+                   int Ho, int Wo, int mode, int stride, int32_t* last_ids, int32_t* first_ids, uint8_t* ids_u8,
+                   float* score, uint8_t* training_mask, void* stream);
+
+/*
  * Link labels of the EAST-fork generator, datasets/icdar.py:83-105 valid_link + :486-539 generate_rbox (the one
  * train.sh uses), with its quirks kept (Q17: direction names move the other axis, x is tested against h-1,
  * index -1 wraps, a link asks "is the neighbour text so far", polygons filled in order).
@@ -249,8 +271,9 @@ PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double r
  * plh_quad_jaccard — tool/bboxes.py:252-282 np_bboxes_jaccard for every (detection, ground truth) pair of every
  * image: both quadrilaterals rasterised as cv2.drawContours(thickness = -1) draws them (outline by cv::line +
  * scan-line interior, cv2 4.13; no mask is materialised) and iou = (float)((double)|A & B| / (double)|A | B|).
- *  dets      [sum D_b, 4, 2] int32 (x, y), gts [sum G_b, 4, 2] int32; coordinates in [0, 2^20) — a pair with a
- *            negative coordinate gets NaN (cv2 would clip the polygon against its mask; not restated)
+ *  dets      [sum D_b, 4, 2] int32 (x, y), gts [sum G_b, 4, 2] int32; |coordinate| < 2^20 (else the pair gets NaN).
+ *            The reference's mask starts at (0, 0): parts of a box at negative coordinates are clipped the way
+ *            cv2 clips them (cv::clipLine on the outline, edge slopes from the clipped segments)
  *  det_off / gt_off [B+1] int32 (device): first detection / ground truth of image b
  *  pair_off  [B+1] int64 (device): pair_off[b] = sum_{i<b} D_i * G_i; total_pairs = pair_off[B]
  *  jaccard   [total_pairs] float: image b's D_b x G_b matrix, row-major, at pair_off[b]

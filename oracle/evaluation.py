@@ -138,29 +138,74 @@ def line_row_runs(p0, p1):
     return runs
 
 
-def filled_quad_rows(pts):
-    """cv2.drawContours(thickness=-1) / fillPoly of one polygon with non-negative integer vertices inside the image,
-    as {row: [(x1, x2), ...]} inclusive intervals (possibly overlapping).
+def clip_line(w, h, p1, p2):
+    """cv::clipLine(Size(w, h), pt1, pt2) (imgproc/drawing.cpp), as restated from the OpenCV sources and pinned
+    against cv2.line in tests/test_evaluation.py: the y side first, then x, each intersection computed in double
+    and truncated.  -> (visible, pt1', pt2')."""
+    (x1, y1), (x2, y2) = p1, p2
+    right, bottom = w - 1, h - 1
+    c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8
+    c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8
+    if (c1 & c2) == 0 and (c1 | c2) != 0:
+        if c1 & 12:
+            a = 0 if c1 < 8 else bottom
+            x1 += int(float(a - y1) * (x2 - x1) / (y2 - y1))
+            y1 = a
+            c1 = (x1 < 0) + (x1 > right) * 2
+        if c2 & 12:
+            a = 0 if c2 < 8 else bottom
+            x2 += int(float(a - y2) * (x2 - x1) / (y2 - y1))
+            y2 = a
+            c2 = (x2 < 0) + (x2 > right) * 2
+        if (c1 & c2) == 0 and (c1 | c2) != 0:
+            if c1:
+                a = 0 if c1 == 1 else right
+                y1 += int(float(a - x1) * (y2 - y1) / (x2 - x1))
+                x1, c1 = a, 0
+            if c2:
+                a = 0 if c2 == 1 else right
+                y2 += int(float(a - x2) * (y2 - y1) / (x2 - x1))
+                x2, c2 = a, 0
+    return (c1 | c2) == 0, (x1, y1), (x2, y2)
 
-    = the outline drawn with cv::line, plus, for every row y in [ymin, ymax) of the non-horizontal edges, the
-    spans between consecutive pairs of the sorted edge abscissae x_e(y) = (x_top << 16) + (y - y_top) * dx_e
-    (dx_e = the 16.16 slope, truncated division), from ceil(x_left) to floor(x_right)."""
+
+def filled_quad_rows(pts, w=None, h=None):
+    """cv2.drawContours(thickness=-1) / fillPoly of one polygon with integer vertices on a w x h image, as
+    {row: [(x1, x2), ...]} inclusive intervals (possibly overlapping).  w, h None: vertices are non-negative and the
+    image holds them all (no clipping).
+
+    = the outline drawn with cv::line (clipped against the image first), plus, for every row y in [ymin, ymax)
+    of the non-horizontal edges, the spans between consecutive pairs of the sorted edge abscissae
+    x_e(y) = x_e(y_top) + (y - y_top) * dx_e (16.16 fixed point, dx_e by truncating division), from
+    ceil(x_left) to floor(x_right), cut to the image.  An edge with an endpoint outside the image takes its
+    abscissae (and, unless the clipped segment is horizontal, its ordinates) from the clipped segment for the slope
+    and is extrapolated back to its own top row."""
     n = len(pts)
+    if w is None:
+        w = max(p[0] for p in pts) + 1
+        h = max(p[1] for p in pts) + 1
     rows, edges = {}, []
     for i in range(n):
         p0, p1 = pts[i - 1], pts[i]
-        for y, r in line_row_runs(p0, p1).items():
-            rows.setdefault(y, []).append(r)
+        vis, q0, q1 = clip_line(w, h, p0, p1)
+        if vis:
+            for y, r in line_row_runs(q0, q1).items():
+                rows.setdefault(y, []).append(r)
         if p0[1] == p1[1]:
             continue
-        X0, X1 = p0[0] << XY_SHIFT, p1[0] << XY_SHIFT
-        dxe = _tdiv(X1 - X0, p1[1] - p0[1])
-        edges.append((p0[1], p1[1], X0, dxe) if p0[1] < p1[1] else (p1[1], p0[1], X1, dxe))
+        c0x, c0y, c1x, c1y = p0[0] << XY_SHIFT, p0[1], p1[0] << XY_SHIFT, p1[1]
+        if not (0 <= p0[0] < w and 0 <= p0[1] < h and 0 <= p1[0] < w and 0 <= p1[1] < h):
+            if q0[1] != q1[1]:
+                c0y, c1y = q0[1], q1[1]
+            c0x, c1x = q0[0] << XY_SHIFT, q1[0] << XY_SHIFT
+        dxe = _tdiv(c1x - c0x, c1y - c0y)
+        edges.append((p0[1], p1[1], c0x + (p0[1] - c0y) * dxe, dxe) if p0[1] < p1[1] else
+                     (p1[1], p0[1], c1x + (p1[1] - c1y) * dxe, dxe))
     if edges:
-        for y in range(min(e[0] for e in edges), max(e[1] for e in edges)):
+        for y in range(max(min(e[0] for e in edges), 0), min(max(e[1] for e in edges), h)):
             xs = sorted(e[2] + (y - e[0]) * e[3] for e in edges if e[0] <= y < e[1])
             for k in range(0, len(xs) - 1, 2):
-                x1, x2 = (xs[k] + XY_ONE - 1) >> XY_SHIFT, xs[k + 1] >> XY_SHIFT
+                x1, x2 = max((xs[k] + XY_ONE - 1) >> XY_SHIFT, 0), min(xs[k + 1] >> XY_SHIFT, w - 1)
                 if x1 <= x2:
                     rows.setdefault(y, []).append((x1, x2))
     return rows
@@ -175,15 +220,16 @@ def mask_from_rows(rows, shape):
 
 
 def quad_jaccard_rows(bbox, gxs, gys):
-    """np_bboxes_jaccard through filled_quad_rows (no cv2): what the CUDA kernel computes."""
-    P = [tuple(int(v) for v in p) for p in np.reshape(bbox, (4, 2))]
-    ra = filled_quad_rows(P)
+    """np_bboxes_jaccard through filled_quad_rows (no cv2): what the CUDA kernel computes.  The mask of
+    tool/bboxes.py:258-262 is (ymax + 10, xmax + 10): only the x < 0 / y < 0 sides ever clip."""
+    bp = np.reshape(bbox, (4, 2))
+    w = int(max(np.max(bp[:, 0]), np.max(gxs)) + 10)
+    h = int(max(np.max(bp[:, 1]), np.max(gys)) + 10)
+    ra = filled_quad_rows([tuple(int(v) for v in p) for p in bp], w, h)
+    ma = mask_from_rows(ra, (h, w))
     out = np.zeros((len(gxs),), np.float32)
     for g in range(len(gxs)):
-        Q = [(int(gxs[g][k]), int(gys[g][k])) for k in range(4)]
-        rb = filled_quad_rows(Q)
-        h = max(max(ra), max(rb)) + 1
-        w = max(max(b for iv in ra.values() for _, b in iv), max(b for iv in rb.values() for _, b in iv)) + 1
-        ma, mb = mask_from_rows(ra, (h, w)), mask_from_rows(rb, (h, w))
+        rb = filled_quad_rows([(int(gxs[g][k]), int(gys[g][k])) for k in range(4)], w, h)
+        mb = mask_from_rows(rb, (h, w))
         out[g] = np.sum(ma & mb) * 1.0 / np.sum(ma | mb)
     return out

@@ -9,6 +9,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "raster.cuh"
 
 namespace plh {
 
@@ -459,9 +460,104 @@ link_labels_icdar_kernel(const int32_t* __restrict__ last, const int32_t* __rest
   }
 }
 
+
+// ------------------------------------------------------------------ N1: polygon rasterisation
+// tool/pixellink_fn.py:66-79 and datasets/icdar.py:486-514 fill the image's quadrilaterals one after the other with
+// cv2.fillPoly (then, in the pixel_link fork, shrink the canvas with cv2.resize(INTER_NEAREST)).  Here nothing is
+// drawn: one CTA per OUTPUT row looks at the source row it samples; thread t turns polygon t into its (at most six)
+// intervals on that row (raster.cuh: cv2's outline + scan-line spans, clipped like cv2 clips), then every thread
+// walks the polygons in order for its pixels: the last one covering the pixel is cv2's result, the first one is
+// what the EAST fork's "text so far" test needs, a flagged one clears the training mask.
+constexpr int kFillChunk = 256;
+constexpr int kFillPPT = 8;  // output pixels per thread: Wo <= 2048
+
+__global__ void __launch_bounds__(kFillChunk)
+fill_quads_kernel(const int32_t* __restrict__ quads, const int32_t* __restrict__ quad_off,
+                  const uint8_t* __restrict__ zero_flags, int H, int W, int Ho, int Wo, int mode, int stride, double ify,
+                  double ifx, int32_t* __restrict__ last_ids, int32_t* __restrict__ first_ids,
+                  uint8_t* __restrict__ ids_u8, float* __restrict__ score, uint8_t* __restrict__ training_mask) {
+  __shared__ Ivs s_iv[kFillChunk];
+  __shared__ uint8_t s_zero[kFillChunk];
+  const int b = blockIdx.y, oy = blockIdx.x, tid = threadIdx.x;
+  // cv2.resize(INTER_NEAREST): source index = min(floor(dst * (1 / (dsize / ssize))), ssize - 1), in double
+  const int sy = mode == 0 ? oy * stride : min((int)floor(__dmul_rn((double)oy, ify)), H - 1);
+  const int q0 = quad_off[b], n = quad_off[b + 1] - q0;
+  int last[kFillPPT], first[kFillPPT], sx[kFillPPT];
+  bool keep[kFillPPT];
+#pragma unroll
+  for (int j = 0; j < kFillPPT; ++j) {
+    const int ox = tid + j * kFillChunk;
+    sx[j] = mode == 0 ? ox * stride : min((int)floor(__dmul_rn((double)ox, ifx)), W - 1);
+    last[j] = 0, first[j] = 0, keep[j] = true;
+  }
+  for (int c0 = 0; c0 < n; c0 += kFillChunk) {
+    const int m = min(n - c0, kFillChunk);
+    __syncthreads();
+    if (tid < m) {
+      int qx[4], qy[4];
+      int ymin = INT_MAX, ymax = INT_MIN;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        qx[k] = quads[(size_t)(q0 + c0 + tid) * 8 + 2 * k], qy[k] = quads[(size_t)(q0 + c0 + tid) * 8 + 2 * k + 1];
+        ymin = min(ymin, qy[k]), ymax = max(ymax, qy[k]);
+      }
+      s_iv[tid].n = 0;
+      if (sy >= ymin && sy <= ymax) {
+        QuadEdges E;
+        quad_edges(qx, qy, W, H, E);
+        quad_row_intervals(E, sy, W, s_iv[tid]);
+      }
+      s_zero[tid] = zero_flags ? zero_flags[q0 + c0 + tid] : 0;
+    }
+    __syncthreads();
+    for (int k = 0; k < m; ++k) {
+      const int ni = s_iv[k].n;
+      if (ni == 0) continue;
+#pragma unroll
+      for (int j = 0; j < kFillPPT; ++j) {
+        bool in = false;
+        for (int i = 0; i < ni; ++i) in = in || (sx[j] >= s_iv[k].a[i] && sx[j] <= s_iv[k].b[i]);
+        if (in) {
+          last[j] = c0 + k + 1;
+          if (first[j] == 0) first[j] = c0 + k + 1;
+          if (s_zero[k]) keep[j] = false;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kFillPPT; ++j) {
+    const int ox = tid + j * kFillChunk;
+    if (ox < Wo) {
+      const size_t o = ((size_t)b * Ho + oy) * Wo + ox;
+      last_ids[o] = last[j];
+      if (first_ids) first_ids[o] = first[j];
+      if (ids_u8) ids_u8[o] = (uint8_t)min(last[j], 255);  // the reference's canvas is uint8: cv2 saturates the fill value
+      if (score) score[o] = last[j] ? 1.f : 0.f;
+      if (training_mask) training_mask[o] = keep[j] ? 1 : 0;
+    }
+  }
+}
+
 }  // namespace plh
 
 using namespace plh;
+
+extern "C" int plh_fill_quads(const int32_t* quads, const int32_t* quad_off, const uint8_t* zero_flags, int B, int H, int W,
+                              int Ho, int Wo, int mode, int stride, int32_t* last_ids, int32_t* first_ids, uint8_t* ids_u8,
+                              float* score, uint8_t* training_mask, void* stream) {
+  if (!quads || !quad_off || !last_ids) return PLH_E_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || Wo > kFillChunk * kFillPPT || H >= kMaxCoord || W >= kMaxCoord)
+    return PLH_E_SHAPE;
+  if (mode != 0 && mode != 1) return PLH_E_PARAM;
+  if (mode == 0 && (stride <= 0 || (long long)(Ho - 1) * stride >= H || (long long)(Wo - 1) * stride >= W)) return PLH_E_PARAM;
+  // cv::resize: inv_scale = (double)dsize / ssize; resizeNN: ifx = 1. / inv_scale
+  const double ify = 1.0 / ((double)Ho / (double)H), ifx = 1.0 / ((double)Wo / (double)W);
+  fill_quads_kernel<<<dim3(Ho, B), kFillChunk, 0, (cudaStream_t)stream>>>(quads, quad_off, zero_flags, H, W, Ho, Wo, mode,
+                                                                          stride, ify, ifx, last_ids, first_ids, ids_u8,
+                                                                          score, training_mask);
+  return launch_status();
+}
 
 extern "C" int plh_link_labels_icdar(const int32_t* last_ids, const int32_t* first_ids, int B, int H, int W, int stride,
                                      float* link_lab, float* score, void* stream) {

@@ -4,15 +4,9 @@
 // cv2.drawContours(thickness = -1) and counting mask pixels) and tool/bboxes.py:158-246 bboxes_matching (greedy
 // Pascal-VOC matching in detection order, `ignored` ground truth).
 //
-// No mask is ever materialised.  cv2's filled contour is, row by row, a union of at most six intervals per
-// quadrilateral (oracle/evaluation.py::filled_quad_rows, pinned against cv2 4.13):
-//   * the outline, drawn with cv::line — LineIterator(8-connected, leftToRight): Bresenham from the endpoint
-//     with the smaller x, err0 = dx - 2dy on the major axis, so the minor coordinate after i major steps is
-//     m_i = (2 dminor i + dmajor - 1) / (2 dmajor); the pixels of an edge on one row are therefore one run
-//     with closed-form ends;
-//   * the scan-line spans: for every row in [ymin, ymax) of the non-horizontal edges, the active edges'
-//     abscissae x_e(y) = (x_top << 16) + (y - y_top) * dx_e (16.16 fixed point, dx_e by truncating division)
-//     are sorted and consecutive pairs filled from ceil(x_left) to floor(x_right).
+// No mask is ever materialised: cv2's filled contour is, row by row, a union of at most six intervals per
+// quadrilateral (raster.cuh; the reference's mask starts at (0, 0) and is 10 pixels larger than the largest
+// coordinate, so only its x < 0 / y < 0 sides clip).
 // One warp per (detection, ground truth) pair, one lane per row: the lane builds both interval sets, merges
 // each into disjoint sorted intervals and counts |A|, |B|, |A ∩ B| with a two-pointer sweep; integer counts
 // are reduced over the warp and iou = (float)((double)inter / (double)union) exactly as numpy does it.
@@ -20,65 +14,9 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "raster.cuh"
 
 namespace plh {
-
-constexpr int kMaxIv = 6;  // 4 outline runs + 2 spans per row of a quadrilateral
-constexpr int kMaxCoord = 1 << 20;
-
-struct Ivs {
-  int n;
-  int a[kMaxIv], b[kMaxIv];
-};
-
-__device__ __forceinline__ long long ceil_div_pos(long long a, long long b) {  // b > 0
-  return a >= 0 ? (a + b - 1) / b : -((-a) / b);
-}
-
-// Intervals of the filled quadrilateral (qx, qy) on row y, unsorted, possibly overlapping.
-__device__ void quad_row_intervals(const int* qx, const int* qy, int y, Ivs& out) {
-  out.n = 0;
-  long long xs[4];
-  int nx = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int p0x = qx[(i + 3) & 3], p0y = qy[(i + 3) & 3], p1x = qx[i], p1y = qy[i];
-    {  // outline run of this edge on row y
-      int x0 = p0x, y0 = p0y, dx = p1x - p0x, dy = p1y - p0y;
-      if (dx < 0) x0 = p1x, y0 = p1y, dx = -dx, dy = -dy;
-      const int sy = dy < 0 ? -1 : 1, ady = dy < 0 ? -dy : dy;
-      const int r = (y - y0) * sy;
-      if (r >= 0 && r <= ady) {
-        int lo, hi;
-        if (ady > dx) {
-          lo = hi = (int)((2ll * dx * r + ady - 1) / (2ll * ady));
-        } else if (ady == 0) {
-          lo = 0, hi = dx;
-        } else {
-          lo = (int)max(ceil_div_pos(2ll * dx * r - dx + 1, 2ll * ady), 0ll);
-          hi = (int)min(ceil_div_pos(2ll * dx * (r + 1) - dx + 1, 2ll * ady) - 1, (long long)dx);
-        }
-        if (lo <= hi) out.a[out.n] = x0 + lo, out.b[out.n] = x0 + hi, ++out.n;
-      }
-    }
-    if (p0y != p1y) {  // scan-line edge
-      const long long dxe = (((long long)(p1x - p0x)) << 16) / (p1y - p0y);  // C++ division truncates, as OpenCV's
-      const int yt = p0y < p1y ? p0y : p1y, yb = p0y < p1y ? p1y : p0y, xt = p0y < p1y ? p0x : p1x;
-      if (y >= yt && y < yb) xs[nx++] = ((long long)xt << 16) + (long long)(y - yt) * dxe;
-    }
-  }
-  // sort the (at most 4) abscissae, fill between consecutive pairs
-  for (int i = 1; i < nx; ++i) {
-    const long long v = xs[i];
-    int j = i - 1;
-    while (j >= 0 && xs[j] > v) xs[j + 1] = xs[j], --j;
-    xs[j + 1] = v;
-  }
-  for (int k = 0; k + 1 < nx; k += 2) {
-    const int x1 = (int)((xs[k] + 65535) >> 16), x2 = (int)(xs[k + 1] >> 16);
-    if (x1 <= x2) out.a[out.n] = x1, out.b[out.n] = x2, ++out.n;
-  }
-}
 
 // sort by start, merge overlaps: disjoint ascending intervals; returns the number of pixels covered
 __device__ int normalise(Ivs& s) {
@@ -136,22 +74,28 @@ quad_jaccard_kernel(const int32_t* __restrict__ dets, const int32_t* __restrict_
     for (int k = 0; k < 4; ++k) {
       ax[k] = dets[(size_t)di * 8 + 2 * k], ay[k] = dets[(size_t)di * 8 + 2 * k + 1];
       bx[k] = gts[(size_t)gi * 8 + 2 * k], by[k] = gts[(size_t)gi * 8 + 2 * k + 1];
-      ok = ok && ax[k] >= 0 && ay[k] >= 0 && bx[k] >= 0 && by[k] >= 0 && ax[k] < kMaxCoord && ay[k] < kMaxCoord &&
-           bx[k] < kMaxCoord && by[k] < kMaxCoord;
+      ok = ok && ax[k] > -kMaxCoord && ay[k] > -kMaxCoord && bx[k] > -kMaxCoord && by[k] > -kMaxCoord &&
+           ax[k] < kMaxCoord && ay[k] < kMaxCoord && bx[k] < kMaxCoord && by[k] < kMaxCoord;
       aminx = min(aminx, ax[k]), amaxx = max(amaxx, ax[k]), aminy = min(aminy, ay[k]), amaxy = max(amaxy, ay[k]);
       bminx = min(bminx, bx[k]), bmaxx = max(bmaxx, bx[k]), bminy = min(bminy, by[k]), bmaxy = max(bmaxy, by[k]);
     }
     float iou;
     if (!ok) {
-      iou = __int_as_float(0x7fc00000);  // negative coordinates: cv2 would clip against the mask, not restated
+      iou = __int_as_float(0x7fc00000);  // |coordinate| >= 2^20
     } else if (amaxx < bminx || bmaxx < aminx || amaxy < bminy || bmaxy < aminy) {
       iou = 0.f;  // every drawn pixel lies inside its quadrilateral's bounding box
     } else {
       long long cA = 0, cB = 0, cI = 0;
-      for (int y = min(aminy, bminy) + lane; y <= max(amaxy, bmaxy); y += 32) {
+      QuadEdges EA, EB;
+      // the reference's mask starts at (0, 0) and is 10 pixels larger than the largest coordinate of the image's
+      // boxes (tool/bboxes.py:258-262): its right and bottom sides never clip
+      const long long far = 4ll * kMaxCoord;
+      quad_edges(ax, ay, far, far, EA);
+      quad_edges(bx, by, far, far, EB);
+      for (int y = max(min(aminy, bminy), 0) + lane; y <= max(amaxy, bmaxy); y += 32) {  // rows above the mask are not drawn
         Ivs A, Bv;
-        quad_row_intervals(ax, ay, y, A);
-        quad_row_intervals(bx, by, y, Bv);
+        quad_row_intervals(EA, y, far, A);
+        quad_row_intervals(EB, y, far, Bv);
         cA += normalise(A);
         cB += normalise(Bv);
         cI += intersect_count(A, Bv);

@@ -1,4 +1,5 @@
-"""Mirror of the EAST geometry restore of the reference's ``datasets/icdar.py`` (lines 410-483)."""
+"""Mirror of the reference's ``datasets/icdar.py``: the EAST geometry restore (lines 410-483) and the ground-truth
+generator ``generate_rbox`` with its ``valid_link`` (lines 83-105, 486-539, 632-634)."""
 from __future__ import annotations
 
 from .. import head
@@ -35,37 +36,38 @@ def restore_rectangle(origin, geometry):
     return restore_rectangle_rbox(origin, geometry)
 
 
-def rasterize_polygons(im_size, polys, tags, min_text_size=10):
-    """Host part of generate_rbox (datasets/icdar.py:486-514): cv2.fillPoly of every polygon, in order, with the
-    same float -> int32 truncation of the vertices.  Returns last_ids (poly_mask: index of the LAST polygon
-    covering a pixel), first_ids (index of the FIRST one: which pixels are text once polygons 0..k are in) and
-    training_mask (0 inside polygons that are tagged or smaller than min_text_size, FLAGS.min_text_size :25)."""
-    import cv2
+def _rasterize_device(im_size, polys, tags, min_text_size):
     import numpy as np
+    import torch
     h, w = int(im_size[0]), int(im_size[1])
-    last = np.zeros((h, w), np.int32)
-    first = np.zeros((h, w), np.int32)
-    training_mask = np.ones((h, w), np.uint8)
     polys = np.asarray(polys)
-    quads = [np.asarray(p).astype(np.int32)[np.newaxis, :, :] for p in polys]
-    for k, (poly, tag) in enumerate(zip(polys, tags)):
-        cv2.fillPoly(last, quads[k], k + 1)
+    quads = polys.astype(np.int32).reshape(-1, 4, 2)               # np.int32 truncation, datasets/icdar.py:497
+    zero = np.zeros((len(quads),), np.uint8)
+    for k, (poly, tag) in enumerate(zip(polys, tags)):             # :499-503 (host: four norms per polygon)
         poly_h = min(np.linalg.norm(poly[0] - poly[3]), np.linalg.norm(poly[1] - poly[2]))
         poly_w = min(np.linalg.norm(poly[0] - poly[1]), np.linalg.norm(poly[2] - poly[3]))
-        if min(poly_h, poly_w) < min_text_size or tag:
-            cv2.fillPoly(training_mask, quads[k], 0)
-    for k in range(len(quads) - 1, -1, -1):          # earliest polygon wins
-        cv2.fillPoly(first, quads[k], k + 1)
-    return last, first, training_mask
+        zero[k] = 1 if (min(poly_h, poly_w) < min_text_size or tag) else 0
+    dev = head._require_gpu(None)
+    return head.fill_quads_raw(torch.as_tensor(quads).to(dev), [len(quads)], h, w, h, w, mode=0, stride=1,
+                               zero_flags=torch.as_tensor(zero).to(dev), want=("last", "first", "training_mask"))
+
+
+def rasterize_polygons(im_size, polys, tags, min_text_size=10):
+    """The drawing half of generate_rbox (datasets/icdar.py:486-514): cv2.fillPoly of every polygon, in order, with
+    the same float -> int32 truncation of the vertices — on the GPU (`plh_fill_quads`, bit-identical to OpenCV).
+    Returns last_ids (poly_mask: index of the LAST polygon covering a pixel), first_ids (index of the FIRST one:
+    which pixels are text once polygons 0..k are in) and training_mask (0 inside polygons that are tagged or
+    smaller than min_text_size, FLAGS.min_text_size :25), as numpy arrays."""
+    out = _rasterize_device(im_size, polys, tags, min_text_size)
+    return out["last"][0].cpu().numpy(), out["first"][0].cpu().numpy(), out["training_mask"][0].cpu().numpy()
 
 
 def _generate(im_size, polys, tags, min_text_size, stride):
     import numpy as np
-    import torch
-    last, first, training_mask = rasterize_polygons(im_size, polys, tags, min_text_size)
-    dev = head._require_gpu()
-    link, score = head.link_labels_icdar_raw(torch.as_tensor(last[None]).to(dev), torch.as_tensor(first[None]).to(dev), stride)
-    return score[0].cpu().numpy().astype(np.uint8), link[0].cpu().numpy(), training_mask[::stride, ::stride]
+    out = _rasterize_device(im_size, polys, tags, min_text_size)
+    link, score = head.link_labels_icdar_raw(out["last"], out["first"], stride)
+    return (score[0].cpu().numpy().astype(np.uint8), link[0].cpu().numpy(),
+            out["training_mask"][0, ::stride, ::stride].cpu().numpy())
 
 
 def generate_rbox(im_size, polys, tags, min_text_size=10):

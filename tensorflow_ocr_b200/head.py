@@ -353,6 +353,45 @@ def contour_boxes_raw(mask: torch.Tensor, ratio_w: float = 1.0, ratio_h: float =
     return out
 
 
+def fill_quads_raw(quads: torch.Tensor, counts, H: int, W: int, Ho: int, Wo: int, mode: int = 0, stride: int = 1,
+                   zero_flags: Optional[torch.Tensor] = None, want=("last",)) -> dict:
+    """plh_fill_quads: cv2.fillPoly of every image's quadrilaterals, in order, sampled on the output grid.
+
+    quads int32 [sum n_b,4,2] (CUDA), counts: polygons per image (host sequence); mode 0: every stride-th canvas
+    pixel, mode 1: cv2.resize(INTER_NEAREST) to (Ho, Wo).  want: any of "last" (always), "first", "ids_u8", "score",
+    "training_mask" -> dict of [B,Ho,Wo] tensors."""
+    lib = _lib.load()
+    dev = quads.device
+    _require_gpu(dev)
+    if quads.dtype != torch.int32:
+        raise ValueError("quads must be int32")
+    counts = [int(c) for c in counts]
+    B = len(counts)
+    if B == 0 or quads.numel() != 8 * sum(counts):
+        raise ValueError("counts do not add up to the polygon array")
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + c)
+    quads = quads.contiguous() if quads.numel() else torch.zeros((1, 4, 2), dtype=torch.int32, device=dev)
+    q_off = torch.tensor(off, dtype=torch.int32).to(dev, non_blocking=True)
+    if zero_flags is not None:
+        if zero_flags.dtype != torch.uint8 or zero_flags.numel() != off[-1]:
+            raise ValueError("zero_flags must be uint8, one per polygon")
+        zero_flags = zero_flags.contiguous() if off[-1] else None
+    shape = (B, int(Ho), int(Wo))
+    out = {"last": torch.empty(shape, dtype=torch.int32, device=dev),
+           "first": torch.empty(shape, dtype=torch.int32, device=dev) if "first" in want else None,
+           "ids_u8": torch.empty(shape, dtype=torch.uint8, device=dev) if "ids_u8" in want else None,
+           "score": torch.empty(shape, dtype=torch.float32, device=dev) if "score" in want else None,
+           "training_mask": torch.empty(shape, dtype=torch.uint8, device=dev) if "training_mask" in want else None}
+    with torch.cuda.device(dev):
+        rc = lib.plh_fill_quads(_p(quads), _p(q_off), _p(zero_flags), B, int(H), int(W), int(Ho), int(Wo), int(mode),
+                                int(stride), _p(out["last"]), _p(out["first"]), _p(out["ids_u8"]), _p(out["score"]),
+                                _p(out["training_mask"]), _stream(dev))
+    _lib.check(rc, "plh_fill_quads")
+    return out
+
+
 def bboxes_matching_raw(dets: torch.Tensor, gts: torch.Tensor, det_counts, gt_counts, gignored: torch.Tensor,
                         matching_threshold: float = 0.5) -> dict:
     """plh_quad_jaccard + plh_bboxes_matching over a batch of images (tool/bboxes.py:158-282).

@@ -29,16 +29,17 @@ def _gt_quads(gxs, gys, device=None):
     return torch.stack([gx, gy], dim=-1).contiguous(), np_in
 
 
-def _check_non_negative(*arrays):
+def _check_range(*arrays):
     for a in arrays:
-        if isinstance(a, np.ndarray) and a.size and a.min() < 0:
-            raise ValueError("negative coordinates are not supported (cv2 clips such polygons against its mask)")
+        if isinstance(a, np.ndarray) and a.size and np.abs(a).max() >= (1 << 20):
+            raise ValueError("box coordinates must be smaller than 2^20 in magnitude")
 
 
 def np_bboxes_jaccard(bbox, gxs, gys):
     """tool/bboxes.py:252-282: Jaccard of the quadrilateral ``bbox`` (8,) against the G quadrilaterals
-    (``gxs``, ``gys`` [G,4]), both rasterised like ``cv2.drawContours(thickness=-1)``.  float32 [G]."""
-    _check_non_negative(np.asarray(bbox) if not torch.is_tensor(bbox) else None,
+    (``gxs``, ``gys`` [G,4]), both rasterised like ``cv2.drawContours(thickness=-1)`` on the reference's mask (origin
+    (0, 0), 10 pixels beyond the largest coordinate: negative coordinates are clipped as cv2 clips them).  float32 [G]."""
+    _check_range(np.asarray(bbox) if not torch.is_tensor(bbox) else None,
                         np.asarray(gxs) if not torch.is_tensor(gxs) else None,
                         np.asarray(gys) if not torch.is_tensor(gys) else None)
     det, np_in = _quads(bbox, "bbox")
@@ -58,7 +59,7 @@ def bboxes_jaccard(bbox, gxs, gys):
 def bboxes_matching(bboxes, gxs, gys, gignored, matching_threshold=0.5, scope=None):
     """tool/bboxes.py:158-246.  ``bboxes`` [N,8] detections in score order, ``gxs`` / ``gys`` [G,4], ``gignored``
     [G].  -> (n_gbboxes, tp_match [N] bool, fp_match [N] bool)."""
-    _check_non_negative(np.asarray(bboxes) if not torch.is_tensor(bboxes) else None,
+    _check_range(np.asarray(bboxes) if not torch.is_tensor(bboxes) else None,
                         np.asarray(gxs) if not torch.is_tensor(gxs) else None,
                         np.asarray(gys) if not torch.is_tensor(gys) else None)
     dets, np_in = _quads(bboxes, "bboxes")
@@ -81,7 +82,7 @@ def bboxes_matching_batch(bboxes, gxs, gys, gignored, matching_threshold=0.5):
     dets = [np.asarray(b, np.int32).reshape(-1, 4, 2) for b in bboxes]
     gts = [np.stack([np.asarray(x, np.int32), np.asarray(y, np.int32)], -1).reshape(-1, 4, 2) for x, y in zip(gxs, gys)]
     ign = [np.asarray(g).astype(bool).astype(np.uint8).reshape(-1) for g in gignored]
-    _check_non_negative(*dets, *gts)
+    _check_range(*dets, *gts)
     dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
     d, _ = head.to_device(np.concatenate(dets) if dets else np.zeros((0, 4, 2), np.int32), dtype=torch.int32, device=dev)
     g, _ = head.to_device(np.concatenate(gts), dtype=torch.int32, device=d.device)

@@ -46,39 +46,46 @@ def link_labels_from_ids(poly_mask):
     return link.cpu().numpy() if np_in else link
 
 
-def rasterize_polygons(h, w, xs, ys):
-    """Host part of generate_rbox (tool/pixellink_fn.py:60-79): fill every polygon at full resolution —
-    1.0 into the score map, its 1-based index into the id map — then nearest-neighbour resize both to
-    (w//4, h//4).  Same OpenCV calls and the same float32 -> int32 truncation of the vertex coordinates as
-    the reference; a handful of polygons per image, so this stays on the host."""
-    import cv2
-    h, w = int(h), int(w)
-    full_score = np.zeros((h, w), dtype=np.float32)
-    full_ids = np.zeros((h, w), dtype=np.uint8)
+def _canvas_quads(h, w, xs, ys):
+    """Vertices as the reference makes them (tool/pixellink_fn.py:68-76): float32 products, truncated to int32."""
     vx = np.asarray(xs, dtype=np.float32) * w      # float32 products, like xs[idx, :] * w
     vy = np.asarray(ys, dtype=np.float32) * h
-    vertices = np.stack([vx, vy], axis=-1).astype(np.int32)   # [n, 4, 2]
-    for number, quad in enumerate(vertices, start=1):
-        cv2.fillPoly(full_score, quad[None], 1.0)
-        cv2.fillPoly(full_ids, quad[None], number)
-    small = (w // 4, h // 4)                        # Python-2 integer division in the reference (:56-57)
-    return (cv2.resize(full_score, small, interpolation=cv2.INTER_NEAREST),
-            cv2.resize(full_ids, small, interpolation=cv2.INTER_NEAREST))
+    return np.stack([vx, vy], axis=-1).astype(np.int32).reshape(-1, 4, 2)
+
+
+def _rasterize_device(h, w, xs, ys):
+    h, w = int(h), int(w)
+    quads = _canvas_quads(h, w, xs, ys)
+    dev = head._require_gpu(None)
+    out = head.fill_quads_raw(torch.as_tensor(quads).to(dev), [len(quads)], h, w, h // 4, w // 4, mode=1,
+                              want=("last", "ids_u8", "score"))    # Python-2 integer division in the reference (:56-57)
+    return out["score"][0], out["ids_u8"][0]
+
+
+def rasterize_polygons(h, w, xs, ys):
+    """tool/pixellink_fn.py:60-79: every polygon filled at full resolution — 1.0 into the score map, its 1-based
+    index into the uint8 id map — then both shrunk to (w//4, h//4) with cv2.resize(INTER_NEAREST).  On the GPU
+    (`plh_fill_quads`): bit-identical to the OpenCV calls, without drawing the full-resolution canvases.
+    -> (res_score_map float32 [h//4, w//4], poly_mask uint8 [h//4, w//4])."""
+    score, ids = _rasterize_device(h, w, xs, ys)
+    return score.cpu().numpy(), ids.cpu().numpy()
 
 
 def generate_rbox(h, w, xs, ys, bboxes, ignored):
     """tool/pixellink_fn.py:53-111.  Same arguments and returns (res_score_map [h/4,w/4] fp32,
     res_link_map [h/4,w/4,8] fp32, show_bboxes [200,4] fp32) as numpy arrays.
 
-    The polygon rasterisation stays on the host (`rasterize_polygons`); the per-pixel link-label loop —
-    O(pixels x 8) interpreted Python in the reference — runs on the GPU (`plh_link_labels`)."""
+    Both halves run on the GPU: the polygon rasterisation + nearest shrink (`plh_fill_quads`) and the per-pixel
+    link-label loop — O(pixels x 8) interpreted Python in the reference (`plh_link_labels`); the id map never
+    leaves the device in between."""
     if len(xs) != len(ignored):
         raise AssertionError("the length of xs and ignored must be the same, but got %s and %s" % (len(xs), len(ignored)))
     n = len(xs)
     show_bboxes = np.zeros((200, 4), dtype=np.float32)   # fixed 200 rows (:65)
     show_bboxes[:n] = np.asarray(bboxes)[:n]
-    res_score_map, ids = rasterize_polygons(h, w, xs, ys)
-    return res_score_map, link_labels_from_ids(ids), show_bboxes
+    score, ids = _rasterize_device(h, w, xs, ys)
+    link, _ = head.link_labels_raw(ids[None], want_pixel=False)
+    return score.cpu().numpy(), link[0].cpu().numpy(), show_bboxes
 
 
 def tf_pixellink_get_rbox(img_size, xs, ys, bboxes, ignored):

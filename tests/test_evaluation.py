@@ -64,6 +64,40 @@ def test_filled_polygon_rows_vs_cv2():
         assert np.array_equal(ref, got), pts.tolist()
 
 
+def test_clipped_lines_and_polygons_vs_cv2():
+    """Vertices outside the image: cv::clipLine, and the edge table built from the clipped segments."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(6)
+    for t in range(3000):
+        p = rng.integers(-40, 90, (2, 2))
+        w, h = 60, 50
+        ref = np.zeros((h, w), np.uint8)
+        cv2.line(ref, tuple(int(v) for v in p[0]), tuple(int(v) for v in p[1]), 1, 1, 8)
+        vis, q0, q1 = oe.clip_line(w, h, tuple(int(v) for v in p[0]), tuple(int(v) for v in p[1]))
+        got = oe.mask_from_rows({y: [r] for y, r in oe.line_row_runs(q0, q1).items()} if vis else {}, (h, w))
+        assert np.array_equal(ref, got), p.tolist()
+    for t in range(3000):
+        pts = (rng.integers(-30, 80, (4, 2)) if t % 2 else rng.integers(-8, 40, (4, 2))).astype(np.int32)
+        if t % 3 == 0:   # the reference's mask: 10 more than the largest coordinate, so only x < 0 / y < 0 clip
+            h, w = max(int(pts[:, 1].max()), 1) + 10, max(int(pts[:, 0].max()), 1) + 10
+        else:
+            h, w = 50, 60
+        ref = np.zeros((h, w), np.uint8)
+        cv2.drawContours(ref, [pts.reshape(-1, 1, 2)], -1, 1, -1)
+        got = oe.mask_from_rows(oe.filled_quad_rows([tuple(int(v) for v in p) for p in pts], w, h), (h, w))
+        assert np.array_equal(ref, got), (pts.tolist(), h, w)
+
+
+def test_interval_jaccard_with_negative_coordinates():
+    rng = np.random.default_rng(8)
+    for t in range(40):
+        bbox = rng.integers(-15, 60, 8)
+        gxs, gys = rng.integers(-15, 70, (3, 4)), rng.integers(-15, 50, (3, 4))
+        if max(bbox[0::2].max(), gxs.max()) < 0 or max(bbox[1::2].max(), gys.max()) < 0:
+            continue
+        assert np.array_equal(oe.quad_jaccard_rows(bbox, gxs, gys), oe.np_bboxes_jaccard(bbox, gxs, gys)), (bbox, gxs, gys)
+
+
 def test_metrics_mirror_equals_the_reference(gold):
     from tensorflow_ocr_b200.tool import metrics
     state = None

@@ -222,3 +222,87 @@ def test_east_loss_at_config4_shape(cuda_dev):
     assert rel_err(outv[0].item(), ref["loss"]) <= TOL
     assert rel_err(gs.cpu().numpy(), ref["grad_score"]) <= TOL
     assert rel_err(gg.cpu().numpy(), ref["grad_geo"]) <= 5e-5   # cosf/sinf/logf vs numpy: a few ulp on tiny terms
+
+
+def test_rasterize_polygons_matches_reference_execution(golden_dir, cuda_dev):
+    """Drawing half of the generate_rbox mirror (plh_fill_quads: cv2.fillPoly + nearest resize on the GPU) vs the
+    reference-executed golden: the score map directly, the id map through the oracle's link labels."""
+    import numpy as np
+    from oracle import labels as OL
+    from tensorflow_ocr_b200.tool import pixellink_fn
+    g = np.load(golden_dir + "/generate_rbox.npz")
+    for ci in range(int(g["n_cases"])):
+        score, ids = pixellink_fn.rasterize_polygons(int(g["h%d" % ci]), int(g["w%d" % ci]), g["xs%d" % ci], g["ys%d" % ci])
+        assert np.array_equal(score, g["score%d" % ci])
+        assert ids.dtype == np.uint8 and np.array_equal(OL.link_labels_from_ids(ids), g["link%d" % ci])
+
+
+@pytest.mark.parametrize("case", ["inside", "leaving", "tiny", "many"])
+def test_fill_quads_vs_cv2(case, cuda_dev):
+    """plh_fill_quads against the OpenCV calls it replaces: cv2.fillPoly of every polygon in order (last / first
+    covering polygon, uint8 saturation, flagged polygons clearing the training mask), sampled with [::s, ::s] and
+    with cv2.resize(INTER_NEAREST); polygons that leave the canvas are clipped the way cv2 clips them."""
+    import cv2
+    import torch
+    from tensorflow_ocr_b200 import head
+    rng = np.random.default_rng({"inside": 1, "leaving": 2, "tiny": 3, "many": 4}[case])
+    shapes = {"inside": [(128, 128), (96, 160)], "leaving": [(100, 140), (64, 64)], "tiny": [(9, 13), (33, 21)], "many": [(150, 200)]}[case]
+    for (H, W) in shapes:
+        counts, quads, flags = [], [], []
+        for b in range(3):
+            n = {"inside": 9, "leaving": 14, "tiny": 5, "many": 300}[case] + b
+            lo, hi = (0.0, 1.0) if case == "inside" else (-0.4, 1.4)
+            q = []
+            for k in range(n):
+                if k % 4 == 3:   # arbitrary (possibly self-intersecting) quadrilateral
+                    q.append(np.stack([rng.uniform(lo, hi, 4) * W, rng.uniform(lo, hi, 4) * H], -1))
+                else:
+                    c = np.array([rng.uniform(lo, hi) * W, rng.uniform(lo, hi) * H])
+                    hw, hh, a = rng.uniform(0.02, 0.3) * W, rng.uniform(0.02, 0.15) * H, rng.uniform(-1.0, 1.0)
+                    R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+                    q.append(np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T + c)
+            q = np.stack(q).astype(np.float32).astype(np.int32)
+            if case == "inside":
+                q = np.clip(q, 0, [W - 1, H - 1]).astype(np.int32)
+            counts.append(n), quads.append(q), flags.append((rng.uniform(size=n) < 0.3).astype(np.uint8))
+        dq = torch.as_tensor(np.concatenate(quads)).to(cuda_dev)
+        df = torch.as_tensor(np.concatenate(flags)).to(cuda_dev)
+        ref = []
+        for b in range(3):
+            last, first, u8, tm = np.zeros((H, W), np.int32), np.zeros((H, W), np.int32), np.zeros((H, W), np.uint8), np.ones((H, W), np.uint8)
+            score = np.zeros((H, W), np.float32)
+            for k, quad in enumerate(quads[b]):
+                cv2.fillPoly(last, quad[None], k + 1), cv2.fillPoly(u8, quad[None], k + 1), cv2.fillPoly(score, quad[None], 1.0)
+                if flags[b][k]:
+                    cv2.fillPoly(tm, quad[None], 0)
+            for k in range(len(quads[b]) - 1, -1, -1):
+                cv2.fillPoly(first, quads[b][k][None], k + 1)
+            ref.append((last, first, u8, score, tm))
+        want = ("last", "first", "ids_u8", "score", "training_mask")
+        for stride in (1, 4):
+            Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+            out = head.fill_quads_raw(dq, counts, H, W, Ho, Wo, mode=0, stride=stride, zero_flags=df, want=want)
+            for b in range(3):
+                for name, r in zip(want, ref[b]):
+                    assert np.array_equal(out[name][b].cpu().numpy(), r[::stride, ::stride]), (case, H, W, stride, b, name)
+        if H >= 4 and W >= 4:
+            Ho, Wo = H // 4, W // 4
+            out = head.fill_quads_raw(dq, counts, H, W, Ho, Wo, mode=1, zero_flags=df, want=want)
+            for b in range(3):
+                for name, r in zip(want, ref[b]):
+                    rr = cv2.resize(r.astype(np.float32) if r.dtype == np.int32 else r, (Wo, Ho), interpolation=cv2.INTER_NEAREST)
+                    assert np.array_equal(out[name][b].cpu().numpy(), rr.astype(r.dtype)), (case, H, W, "resize", b, name)
+
+
+def test_fill_quads_argument_errors(cuda_dev):
+    import torch
+    from tensorflow_ocr_b200 import head
+    q = torch.zeros((2, 4, 2), dtype=torch.int32, device=cuda_dev)
+    with pytest.raises(ValueError):
+        head.fill_quads_raw(q, [3], 32, 32, 32, 32)                       # counts do not add up
+    with pytest.raises(ValueError):
+        head.fill_quads_raw(q, [2], 32, 32, 32, 4096)                     # output wider than 2048
+    with pytest.raises(ValueError):
+        head.fill_quads_raw(q, [2], 32, 32, 32, 32, mode=0, stride=2)     # grid reaches past the canvas
+    out = head.fill_quads_raw(q[:0], [0], 16, 16, 16, 16, want=("last", "training_mask"))   # no polygons: empty maps
+    assert int(out["last"].abs().sum()) == 0 and int(out["training_mask"].min()) == 1

@@ -91,11 +91,31 @@ def test_degenerate_and_identical_quads():
     assert tb.np_bboxes_jaccard(np.array([10, 10, 50, 10, 50, 30, 10, 30]), gxs, gys)[0] == 1.0
 
 
+def test_negative_coordinates_are_clipped_like_cv2():
+    """Boxes sticking out of the image at the top / left (minAreaRect corners near the border do)."""
+    from oracle import evaluation as oe
+    from tensorflow_ocr_b200.tool import bboxes as tb
+    rng = np.random.default_rng(17)
+    n = 0
+    for t in range(60):
+        lo = -25 if t % 2 else -6
+        bboxes = rng.integers(lo, 90, (4, 8)).astype(np.int32)
+        gxs, gys = rng.integers(lo, 100, (5, 4)).astype(np.int32), rng.integers(lo, 70, (5, 4)).astype(np.int32)
+        gi = (rng.uniform(size=5) < 0.2).astype(np.int32)
+        for b in bboxes:
+            assert np.array_equal(tb.np_bboxes_jaccard(b, gxs, gys), oe.np_bboxes_jaccard(b, gxs, gys)), (b, gxs, gys)
+            n += 1
+        o_n, o_tp, o_fp = oe.bboxes_matching(bboxes, gxs, gys, gi, 0.3)
+        g_n, g_tp, g_fp = tb.bboxes_matching(bboxes, gxs, gys, gi, matching_threshold=0.3)
+        assert int(g_n) == o_n and np.array_equal(g_tp, o_tp) and np.array_equal(g_fp, o_fp)
+    assert n == 240
+
+
 def test_argument_errors():
     from tensorflow_ocr_b200.tool import bboxes as tb
     gxs = np.array([[1, 5, 5, 1]]); gys = np.array([[1, 1, 5, 5]])
     with pytest.raises(ValueError):
-        tb.np_bboxes_jaccard(np.array([-1, 0, 5, 0, 5, 5, 0, 5]), gxs, gys)          # negative coordinate
+        tb.np_bboxes_jaccard(np.array([1 << 20, 0, 5, 0, 5, 5, 0, 5]), gxs, gys)     # coordinate out of range
     with pytest.raises(ValueError):
         tb.np_bboxes_jaccard(np.arange(8), np.zeros((0, 4), np.int32), np.zeros((0, 4), np.int32))   # no ground truth
     with pytest.raises(ValueError):

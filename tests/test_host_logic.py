@@ -209,17 +209,3 @@ def test_scheduling_hints_map_to_the_reserved_words():
     hdr = open(os.path.join(ROOT, "include", "plhead.h")).read()
     for word in ("bit 2: only the first kernel", "bit 3: everything after it", "Bit 1: scheduling hint", "Bit 2: scheduling hint"):
         assert word in hdr, word
-
-
-def test_rasterize_polygons_matches_reference_execution(golden_dir):
-    """Host half of the generate_rbox mirror (cv2 fill + nearest resize) vs the reference-executed golden:
-    the score map directly, the id map through the oracle's link labels (the GPU half is tested in
-    tests/test_gpu_aux.py)."""
-    import numpy as np
-    from oracle import labels as OL
-    from tensorflow_ocr_b200.tool import pixellink_fn
-    g = np.load(golden_dir + "/generate_rbox.npz")
-    for ci in range(int(g["n_cases"])):
-        score, ids = pixellink_fn.rasterize_polygons(int(g["h%d" % ci]), int(g["w%d" % ci]), g["xs%d" % ci], g["ys%d" % ci])
-        assert np.array_equal(score, g["score%d" % ci])
-        assert ids.dtype == np.uint8 and np.array_equal(OL.link_labels_from_ids(ids), g["link%d" % ci])
