@@ -267,6 +267,28 @@ PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double r
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The head's logit producer: one level of the feature fusion that ends both networks,
+ * nets/pixellink.py:37-38,56-67 and nets/model.py:14-15,129-141 —
+ *     y = bilinear_x2(prev) + act_a(scale_a * (xa Wa) + shift_a) [+ act_b(scale_b * (xb Wb) + shift_b)]
+ * and, when w_out is given (the last level),  logits = y w_out + b_out, split into the pixel and link tensors the
+ * loss / decode entry points read.  The 2 pixel and 16 link channels go through together: 18 columns, pixel first.
+ *  xa, xb    [B,H,W,Ka] / [B,H,W,Kb] float NHWC feature maps (xb optional: fc7 + conv5_3 share a level); K % 4 == 0
+ *  wa, wb    [K,18] float: the 1x1 convolutions' weights, pixel columns 0-1, link columns 2-17
+ *  scale, shift [18] optional: per-channel affine after the convolution (shift alone = bias; both = batch norm in
+ *            its inference form); relu != 0: ReLU after it (nets/model.py:103-107 arg_scope)
+ *  prev      [B,H/2,W/2,18] optional: the previous level, upsampled like tf.image.resize_bilinear(align_corners =
+ *            False) does for an exact factor 2
+ *  w_out [18,18] (in, out), b_out [18] optional; y18 [B,H,W,18] (w_out null) or pix_logits [B,H,W,2] +
+ *            link_logits [B,H,W,16] (w_out given)
+ * fp32 in, fp32 out; products on the tensor cores with the 3xTF32 split (fp32-accurate: within 1e-5 of an fp64
+ * evaluation relative to the largest logit, the contract tests/test_gpu_headfuse.py states).
+ */
+PLH_API int plh_head_fuse_level(const float* xa, int Ka, const float* wa, const float* scale_a, const float* shift_a, int relu_a,
+                        const float* xb, int Kb, const float* wb, const float* scale_b, const float* shift_b, int relu_b,
+                        const float* prev, const float* w_out, const float* b_out, int B, int H, int W, float* y18,
+                        float* pix_logits, float* link_logits, void* stream);
+
+/*
  * Detection evaluation.
  * plh_quad_jaccard — tool/bboxes.py:252-282 np_bboxes_jaccard for every (detection, ground truth) pair of every
  * image: both quadrilaterals rasterised as cv2.drawContours(thickness = -1) draws them (outline by cv::line +

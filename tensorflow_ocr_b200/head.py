@@ -353,6 +353,49 @@ def contour_boxes_raw(mask: torch.Tensor, ratio_w: float = 1.0, ratio_h: float =
     return out
 
 
+def head_fuse_level_raw(feats, prev: Optional[torch.Tensor] = None, w_out: Optional[torch.Tensor] = None,
+                        b_out: Optional[torch.Tensor] = None):
+    """plh_head_fuse_level: one level of the logit producer (nets/pixellink.py:56-67, nets/model.py:129-141).
+
+    feats: one or two (x [B,H,W,K], w [K,18], scale [18] | None, shift [18] | None, relu) tuples (CUDA fp32);
+    prev [B,H/2,W/2,18] | None; w_out [18,18] (in, out) + b_out [18] for the last level.
+    -> y18 [B,H,W,18], or (pixel logits [B,H,W,2], link logits [B,H,W,16]) when w_out is given."""
+    lib = _lib.load()
+    if not 1 <= len(feats) <= 2:
+        raise ValueError("a level fuses one or two feature maps")
+    x0 = feats[0][0]
+    dev = x0.device
+    _require_gpu(dev)
+    B, H, W = x0.shape[:3]
+    keep, flat = [], []
+    for (x, w, scale, shift, relu) in feats:
+        if x.dim() != 4 or tuple(x.shape[:3]) != (B, H, W) or tuple(w.shape) != (x.shape[3], 18):
+            raise ValueError("feature [B,H,W,K] with weights [K,18] expected, got %s / %s" % (tuple(x.shape), tuple(w.shape)))
+        t = [x.contiguous().float(), w.contiguous().float(), None if scale is None else scale.contiguous().float(),
+             None if shift is None else shift.contiguous().float()]
+        keep.append(t)
+        flat += [_p(t[0]), int(x.shape[3]), _p(t[1]), _p(t[2]), _p(t[3]), int(bool(relu))]
+    if len(feats) == 1:
+        flat += [None, 0, None, None, None, 0]
+    if prev is not None:
+        if tuple(prev.shape) != (B, H // 2, W // 2, 18) or H % 2 or W % 2:
+            raise ValueError("prev must be [B,H/2,W/2,18], got %s for a %dx%d level" % (tuple(prev.shape), H, W))
+        prev = prev.contiguous()
+    if w_out is not None:
+        w_out = w_out.contiguous().float()
+        b_out = None if b_out is None else b_out.contiguous().float()
+        pix = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev)
+        link = torch.empty((B, H, W, 16), dtype=torch.float32, device=dev)
+        y18 = None
+    else:
+        y18 = torch.empty((B, H, W, 18), dtype=torch.float32, device=dev)
+        pix = link = None
+    with torch.cuda.device(dev):
+        rc = lib.plh_head_fuse_level(*flat, _p(prev), _p(w_out), _p(b_out), B, H, W, _p(y18), _p(pix), _p(link), _stream(dev))
+    _lib.check(rc, "plh_head_fuse_level")
+    return y18 if w_out is None else (pix, link)
+
+
 def fill_quads_raw(quads: torch.Tensor, counts, H: int, W: int, Ho: int, Wo: int, mode: int = 0, stride: int = 1,
                    zero_flags: Optional[torch.Tensor] = None, want=("last",)) -> dict:
     """plh_fill_quads: cv2.fillPoly of every image's quadrilaterals, in order, sampled on the output grid.

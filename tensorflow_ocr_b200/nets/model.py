@@ -12,7 +12,7 @@ import torch
 
 from .. import _lib, head
 
-__all__ = ["dice_coefficient", "OHNM_single_image", "OHNM_batch", "get_pos_and_neg_masks", "loss",
+__all__ = ["feature_fusion", "dice_coefficient", "OHNM_single_image", "OHNM_batch", "get_pos_and_neg_masks", "loss",
            "loss_with_stats"]
 
 
@@ -139,3 +139,48 @@ def dice_coefficient(y_true_cls, y_pred_cls, training_mask):
         outv, _ = head.dice_raw(t, p, m, want_grad=False)
         return outv[0].cpu().numpy()[()]
     return _Dice.apply(p, t, m)
+
+
+def feature_fusion(feature_maps, params):
+    """nets/model.py:129-141 (with ``unpool`` :14-15): the fusion that ends ``model()``,
+
+        pixel_1 = unpool(c(f0)) + c(f1);  pixel_2 = unpool(pixel_1) + c(f2);  pixel_3 = unpool(pixel_2) + c(f3)
+        pixel_4 = conv1x1(pixel_3)                        (and the same for the 16 link channels)
+
+    where ``c`` is ``slim.conv2d(., n, 1)`` under the arg_scope of :103-107 — batch norm, here in its INFERENCE
+    form folded to a per-channel scale and shift, then ReLU.  ``feature_maps`` = [pool5, pool4, pool3, pool2]
+    (NHWC, each level twice the previous one); ``params["pixel"]`` / ``params["link"]`` = five
+    ``(weights [K,n], scale [n] | None, shift [n])`` triples: the four fuse convolutions f0..f3 and the plain last one.
+    Returns ``(pixel_4 [B,H,W,2], link_4 [B,H,W,16])`` (numpy in -> numpy out)."""
+    import torch
+    np_in, dev, x = False, None, []
+    for f in feature_maps:
+        t, was_np = head.to_device(f, device=dev)
+        dev, np_in = t.device, np_in or was_np
+        x.append(t)
+
+    def cat(i, j, ones=False):
+        a, b = params["pixel"][i][j], params["link"][i][j]
+        if a is None and b is None:
+            return None
+        a = np.ones(2, np.float32) if a is None else a
+        b = np.ones(16, np.float32) if b is None else b
+        ta, _ = head.to_device(a, device=dev)
+        tb, _ = head.to_device(b, device=dev)
+        return torch.cat([ta, tb], dim=-1).contiguous()
+
+    prev = None
+    for i in range(4):
+        feat = (x[i], cat(i, 0), cat(i, 1), cat(i, 2), True)
+        if i < 3:
+            prev = head.head_fuse_level_raw([feat], prev=prev)
+        else:
+            w_out = torch.zeros((18, 18), dtype=torch.float32, device=dev)
+            w_out[:2, :2], _ = head.to_device(params["pixel"][4][0], device=dev)
+            w_out[2:, 2:], _ = head.to_device(params["link"][4][0], device=dev)
+            if params["pixel"][4][1] is not None or params["link"][4][1] is not None:
+                w_out = w_out * cat(4, 1)[None, :]
+            pixel_4, link_4 = head.head_fuse_level_raw([feat], prev=prev, w_out=w_out, b_out=cat(4, 2))
+    if np_in:
+        return pixel_4.cpu().numpy(), link_4.cpu().numpy()
+    return pixel_4, link_4

@@ -1,4 +1,5 @@
-"""Mirror of the head part of the reference's ``nets/pixellink.py`` (lines 69-72, 88-263)."""
+"""Mirror of the head part of the reference's ``nets/pixellink.py``: the feature fusion that produces the logits
+(lines 37-38, 56-67) and the loss (lines 69-72, 88-263)."""
 from __future__ import annotations
 
 import torch
@@ -6,7 +7,7 @@ import torch
 from .. import _lib, head
 from .model import _FusedLoss
 
-__all__ = ["PixelLinkNet"]
+__all__ = ["PixelLinkNet", "pixellink_layers"]
 
 
 class PixelLinkNet(object):
@@ -53,3 +54,47 @@ class PixelLinkNet(object):
         if self._np_in:
             self.losses = [l.cpu().numpy()[()] for l in self.losses]
         return None
+
+
+_FUSE_SCOPES = (("fc7", 6), ("conv5_3", 5), ("conv4_3", 4), ("conv3_3", 3))
+
+
+def _cat18(pix, link, device):
+    """Pixel (2 columns) and link (16 columns) parameters side by side: the two branches share one pass."""
+    a, _ = head.to_device(pix, device=device)
+    b, _ = head.to_device(link, device=device)
+    return torch.cat([a, b], dim=-1).contiguous()
+
+
+def pixellink_layers(end_points, params):
+    """nets/pixellink.py:56-67 ``_add_pixellink_layers`` (with ``unpool`` :37-38) on the GPU:
+
+        s1 = conv1x1(fc7) + conv1x1(conv5_3);  s2 = unpool(s1) + conv1x1(conv4_3);
+        s3 = unpool(s2) + conv1x1(conv3_3);    pixel_cls / link_cls = conv1x1(s3)
+
+    ``end_points``: the NHWC feature maps ``fc7``, ``conv5_3`` (1/16), ``conv4_3`` (1/8), ``conv3_3`` (1/4);
+    ``params[scope] = (weights [K,n], biases [n])`` for the reference's ten variable scopes
+    ``stage_{6,5,4,3}_{pixel,link}_fuse``, ``text_predication``, ``link_predication``.
+    Returns ``(pixel_cls [B,H,W,2], link_cls [B,H,W,16])`` (numpy in -> numpy out)."""
+    x = {}
+    np_in = False
+    dev = None
+    for name, _ in _FUSE_SCOPES:
+        x[name], was_np = head.to_device(end_points[name], device=dev)
+        dev = x[name].device
+        np_in = np_in or was_np
+    feats = {}
+    for name, st in _FUSE_SCOPES:
+        w = _cat18(params["stage_%d_pixel_fuse" % st][0], params["stage_%d_link_fuse" % st][0], dev)
+        b = _cat18(params["stage_%d_pixel_fuse" % st][1], params["stage_%d_link_fuse" % st][1], dev)
+        feats[name] = (x[name], w, None, b, False)
+    w_out = torch.zeros((18, 18), dtype=torch.float32, device=dev)     # the two last convolutions as one block matrix
+    w_out[:2, :2], _ = head.to_device(params["text_predication"][0], device=dev)
+    w_out[2:, 2:], _ = head.to_device(params["link_predication"][0], device=dev)
+    b_out = _cat18(params["text_predication"][1], params["link_predication"][1], dev)
+    s1 = head.head_fuse_level_raw([feats["fc7"], feats["conv5_3"]])
+    s2 = head.head_fuse_level_raw([feats["conv4_3"]], prev=s1)
+    pixel_cls, link_cls = head.head_fuse_level_raw([feats["conv3_3"]], prev=s2, w_out=w_out, b_out=b_out)
+    if np_in:
+        return pixel_cls.cpu().numpy(), link_cls.cpu().numpy()
+    return pixel_cls, link_cls

@@ -578,6 +578,129 @@ def golden_evaluation():
     save("evaluation", n_cases=n_cases, **out)
 
 
+# ----------------------------------------------------------------------------- the head's logit producer (N3)
+class _NpSlim:
+    """Eager float64 stand-in for slim.conv2d (1x1 only) / arg_scope / batch_norm, weights supplied by the test:
+    by `scope` name when the call names one (nets/pixellink.py), else in call order (nets/model.py)."""
+
+    def __init__(self, by_scope=None, in_order=None):
+        self.by_scope, self.in_order, self.calls, self.defaults = by_scope, in_order, [], [{}]
+        self.batch_norm = "batch_norm"
+
+    def l2_regularizer(self, _wd):
+        return None
+
+    def arg_scope(self, _fns, **kw):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self.defaults.append({**self.defaults[-1], **kw})
+            try:
+                yield
+            finally:
+                self.defaults.pop()
+        return cm()
+
+    def conv2d(self, x, num_outputs, kernel_size, scope=None, **kw):
+        args = {**self.defaults[-1], **kw}
+        assert kernel_size in (1, [1, 1]), kernel_size
+        rec = self.by_scope[scope] if scope is not None else self.in_order[len(self.calls)]
+        self.calls.append(scope)
+        w = np.asarray(rec["w"], np.float64)
+        assert w.shape == (x.shape[-1], num_outputs), (w.shape, x.shape, num_outputs)
+        y = np.asarray(x, np.float64) @ w
+        if args.get("normalizer_fn") is not None:      # inference-mode batch norm folded to scale / shift
+            y = y * np.asarray(rec["scale"], np.float64) + np.asarray(rec["shift"], np.float64)
+        else:
+            y = y + np.asarray(rec["b"], np.float64)
+        act = args.get("activation_fn")
+        return act(y) if act is not None else y
+
+
+def _np_tf_image():
+    from oracle.head_logits import resize_bilinear_x2
+    t = types.SimpleNamespace()
+    t.shape = lambda x: np.asarray(np.shape(x))
+
+    def resize_bilinear(x, size):
+        assert tuple(int(v) for v in size) == (2 * x.shape[1], 2 * x.shape[2]), size
+        return resize_bilinear_x2(x)     # TF op semantics restated (oracle/head_logits.py)
+    t.image = types.SimpleNamespace(resize_bilinear=resize_bilinear)
+    t.nn = types.SimpleNamespace(relu=lambda v: np.maximum(v, 0.0))
+    t.contrib = types.SimpleNamespace(layers=types.SimpleNamespace(xavier_initializer=lambda: None))
+    t.zeros_initializer = lambda: None
+    return t
+
+
+def golden_head_logits():
+    """nets/pixellink.py:37-38 unpool + :57-67 (the body of _add_pixellink_layers up to link_cls) and
+    nets/model.py:14-15 unpool + :129-141 (pixel_1 .. link_4 inside the arg_scope of :103-107), executed as written
+    over eager float64 stand-ins for slim.conv2d / tf.image.resize_bilinear."""
+    rng = np.random.default_rng(77)
+    tfi = _np_tf_image()
+    out = {}
+    # ---- nets/pixellink.py
+    B, H, W = 1, 16, 24           # 1/4-resolution map; conv4_3 at 1/8, conv5_3 / fc7 at 1/16
+    chans = {"fc7": 40, "conv5_3": 32, "conv4_3": 24, "conv3_3": 20}
+    ep = {"fc7": rng.standard_normal((B, H // 4, W // 4, chans["fc7"])), "conv5_3": rng.standard_normal((B, H // 4, W // 4, chans["conv5_3"])),
+          "conv4_3": rng.standard_normal((B, H // 2, W // 2, chans["conv4_3"])), "conv3_3": rng.standard_normal((B, H, W, chans["conv3_3"]))}
+    ep = {k: v.astype(np.float32) for k, v in ep.items()}
+    weights = {}
+    for kind, n, last in (("pixel", 2, "text_predication"), ("link", 16, "link_predication")):
+        for st, name in ((6, "fc7"), (5, "conv5_3"), (4, "conv4_3"), (3, "conv3_3")):
+            weights["stage_%d_%s_fuse" % (st, kind)] = dict(w=(rng.standard_normal((chans[name], n)) / np.sqrt(chans[name])).astype(np.float32),
+                                                             b=(0.1 * rng.standard_normal(n)).astype(np.float32))
+        weights[last] = dict(w=(rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32), b=(0.1 * rng.standard_normal(n)).astype(np.float32))
+    slim_ = _NpSlim(by_scope=weights)
+    ns = dict(tf=tfi, slim=slim_)
+    exec(cut_lines("nets/pixellink.py", 37, 38), ns)                       # def unpool(self, inputs)
+    self_ = types.SimpleNamespace(weight_decay=1e-5, unpool=lambda x: ns["unpool"](None, x))
+    body = cut_lines("nets/pixellink.py", 57, 67)
+    print("nets/pixellink.py:57-67\n" + "\n".join("   | " + l[:110] for l in body.split("\n")[:3]) + "\n   | ...")
+    ns.update(self=self_, end_points=ep)
+    exec(body, ns)
+    assert len(slim_.calls) == 10, slim_.calls
+    for k, v in ep.items():
+        out["pl_" + k] = v
+    for k, v in weights.items():
+        out["pl_w_" + k], out["pl_b_" + k] = v["w"], v["b"]
+    out["pl_pixel_cls"], out["pl_link_cls"] = ns["pixel_cls"].astype(np.float32), ns["link_cls"].astype(np.float32)
+    # ---- nets/model.py
+    B, H, W = 1, 16, 16
+    fch = [40, 32, 24, 12]        # pool5 (1/32), pool4, pool3, pool2 (1/4)
+    fm = [rng.standard_normal((B, H // 8, W // 8, fch[0])), rng.standard_normal((B, H // 4, W // 4, fch[1])),
+          rng.standard_normal((B, H // 2, W // 2, fch[2])), rng.standard_normal((B, H, W, fch[3]))]
+    fm = [v.astype(np.float32) for v in fm]
+    order = []
+    recs = {}
+    for kind, n in (("pixel", 2), ("link", 16)):     # call order of :129-141: pixel f0..f3, link f0..f3, pixel_4, link_4
+        for i in range(4):
+            r = dict(w=(rng.standard_normal((fch[i], n)) / np.sqrt(fch[i])).astype(np.float32),
+                     scale=rng.uniform(0.5, 1.5, n).astype(np.float32), shift=(0.3 * rng.standard_normal(n)).astype(np.float32))
+            recs["%s_f%d" % (kind, i)] = r
+            order.append(r)
+    for kind, n in (("pixel", 2), ("link", 16)):
+        r = dict(w=(rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32), b=(0.1 * rng.standard_normal(n)).astype(np.float32))
+        recs["%s_out" % kind] = r
+        order.append(r)
+    slim_ = _NpSlim(in_order=order)
+    ns = dict(tf=tfi, slim=slim_, np=np, feature_maps=fm, PIXEL_OUTPUT=2, LINK_OUTPUT=16, print=lambda *a, **k: None)
+    exec(cut_lines("nets/model.py", 14, 15), ns)                            # def unpool(inputs)
+    body = cut_lines("nets/model.py", 129, 141)
+    print("nets/model.py:129-141\n" + "\n".join("   | " + l[:110] for l in body.split("\n")[:2]) + "\n   | ...")
+    with slim_.arg_scope([slim_.conv2d], activation_fn=tfi.nn.relu, normalizer_fn=slim_.batch_norm, normalizer_params={}):   # :103-107
+        exec(body, ns)
+    assert len(slim_.calls) == 10
+    for i, v in enumerate(fm):
+        out["md_f%d" % i] = v
+    for k, r in recs.items():
+        for kk, vv in r.items():
+            out["md_%s_%s" % (k, kk)] = vv
+    out["md_pixel_4"], out["md_link_4"] = ns["pixel_4"].astype(np.float32), ns["link_4"].astype(np.float32)
+    save("head_logits", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     only = sys.argv[1] if len(sys.argv) > 1 else None
@@ -589,6 +712,8 @@ if __name__ == "__main__":
         golden_icdar_generate_rbox()
     elif only == "evaluation":
         golden_evaluation()
+    elif only == "head_logits":
+        golden_head_logits()
     else:
         golden_model_loss()
         golden_vgg16()
@@ -598,3 +723,4 @@ if __name__ == "__main__":
         golden_link_graph()
         golden_icdar_generate_rbox()
         golden_evaluation()
+        golden_head_logits()

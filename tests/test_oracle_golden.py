@@ -192,3 +192,27 @@ def test_icdar_generate_rbox_golden(golden_dir):
         assert np.array_equal(geo, g["geo%d" % ci])
         assert np.array_equal(tm, g["tmask%d" % ci])
         assert geo.sum() > 1000 and (geo[:, 0].sum() > 0 or geo[0].sum() > 0)   # the wrap-around borders are exercised
+
+
+def test_head_logits_golden(golden_dir):
+    """N3: oracle/head_logits.py vs the reference's own fusion lines executed (nets/pixellink.py:57-67,
+    nets/model.py:129-141; make_golden.py::golden_head_logits)."""
+    from oracle import head_logits as OH
+    g = np.load(golden_dir + "/head_logits.npz")
+    ep = {k: g["pl_" + k] for k in ("fc7", "conv5_3", "conv4_3", "conv3_3")}
+    scopes = ["stage_%d_%s_fuse" % (st, kind) for kind in ("pixel", "link") for st in (6, 5, 4, 3)] + ["text_predication", "link_predication"]
+    p = {s: (g["pl_w_" + s], g["pl_b_" + s]) for s in scopes}
+    pix, link = OH.pixellink_layers(ep, p)
+    assert pix.shape == g["pl_pixel_cls"].shape and link.shape[-1] == 16
+    np.testing.assert_allclose(pix, g["pl_pixel_cls"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(link, g["pl_link_cls"], rtol=0, atol=2e-6)
+    fm = [g["md_f%d" % i] for i in range(4)]
+    q = {kind: [(g["md_%s_f%d_w" % (kind, i)], g["md_%s_f%d_scale" % (kind, i)], g["md_%s_f%d_shift" % (kind, i)]) for i in range(4)]
+         + [(g["md_%s_out_w" % kind], None, g["md_%s_out_b" % kind])] for kind in ("pixel", "link")}
+    pix, link = OH.model_head(fm, q)
+    np.testing.assert_allclose(pix, g["md_pixel_4"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(link, g["md_link_4"], rtol=0, atol=2e-6)
+    # unpool: TF's align_corners=False arithmetic on a ramp (x2: every other output sits on a source pixel,
+    # the ones between are midpoints, the last row / column repeats)
+    r = OH.resize_bilinear_x2(np.arange(4.0).reshape(1, 1, 4, 1))
+    np.testing.assert_array_equal(r[0, 0, :, 0], [0, 0.5, 1, 1.5, 2, 2.5, 3, 3])
