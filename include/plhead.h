@@ -280,8 +280,8 @@ PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double r
  *            False) does for an exact factor 2
  *  w_out [18,18] (in, out), b_out [18] optional; y18 [B,H,W,18] (w_out null) or pix_logits [B,H,W,2] +
  *            link_logits [B,H,W,16] (w_out given)
- * fp32 in, fp32 out; products on the tensor cores with the 3xTF32 split (fp32-accurate: within 1e-5 of an fp64
- * evaluation relative to the largest logit, the contract tests/test_gpu_headfuse.py states).
+ * fp32 in, fp32 FMA accumulation, fp32 out: within 1e-5 of an fp64 evaluation relative to the largest logit (the
+ * contract tests/test_gpu_headfuse.py states).  wa / wb must be 16-byte aligned like the feature maps.
  */
 PLH_API int plh_head_fuse_level(const float* xa, int Ka, const float* wa, const float* scale_a, const float* shift_a, int relu_a,
                         const float* xb, int Kb, const float* wb, const float* scale_b, const float* shift_b, int relu_b,

@@ -4,59 +4,50 @@
 // conv5_3, conv4_3, conv3_3) and nets/model.py:14-15,129-141 (the EAST fork over pool5..pool2): per level
 //     y = up2(prev) + sum_f act_f(scale_f * (x_f W_f) + shift_f)          (1x1 convolutions, f = 1 or 2 features)
 // and at the last level   logits = y W_out + b_out,   written as the [.,2] pixel and [.,16] link tensors the loss /
-// decode kernels read.  The 2 pixel and 16 link channels go through together (18 columns, padded to 24).
+// decode kernels read.  The 2 pixel and 16 link channels go through together (18 columns).
 //
-// One launch per level.  A level is a skinny GEMM [pixels x K] x [K x 18] whose cost is reading the activations
-// once (K * 4 B per pixel against 36 K flop: 9 flop/B, far below the machine balance), so the kernel is built to
-// stream: persistent CTAs, tiles of 128 consecutive pixels, the K axis in 32-channel chunks through a 4-stage
-// cp.async ring (activations 16 B at a time, the chunk's weight rows beside them), and the arithmetic on the
-// tensor cores so that issue slots never limit the stream: mma.sync m16n8k8 TF32 with the 3xTF32 split
-// (a = a_hi + a_lo, b = b_hi + b_lo, a_hi b_hi + a_hi b_lo + a_lo b_hi accumulated in fp32), which keeps fp32
-// accuracy (dropped term ~2^-22 relative) — plain TF32 would miss the 1e-5 contract.  tcgen05 would need both
-// operands of the split staged in shared memory; with an HBM-bound level there is nothing for it to win.
-// The epilogue applies scale / shift / ReLU per feature, adds the bilinear x2 of the previous level
-// (tf.image.resize_bilinear, align_corners = False: taps (y >> 1, x >> 1) and the next row / column, weight 0.5 on
-// odd coordinates, clamped at the far edge), and the last level multiplies by the 18x18 output matrix out of
-// shared memory and stores both tensors coalesced.
+// One launch per level.  A level is a skinny GEMM [pixels x K] x [K x 18]: 18 FMA per activation read, 4.5 FMA per
+// byte — on a B200 (36 T fp32 FMA/s against 6.5 TB/s) the stream of activations and the fp32 pipe are about
+// equally loaded, so the kernel is built to keep both busy: persistent CTAs, tiles of 128 consecutive pixels, the
+// K axis in 32-channel chunks through a 3-stage cp.async ring that runs ACROSS tile boundaries (activations 16 B
+// at a time, the chunk's weight rows — contiguous in memory — beside them), and plain fp32 FMAs on a 4 pixel x 18
+// output register tile per thread (72 independent accumulators; the four warps of a CTA split the chunk's
+// channels, their partial sums meet in shared memory once per tile and feature).  Per 8 channels a thread
+// issues 8 + 72 shared-memory loads (the weight ones are warp-wide broadcasts) for 576 FMAs.
+// A first version ran the products on the tensor cores (mma.sync m16n8k8 TF32 with the 3xTF32 split, needed for
+// the 1e-5 contract): on this part the legacy MMA path saturated (`math_pipe_throttle`) at 0.34 of the HBM
+// roofline — three TF32 MMAs per fp32 product, padded from 18 to 24 columns, is MORE pipe time than the FMAs
+// (profiles/r02_headfuse.txt).  tcgen05 would need both halves of the split staged in shared memory in the
+// canonical layout; not attempted.
+// The epilogue (one thread per pixel) sums the partials, applies scale / shift / ReLU per feature, adds the
+// bilinear x2 of the previous level (tf.image.resize_bilinear, align_corners = False: taps (y >> 1, x >> 1) and
+// the next row / column, weight 0.5 on odd coordinates, clamped at the far edge), and the last level multiplies
+// by the 18x18 output matrix and stores both tensors.
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace plh {
 
-constexpr int kHfThreads = 256;                 // 8 warps x 16 pixels
-constexpr int kHfTile = 128;                    // pixels per tile
+constexpr int kHfThreads = 128;                 // 4 warps: each takes 8 of a chunk's 32 channels
+constexpr int kHfTile = 128;                    // pixels per tile: 4 per lane
 constexpr int kHfKC = 32;                       // channels per chunk
-constexpr int kHfStages = 4;
-constexpr int kHfAStride = kHfKC + 4;           // floats per pixel row in shared memory (conflict-free fragments)
-constexpr int kHfN = 18, kHfNP = 24;            // output columns, padded to three n8 tiles
-constexpr int kHfStageFloats = kHfTile * kHfAStride + kHfKC * kHfNP;
-constexpr size_t kHfSmem = (size_t)kHfStages * kHfStageFloats * 4 + (size_t)(kHfN * kHfN + kHfN + 8 * 16 * kHfNP) * 4;
+constexpr int kHfStages = 3;
+constexpr int kHfAStride = kHfKC + 4;           // floats per pixel row in shared memory (conflict-free 128-bit reads)
+constexpr int kHfN = 18;                        // output columns
+constexpr int kHfWFloats = kHfKC * kHfN;        // a chunk's weight rows as they lie in memory
+constexpr int kHfStageFloats = kHfTile * kHfAStride + kHfWFloats;
+constexpr int kHfPartial = 4 * kHfTile * (kHfN + 1);          // [warp][pixel][18 (+1: conflict-free column reads)]
+constexpr int kHfMisc = kHfN * kHfN + kHfN + 4 * kHfN;        // output matrix, its bias, scale / shift of two features
+constexpr size_t kHfSmem = (size_t)(kHfStages * kHfStageFloats + kHfPartial + kHfMisc + 2) * 4;
 
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool pred) {
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {  // bytes < 16: the rest is zero-filled
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  const int bytes = pred ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool pred) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  const int bytes = pred ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void split_tf32(float v, unsigned& hi, unsigned& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-  const float r = v - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 struct HfFeature {
   const float* x;      // [pixels, K]
@@ -80,175 +71,161 @@ struct HfArgs {
 
 __global__ void __launch_bounds__(kHfThreads, 2) head_fuse_kernel(const HfArgs a) {
   extern __shared__ __align__(16) float hf_smem[];
-  float* s_wout = hf_smem + kHfStages * kHfStageFloats;  // [18][18]
+  float* s_part = hf_smem + kHfStages * kHfStageFloats;  // [4][128][19]
+  float* s_wout = s_part + kHfPartial;                   // [18][18] (8-byte aligned: kHfPartial is even)
   float* s_bout = s_wout + kHfN * kHfN;                  // [18]
-  float* s_y = s_bout + kHfN;                            // [8 warps][16][24]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  float* s_aff = s_bout + kHfN;                          // [feature][scale | shift][18]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long total = (long long)a.B * a.H * a.W;
   const long long ntiles = (total + kHfTile - 1) / kHfTile;
-  // the pad columns of the weight rows are never written by the copies: zero them once
-  for (int i = tid; i < kHfStages * kHfKC * (kHfNP - kHfN); i += kHfThreads) {
-    const int st = i / (kHfKC * (kHfNP - kHfN)), r = i % (kHfKC * (kHfNP - kHfN));
-    hf_smem[st * kHfStageFloats + kHfTile * kHfAStride + (r / (kHfNP - kHfN)) * kHfNP + kHfN + r % (kHfNP - kHfN)] = 0.f;
-  }
-  if (a.w_out) {
-    for (int i = tid; i < kHfN * kHfN; i += kHfThreads) s_wout[i] = a.w_out[i];
-    if (tid < kHfN) s_bout[tid] = a.b_out ? a.b_out[tid] : 0.f;
+  for (int i = tid; i < kHfN * kHfN; i += kHfThreads) s_wout[i] = a.w_out ? a.w_out[i] : 0.f;
+  if (tid < kHfN) s_bout[tid] = a.b_out ? a.b_out[tid] : 0.f;
+  if (tid < 4 * kHfN) {
+    const int fi = tid / (2 * kHfN), which = (tid / kHfN) & 1, c = tid % kHfN;
+    const float* src = which ? a.f[fi].shift : a.f[fi].scale;
+    s_aff[tid] = (fi < a.nf && src) ? src[c] : (which ? 0.f : 1.f);
   }
   __syncthreads();
 
+  // The chunk stream: (tile, feature, 32-channel chunk) in the order they are consumed, issued kHfStages - 1
+  // chunks ahead ACROSS tile boundaries, so the epilogue of a tile runs under the loads of the next one.
+  long long i_tile = blockIdx.x;
+  int i_f = 0, i_ch = 0, i_slot = 0;
+  auto issue = [&]() {
+    if (i_tile < ntiles) {
+      const HfFeature& F = a.f[i_f];
+      float* sA = hf_smem + i_slot * kHfStageFloats;
+      float* sW = sA + kHfTile * kHfAStride;
+      const int k0 = i_ch * kHfKC;
+      const float* src = F.x + (i_tile * kHfTile) * F.K + k0;
+      const int rows = (int)min((long long)kHfTile, total - i_tile * kHfTile);
+#pragma unroll
+      for (int i = 0; i < (kHfTile * kHfKC / 4) / kHfThreads; ++i) {   // activations: 8 copies of 16 B per thread
+        const int idx = tid + i * kHfThreads, p = idx >> 3, q = idx & 7;
+        const bool ok = p < rows && k0 + q * 4 < F.K;
+        cp_async16(sA + p * kHfAStride + q * 4, ok ? src + (size_t)p * F.K + q * 4 : F.x, ok ? 16 : 0);
+      }
+      for (int i = tid; i < kHfWFloats / 4; i += kHfThreads) {         // weights: the chunk's rows are contiguous (2304 B)
+        const int nb = max(min(min(kHfKC, F.K - k0) * kHfN * 4 - i * 16, 16), 0);
+        cp_async16(sW + i * 4, nb ? F.w + (size_t)k0 * kHfN + i * 4 : F.w, nb);
+      }
+      const int nch = (F.K + kHfKC - 1) / kHfKC;
+      if (++i_ch == nch) {
+        i_ch = 0;
+        if (++i_f == a.nf) i_f = 0, i_tile += gridDim.x;
+      }
+    }
+    cp_async_commit();
+    i_slot = i_slot + 1 == kHfStages ? 0 : i_slot + 1;
+  };
+  for (int s = 0; s < kHfStages - 1; ++s) issue();
+  int c_slot = 0;
+
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long px0 = tile * kHfTile;
-    float y[3][4];
+    const long long px = tile * kHfTile + tid;   // the pixel this thread finishes in the epilogue
+    float y[kHfN];
 #pragma unroll
-    for (int n = 0; n < 3; ++n)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) y[n][i] = 0.f;
+    for (int o = 0; o < kHfN; ++o) y[o] = 0.f;
 
     for (int fi = 0; fi < a.nf; ++fi) {
-      const HfFeature F = a.f[fi];
-      const int nchunks = (F.K + kHfKC - 1) / kHfKC;
-      auto issue = [&](int c) {
-        if (c < nchunks) {
-          float* sA = hf_smem + (c % kHfStages) * kHfStageFloats;
-          float* sW = sA + kHfTile * kHfAStride;
-          const int k0 = c * kHfKC;
+      const int nchunks = (a.f[fi].K + kHfKC - 1) / kHfKC;
+      float acc[4][kHfN];   // pixels lane, lane + 32, lane + 64, lane + 96; this warp's 8 channels of every chunk
 #pragma unroll
-          for (int i = 0; i < (kHfTile * kHfKC / 4) / kHfThreads; ++i) {   // 4 copies of 16 B per thread
-            const int idx = tid + i * kHfThreads, p = idx >> 3, q = idx & 7;
-            const long long px = px0 + p;
-            const bool ok = px < total && k0 + q * 4 < F.K;
-            cp_async16(sA + p * kHfAStride + q * 4, F.x + (ok ? px * F.K + k0 + q * 4 : 0), ok);
-          }
-          for (int idx = tid; idx < kHfKC * kHfN; idx += kHfThreads) {
-            const int r = idx / kHfN, cidx = idx - r * kHfN;
-            const bool ok = k0 + r < F.K;
-            cp_async4(sW + r * kHfNP + cidx, F.w + (ok ? (size_t)(k0 + r) * kHfN + cidx : 0), ok);
-          }
-        }
-        cp_async_commit();
-      };
-      float c[3][4];
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int n = 0; n < 3; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) c[n][i] = 0.f;
-      __syncthreads();  // the ring is free: the previous feature / tile has been consumed
-      for (int s = 0; s < kHfStages - 1; ++s) issue(s);
+        for (int o = 0; o < kHfN; ++o) acc[j][o] = 0.f;
       for (int ch = 0; ch < nchunks; ++ch) {
         cp_async_wait<kHfStages - 2>();
-        __syncthreads();             // chunk ch has landed for every thread; chunk ch-1's buffer is free
-        issue(ch + kHfStages - 1);
-        const float* sA = hf_smem + (ch % kHfStages) * kHfStageFloats + warp * 16 * kHfAStride;
-        const float* sW = hf_smem + (ch % kHfStages) * kHfStageFloats + kHfTile * kHfAStride;
+        __syncthreads();             // this chunk has landed for every thread; the slot consumed last is free
+        issue();
+        const float* sA = hf_smem + c_slot * kHfStageFloats + 8 * warp;
+        const float* sW = hf_smem + c_slot * kHfStageFloats + kHfTile * kHfAStride + 8 * warp * kHfN;
+        c_slot = c_slot + 1 == kHfStages ? 0 : c_slot + 1;
 #pragma unroll
-        for (int ks = 0; ks < kHfKC / 8; ++ks) {
-          unsigned ah[4], al[4];
-          split_tf32(sA[g * kHfAStride + ks * 8 + t], ah[0], al[0]);
-          split_tf32(sA[(g + 8) * kHfAStride + ks * 8 + t], ah[1], al[1]);
-          split_tf32(sA[g * kHfAStride + ks * 8 + t + 4], ah[2], al[2]);
-          split_tf32(sA[(g + 8) * kHfAStride + ks * 8 + t + 4], ah[3], al[3]);
+        for (int half = 0; half < 2; ++half) {
+          float4 av[4];
 #pragma unroll
-          for (int n = 0; n < 3; ++n) {
-            unsigned bh0, bl0, bh1, bl1;
-            split_tf32(sW[(ks * 8 + t) * kHfNP + n * 8 + g], bh0, bl0);
-            split_tf32(sW[(ks * 8 + t + 4) * kHfNP + n * 8 + g], bh1, bl1);
-            mma_tf32(c[n], al, bh0, bh1);
-            mma_tf32(c[n], ah, bl0, bl1);
-            mma_tf32(c[n], ah, bh0, bh1);
-          }
-        }
-      }
-      cp_async_wait<0>();
-      // scale / shift / ReLU of this feature; c[n][0,1]: row g, columns n*8 + 2t, +1; c[n][2,3]: row g + 8
+          for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const float4*>(sA + (lane + 32 * j) * kHfAStride + 4 * half);
 #pragma unroll
-      for (int n = 0; n < 3; ++n)
+          for (int kk = 0; kk < 4; ++kk) {
+            float w[kHfN];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int col = n * 8 + 2 * t + (i & 1);
-          float v = c[n][i];
-          if (col < kHfN) {
-            if (F.scale) v = __fmul_rn(v, F.scale[col]);
-            if (F.shift) v = __fadd_rn(v, F.shift[col]);
-            if (F.relu) v = fmaxf(v, 0.f);
-          }
-          y[n][i] += v;
-        }
-    }
-
-    // bilinear x2 of the previous level (TF: top + (bottom - top) * fy on rows interpolated the same way in x)
-    if (a.prev) {
+            for (int o = 0; o < kHfN; o += 2) {
+              const float2 t2 = *reinterpret_cast<const float2*>(sW + (4 * half + kk) * kHfN + o);   // warp-wide broadcast
+              w[o] = t2.x, w[o + 1] = t2.y;
+            }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const long long px = px0 + warp * 16 + g + 8 * h;
-        if (px < total) {
-          const int hw = a.H * a.W, b = (int)(px / hw), r = (int)(px - (long long)b * hw), yy = r / a.W, xx = r - yy * a.W;
-          const int Hp = a.H >> 1, Wp = a.W >> 1;
-          const int ylo = yy >> 1, yhi = min(ylo + 1, Hp - 1), xlo = xx >> 1, xhi = min(xlo + 1, Wp - 1);
-          const float fy = (yy & 1) ? 0.5f : 0.f, fx = (xx & 1) ? 0.5f : 0.f;
-          const float* P = a.prev + (size_t)b * Hp * Wp * kHfN;
+            for (int j = 0; j < 4; ++j) {
+              const float x = kk == 0 ? av[j].x : (kk == 1 ? av[j].y : (kk == 2 ? av[j].z : av[j].w));
 #pragma unroll
-          for (int n = 0; n < 3; ++n) {
-            const int col = n * 8 + 2 * t;
-            if (col < kHfN) {
-              const float2 tl = *reinterpret_cast<const float2*>(P + ((size_t)ylo * Wp + xlo) * kHfN + col);
-              const float2 tr = *reinterpret_cast<const float2*>(P + ((size_t)ylo * Wp + xhi) * kHfN + col);
-              const float2 bl = *reinterpret_cast<const float2*>(P + ((size_t)yhi * Wp + xlo) * kHfN + col);
-              const float2 br = *reinterpret_cast<const float2*>(P + ((size_t)yhi * Wp + xhi) * kHfN + col);
-              const float top0 = __fadd_rn(tl.x, __fmul_rn(__fsub_rn(tr.x, tl.x), fx)), top1 = __fadd_rn(tl.y, __fmul_rn(__fsub_rn(tr.y, tl.y), fx));
-              const float bot0 = __fadd_rn(bl.x, __fmul_rn(__fsub_rn(br.x, bl.x), fx)), bot1 = __fadd_rn(bl.y, __fmul_rn(__fsub_rn(br.y, bl.y), fx));
-              y[n][2 * h] += __fadd_rn(top0, __fmul_rn(__fsub_rn(bot0, top0), fy));
-              y[n][2 * h + 1] += __fadd_rn(top1, __fmul_rn(__fsub_rn(bot1, top1), fy));
+              for (int o = 0; o < kHfN; ++o) acc[j][o] = fmaf(x, w[o], acc[j][o]);
             }
           }
         }
       }
+      // the four warps' partial sums meet in shared memory; thread p finishes pixel p
+      __syncthreads();   // (the partial buffer of the previous feature / tile has been read)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 0; o < kHfN; ++o) s_part[(warp * kHfTile + lane + 32 * j) * (kHfN + 1) + o] = acc[j][o];
+      __syncthreads();
+      const float* sc = s_aff + fi * 2 * kHfN;
+      const bool relu = a.f[fi].relu != 0;
+#pragma unroll
+      for (int o = 0; o < kHfN; ++o) {
+        float v = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) v += s_part[(w4 * kHfTile + tid) * (kHfN + 1) + o];
+        v = __fadd_rn(__fmul_rn(v, sc[o]), sc[kHfN + o]);
+        if (relu) v = fmaxf(v, 0.f);
+        y[o] += v;
+      }
     }
 
-    // this warp's 16 x 24 result through shared memory: the stores (and the output matrix) want whole pixel rows
-    float* sy = s_y + warp * 16 * kHfNP;
+    if (px < total) {
+      // bilinear x2 of the previous level (TF: top + (bottom - top) * fy on rows interpolated the same way in x)
+      if (a.prev) {
+        const int hw = a.H * a.W, Hp = a.H >> 1, Wp = a.W >> 1;
+        const int b = (int)(px / hw), r = (int)(px - (long long)b * hw), yy = r / a.W, xx = r - yy * a.W;
+        const int ylo = yy >> 1, yhi = min(ylo + 1, Hp - 1), xlo = xx >> 1, xhi = min(xlo + 1, Wp - 1);
+        const float fy = (yy & 1) ? 0.5f : 0.f, fx = (xx & 1) ? 0.5f : 0.f;
+        const float* P = a.prev + (size_t)b * Hp * Wp * kHfN;
+        const float2* tl = reinterpret_cast<const float2*>(P + ((size_t)ylo * Wp + xlo) * kHfN);
+        const float2* tr = reinterpret_cast<const float2*>(P + ((size_t)ylo * Wp + xhi) * kHfN);
+        const float2* bl = reinterpret_cast<const float2*>(P + ((size_t)yhi * Wp + xlo) * kHfN);
+        const float2* br = reinterpret_cast<const float2*>(P + ((size_t)yhi * Wp + xhi) * kHfN);
 #pragma unroll
-    for (int n = 0; n < 3; ++n) {
-      *reinterpret_cast<float2*>(sy + g * kHfNP + n * 8 + 2 * t) = make_float2(y[n][0], y[n][1]);
-      *reinterpret_cast<float2*>(sy + (g + 8) * kHfNP + n * 8 + 2 * t) = make_float2(y[n][2], y[n][3]);
-    }
-    __syncwarp();
-    const long long wpx0 = px0 + warp * 16;
-    if (a.w_out) {
-      // lane = (pixel, half): nine of the 18 outputs each
-      const int p = lane >> 1, o0 = (lane & 1) * 9;
-      float z[9];
-#pragma unroll
-      for (int o = 0; o < 9; ++o) z[o] = s_bout[o0 + o];
-      for (int i = 0; i < kHfN; ++i) {
-        const float v = sy[p * kHfNP + i];
-#pragma unroll
-        for (int o = 0; o < 9; ++o) z[o] = fmaf(v, s_wout[i * kHfN + o0 + o], z[o]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int o = 0; o < 9; ++o) sy[p * kHfNP + o0 + o] = z[o];
-      __syncwarp();
-      // pixel logits: 16 pixels x 2 floats = 32 consecutive floats; link logits: 16 x 16 = 64 float4
-      if (wpx0 + (lane >> 1) < total) a.pix[wpx0 * 2 + lane] = sy[(lane >> 1) * kHfNP + (lane & 1)];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int q = lane + 32 * h, pp = q >> 2, c4 = (q & 3) * 4;
-        if (wpx0 + pp < total) {
-          const float* s = sy + pp * kHfNP + 2 + c4;
-          *reinterpret_cast<float4*>(a.link + (wpx0 + pp) * 16 + c4) = make_float4(s[0], s[1], s[2], s[3]);
+        for (int o = 0; o < kHfN / 2; ++o) {
+          const float2 q0 = tl[o], q1 = tr[o], q2 = bl[o], q3 = br[o];
+          const float top0 = __fadd_rn(q0.x, __fmul_rn(__fsub_rn(q1.x, q0.x), fx)), top1 = __fadd_rn(q0.y, __fmul_rn(__fsub_rn(q1.y, q0.y), fx));
+          const float bot0 = __fadd_rn(q2.x, __fmul_rn(__fsub_rn(q3.x, q2.x), fx)), bot1 = __fadd_rn(q2.y, __fmul_rn(__fsub_rn(q3.y, q2.y), fx));
+          y[2 * o] += __fadd_rn(top0, __fmul_rn(__fsub_rn(bot0, top0), fy));
+          y[2 * o + 1] += __fadd_rn(top1, __fmul_rn(__fsub_rn(bot1, top1), fy));
         }
       }
-    } else {
-      // [pixels, 18]: 16 pixels x 18 floats = 288 consecutive floats = 9 per lane
+      if (a.w_out) {
+        float z[kHfN];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const int q = lane + 32 * i, pp = q / kHfN, cc = q - pp * kHfN;
-        if (wpx0 + pp < total) a.y18[wpx0 * kHfN + q] = sy[pp * kHfNP + cc];
+        for (int o = 0; o < kHfN; ++o) z[o] = s_bout[o];
+#pragma unroll
+        for (int i = 0; i < kHfN; ++i)
+#pragma unroll
+          for (int o = 0; o < kHfN; o += 2) {
+            const float2 t2 = *reinterpret_cast<const float2*>(s_wout + i * kHfN + o);
+            z[o] = fmaf(y[i], t2.x, z[o]), z[o + 1] = fmaf(y[i], t2.y, z[o + 1]);
+          }
+        *reinterpret_cast<float2*>(a.pix + px * 2) = make_float2(z[0], z[1]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(a.link + px * 16 + 4 * q) = make_float4(z[2 + 4 * q], z[3 + 4 * q], z[4 + 4 * q], z[5 + 4 * q]);
+      } else {
+#pragma unroll
+        for (int o = 0; o < kHfN; o += 2) *reinterpret_cast<float2*>(a.y18 + px * kHfN + o) = make_float2(y[o], y[o + 1]);
       }
     }
-    __syncwarp();
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace plh
@@ -266,7 +243,8 @@ extern "C" int plh_head_fuse_level(const float* xa, int Ka, const float* wa, con
   if (B <= 0 || H <= 0 || W <= 0 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
   if (Ka <= 0 || (Ka & 3) || (xb && (Kb <= 0 || (Kb & 3)))) return PLH_E_SHAPE;   // 16-byte rows
   if (prev && ((H & 1) || (W & 1))) return PLH_E_SHAPE;                            // the level is exactly twice the previous one
-  if (!aligned16(xa) || (xb && !aligned16(xb)) || (link_logits && !aligned16(link_logits))) return PLH_E_ALIGN;
+  if (!aligned16(xa) || !aligned16(wa) || (xb && (!aligned16(xb) || !aligned16(wb))) || (link_logits && !aligned16(link_logits)))
+    return PLH_E_ALIGN;
   HfArgs a;
   a.f[0] = HfFeature{xa, wa, scale_a, shift_a, Ka, relu_a};
   a.f[1] = HfFeature{xb, wb, scale_b, shift_b, xb ? Kb : 0, relu_b};
@@ -277,7 +255,7 @@ extern "C" int plh_head_fuse_level(const float* xa, int Ka, const float* wa, con
   int rc;
   if ((rc = ensure_dynamic_smem(optin, head_fuse_kernel, kHfSmem))) return rc;
   const long long ntiles = ((long long)B * H * W + kHfTile - 1) / kHfTile;
-  const int grid = (int)std::min<long long>(ntiles, 2ll * kNumSMs);
+  const int grid = (int)std::min<long long>(ntiles, 2ll * kNumSMs);   // two resident CTAs per SM
   head_fuse_kernel<<<grid, kHfThreads, kHfSmem, (cudaStream_t)stream>>>(a);
   return launch_status();
 }

@@ -1,8 +1,8 @@
 """N3 on the GPU: the logit producer (csrc/headfuse.cu through the C ABI and the nets mirrors) against the
 reference-executed golden and the float64 oracle.
 
-Tolerance (the contract of include/plhead.h): |gpu - f64| <= 1e-5 * max|f64| per tensor — fp32 accumulation of K up
-to 1024 products done with the 3xTF32 split; plain TF32 would be ~1e-3."""
+Tolerance (the contract of include/plhead.h): |gpu - f64| <= 1e-5 * max|f64| per tensor — fp32 FMA accumulation of K up
+to 2048 products."""
 import numpy as np
 import pytest
 
