@@ -161,9 +161,9 @@ using namespace plh;
 
 extern "C" int plh_quad_jaccard(const int32_t* dets, const int32_t* gts, const int32_t* det_off, const int32_t* gt_off,
                                 const int64_t* pair_off, int B, long long total_pairs, float* jaccard, void* stream) {
-  if (!dets || !gts || !det_off || !gt_off || !pair_off || !jaccard) return PLH_E_NULL;
   if (B <= 0 || total_pairs < 0) return PLH_E_SHAPE;
-  if (total_pairs == 0) return PLH_OK;
+  if (total_pairs == 0) return PLH_OK;   // no detections or no ground truth anywhere: nothing to compute
+  if (!dets || !gts || !det_off || !gt_off || !pair_off || !jaccard) return PLH_E_NULL;
   const int grid = (int)std::min<long long>((total_pairs + 7) / 8, kNumSMs * 8);
   quad_jaccard_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dets, gts, det_off, gt_off, (const long long*)pair_off, B,
                                                                total_pairs, jaccard);
@@ -173,7 +173,7 @@ extern "C" int plh_quad_jaccard(const int32_t* dets, const int32_t* gts, const i
 extern "C" int plh_bboxes_matching(const float* jaccard, const int32_t* det_off, const int32_t* gt_off,
                                    const int64_t* pair_off, int B, const uint8_t* gignored, float matching_threshold,
                                    uint8_t* gmatch, uint8_t* tp, uint8_t* fp, int32_t* n_gbboxes, void* stream) {
-  if (!jaccard || !det_off || !gt_off || !pair_off || !gignored || !gmatch || !tp || !fp || !n_gbboxes) return PLH_E_NULL;
+  if (!det_off || !gt_off || !pair_off || !n_gbboxes) return PLH_E_NULL;   // the per-box arrays may be empty
   if (B <= 0) return PLH_E_SHAPE;
   bboxes_matching_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(jaccard, det_off, gt_off, (const long long*)pair_off, gignored,
                                                              matching_threshold, gmatch, tp, fp, n_gbboxes);

@@ -462,8 +462,8 @@ def bboxes_matching_raw(dets: torch.Tensor, gts: torch.Tensor, det_counts, gt_co
     g_off = torch.tensor(gt_off, dtype=torch.int32).to(dev, non_blocking=True)
     p_off = torch.tensor(pair_off, dtype=torch.int64).to(dev, non_blocking=True)
     out = {"jaccard": torch.empty((max(pair_off[-1], 1),), dtype=torch.float32, device=dev)[:pair_off[-1]],
-           "tp": torch.empty((det_off[-1],), dtype=torch.uint8, device=dev),
-           "fp": torch.empty((det_off[-1],), dtype=torch.uint8, device=dev),
+           "tp": torch.empty((max(det_off[-1], 1),), dtype=torch.uint8, device=dev)[:det_off[-1]],
+           "fp": torch.empty((max(det_off[-1], 1),), dtype=torch.uint8, device=dev)[:det_off[-1]],
            "n_gbboxes": torch.empty((B,), dtype=torch.int32, device=dev), "pair_off": pair_off,
            "det_off": det_off, "gt_off": gt_off}
     gmatch = torch.empty((max(gt_off[-1], 1),), dtype=torch.uint8, device=dev)

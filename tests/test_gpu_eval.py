@@ -111,6 +111,17 @@ def test_negative_coordinates_are_clipped_like_cv2():
     assert n == 240
 
 
+def test_no_detections():
+    """An image without detections: empty TP / FP arrays, the ground-truth count still reported."""
+    from tensorflow_ocr_b200.tool import bboxes as tb
+    gxs = np.array([[1, 5, 5, 1], [10, 20, 20, 10]]); gys = np.array([[1, 1, 5, 5], [10, 10, 14, 14]])
+    n, tp, fp = tb.bboxes_matching(np.zeros((0, 8), np.int32), gxs, gys, np.array([0, 1]))
+    assert int(n) == 1 and tp.shape == (0,) and fp.shape == (0,)
+    n, tps, fps = tb.bboxes_matching_batch([np.zeros((0, 8), np.int32), np.array([[1, 1, 5, 1, 5, 5, 1, 5]])], [gxs, gxs], [gys, gys],
+                                           [np.array([0, 0]), np.array([0, 0])])
+    assert list(n) == [2, 2] and tps[0].shape == (0,) and list(tps[1]) == [True] and list(fps[1]) == [False]
+
+
 def test_argument_errors():
     from tensorflow_ocr_b200.tool import bboxes as tb
     gxs = np.array([[1, 5, 5, 1]]); gys = np.array([[1, 1, 5, 5]])
