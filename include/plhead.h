@@ -280,13 +280,18 @@ PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double r
  *            False) does for an exact factor 2
  *  w_out [18,18] (in, out), b_out [18] optional; y18 [B,H,W,18] (w_out null) or pix_logits [B,H,W,2] +
  *            link_logits [B,H,W,16] (w_out given)
+ *  flags [B,H,W] uint16 optional (last level only, with flag_params = the decode's thresholds): the word
+ *            plh_decode_flags would compute from the logits just produced (bit-identical: same logit-space
+ *            thresholds on the same fp32 values), so that plh_decode_from_flags can start without reading the 72 B
+ *            per pixel of logits again
  * fp32 in, fp32 FMA accumulation, fp32 out: within 1e-5 of an fp64 evaluation relative to the largest logit (the
  * contract tests/test_gpu_headfuse.py states).  wa / wb must be 16-byte aligned like the feature maps.
  */
 PLH_API int plh_head_fuse_level(const float* xa, int Ka, const float* wa, const float* scale_a, const float* shift_a, int relu_a,
                         const float* xb, int Kb, const float* wb, const float* scale_b, const float* shift_b, int relu_b,
                         const float* prev, const float* w_out, const float* b_out, int B, int H, int W, float* y18,
-                        float* pix_logits, float* link_logits, void* stream);
+                        float* pix_logits, float* link_logits, const plh_decode_params* flag_params, uint16_t* flags,
+                        void* stream);
 
 /*
  * Detection evaluation.

@@ -54,7 +54,7 @@ SIGNATURES = {
     "plh_link_labels_icdar": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "plh_contour_workspace_bytes": (_sz, [_i, _i, _i]),
     "plh_contour_boxes": (_i, [_vp, _i, _i, _i, C.c_double, C.c_double, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "plh_head_fuse_level": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "plh_head_fuse_level": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plh_fill_quads": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plh_quad_jaccard": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
     "plh_bboxes_matching": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.c_float, _vp, _vp, _vp, _vp, _vp]),

@@ -29,6 +29,8 @@
 
 namespace plh {
 
+float prob_to_logit_threshold(float t);  // loss.cu
+
 constexpr int kHfThreads = 128;                 // 4 warps: each takes 8 of a chunk's 32 channels
 constexpr int kHfTile = 128;                    // pixels per tile: 4 per lane
 constexpr int kHfKC = 32;                       // channels per chunk
@@ -67,6 +69,8 @@ struct HfArgs {
   float* y18;          // [pixels, 18]  (levels before the last)
   float* pix;          // [pixels, 2]   (last level)
   float* link;         // [pixels, 16]
+  uint16_t* flags;     // [pixels] or null: the decode's threshold word of the pixel just produced
+  float tp_logit, tl_logit;
 };
 
 __global__ void __launch_bounds__(kHfThreads, 2) head_fuse_kernel(const HfArgs a) {
@@ -216,6 +220,12 @@ __global__ void __launch_bounds__(kHfThreads, 2) head_fuse_kernel(const HfArgs a
             z[o] = fmaf(y[i], t2.x, z[o]), z[o + 1] = fmaf(y[i], t2.y, z[o + 1]);
           }
         *reinterpret_cast<float2*>(a.pix + px * 2) = make_float2(z[0], z[1]);
+        if (a.flags) {   // decode_flags_kernel's word (decode.cu): bit d = link d passes, bit 8 = the pixel passes, in logit space
+          unsigned f = (z[1] - z[0]) > a.tp_logit ? 256u : 0u;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) f |= ((z[3 + 2 * d] - z[2 + 2 * d]) > a.tl_logit ? 1u : 0u) << d;
+          a.flags[px] = (uint16_t)f;
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<float4*>(a.link + px * 16 + 4 * q) = make_float4(z[2 + 4 * q], z[3 + 4 * q], z[4 + 4 * q], z[5 + 4 * q]);
@@ -236,7 +246,8 @@ extern "C" int plh_head_fuse_level(const float* xa, int Ka, const float* wa, con
                                    int relu_a, const float* xb, int Kb, const float* wb, const float* scale_b,
                                    const float* shift_b, int relu_b, const float* prev, const float* w_out,
                                    const float* b_out, int B, int H, int W, float* y18, float* pix_logits,
-                                   float* link_logits, void* stream) {
+                                   float* link_logits, const plh_decode_params* flag_params, uint16_t* flags,
+                                   void* stream) {
   if (!xa || !wa) return PLH_E_NULL;
   if (xb && !wb) return PLH_E_NULL;
   if (w_out ? (!pix_logits || !link_logits) : !y18) return PLH_E_NULL;
@@ -251,6 +262,13 @@ extern "C" int plh_head_fuse_level(const float* xa, int Ka, const float* wa, con
   a.nf = xb ? 2 : 1;
   a.prev = prev, a.w_out = w_out, a.b_out = b_out, a.B = B, a.H = H, a.W = W;
   a.y18 = y18, a.pix = pix_logits, a.link = link_logits;
+  a.flags = nullptr, a.tp_logit = a.tl_logit = 0.f;
+  if (flags) {
+    if (!w_out || !flag_params) return PLH_E_NULL;   // the threshold word belongs to the logits of the last level
+    a.flags = flags;
+    a.tp_logit = prob_to_logit_threshold(flag_params->pixel_thresh);
+    a.tl_logit = prob_to_logit_threshold(flag_params->link_thresh);
+  }
   static SmemOptIn optin;
   int rc;
   if ((rc = ensure_dynamic_smem(optin, head_fuse_kernel, kHfSmem))) return rc;

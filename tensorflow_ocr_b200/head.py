@@ -354,12 +354,13 @@ def contour_boxes_raw(mask: torch.Tensor, ratio_w: float = 1.0, ratio_h: float =
 
 
 def head_fuse_level_raw(feats, prev: Optional[torch.Tensor] = None, w_out: Optional[torch.Tensor] = None,
-                        b_out: Optional[torch.Tensor] = None):
+                        b_out: Optional[torch.Tensor] = None, flags_cfg: Optional["DecodeConfig"] = None):
     """plh_head_fuse_level: one level of the logit producer (nets/pixellink.py:56-67, nets/model.py:129-141).
 
     feats: one or two (x [B,H,W,K], w [K,18], scale [18] | None, shift [18] | None, relu) tuples (CUDA fp32);
     prev [B,H/2,W/2,18] | None; w_out [18,18] (in, out) + b_out [18] for the last level.
-    -> y18 [B,H,W,18], or (pixel logits [B,H,W,2], link logits [B,H,W,16]) when w_out is given."""
+    -> y18 [B,H,W,18], or (pixel logits [B,H,W,2], link logits [B,H,W,16]) when w_out is given; with flags_cfg (a
+    DecodeConfig, last level only) also the decode's threshold words int16 [B,H,W] as third element."""
     lib = _lib.load()
     if not 1 <= len(feats) <= 2:
         raise ValueError("a level fuses one or two feature maps")
@@ -390,10 +391,19 @@ def head_fuse_level_raw(feats, prev: Optional[torch.Tensor] = None, w_out: Optio
     else:
         y18 = torch.empty((B, H, W, 18), dtype=torch.float32, device=dev)
         pix = link = None
+    flags, dp = None, None
+    if flags_cfg is not None:
+        if w_out is None:
+            raise ValueError("threshold words belong to the last level (w_out given)")
+        flags = torch.empty((B, H, W), dtype=torch.int16, device=dev)
+        dp = flags_cfg.c_struct()
     with torch.cuda.device(dev):
-        rc = lib.plh_head_fuse_level(*flat, _p(prev), _p(w_out), _p(b_out), B, H, W, _p(y18), _p(pix), _p(link), _stream(dev))
+        rc = lib.plh_head_fuse_level(*flat, _p(prev), _p(w_out), _p(b_out), B, H, W, _p(y18), _p(pix), _p(link),
+                                     C.byref(dp) if dp is not None else None, _p(flags), _stream(dev))
     _lib.check(rc, "plh_head_fuse_level")
-    return y18 if w_out is None else (pix, link)
+    if w_out is None:
+        return y18
+    return (pix, link) if flags is None else (pix, link, flags)
 
 
 def fill_quads_raw(quads: torch.Tensor, counts, H: int, W: int, Ho: int, Wo: int, mode: int = 0, stride: int = 1,

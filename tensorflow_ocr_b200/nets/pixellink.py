@@ -66,7 +66,7 @@ def _cat18(pix, link, device):
     return torch.cat([a, b], dim=-1).contiguous()
 
 
-def pixellink_layers(end_points, params):
+def pixellink_layers(end_points, params, decode_config=None):
     """nets/pixellink.py:56-67 ``_add_pixellink_layers`` (with ``unpool`` :37-38) on the GPU:
 
         s1 = conv1x1(fc7) + conv1x1(conv5_3);  s2 = unpool(s1) + conv1x1(conv4_3);
@@ -75,7 +75,10 @@ def pixellink_layers(end_points, params):
     ``end_points``: the NHWC feature maps ``fc7``, ``conv5_3`` (1/16), ``conv4_3`` (1/8), ``conv3_3`` (1/4);
     ``params[scope] = (weights [K,n], biases [n])`` for the reference's ten variable scopes
     ``stage_{6,5,4,3}_{pixel,link}_fuse``, ``text_predication``, ``link_predication``.
-    Returns ``(pixel_cls [B,H,W,2], link_cls [B,H,W,16])`` (numpy in -> numpy out)."""
+    Returns ``(pixel_cls [B,H,W,2], link_cls [B,H,W,16])`` (numpy in -> numpy out).  With ``decode_config`` (a
+    ``head.DecodeConfig``) a third element: the decode's threshold words of these logits (what
+    ``head.decode_flags_raw`` would compute), for ``head.decode_from_flags_raw`` — the decode then never reads the
+    logits."""
     x = {}
     np_in = False
     dev = None
@@ -94,7 +97,5 @@ def pixellink_layers(end_points, params):
     b_out = _cat18(params["text_predication"][1], params["link_predication"][1], dev)
     s1 = head.head_fuse_level_raw([feats["fc7"], feats["conv5_3"]])
     s2 = head.head_fuse_level_raw([feats["conv4_3"]], prev=s1)
-    pixel_cls, link_cls = head.head_fuse_level_raw([feats["conv3_3"]], prev=s2, w_out=w_out, b_out=b_out)
-    if np_in:
-        return pixel_cls.cpu().numpy(), link_cls.cpu().numpy()
-    return pixel_cls, link_cls
+    res = head.head_fuse_level_raw([feats["conv3_3"]], prev=s2, w_out=w_out, b_out=b_out, flags_cfg=decode_config)
+    return tuple(t.cpu().numpy() for t in res) if np_in else res

@@ -109,6 +109,29 @@ def test_produced_logits_feed_the_loss(cuda_dev):
     assert np.isfinite(out["stats"].cpu().numpy()).all()
 
 
+def test_threshold_words_from_the_producer(cuda_dev):
+    """The last level can emit the decode's threshold words: identical to plh_decode_flags on the logits it wrote,
+    and the decode started from them gives the boxes of the decode started from the logits."""
+    import torch
+    from tensorflow_ocr_b200 import head
+    from tensorflow_ocr_b200.nets import pixellink
+    rng = np.random.default_rng(12)
+    B, H, W = 2, 64, 64
+    chans = {"fc7": 64, "conv5_3": 32, "conv4_3": 32, "conv3_3": 32}
+    ep = {"fc7": rng.standard_normal((B, H // 4, W // 4, 64)), "conv5_3": rng.standard_normal((B, H // 4, W // 4, 32)),
+          "conv4_3": rng.standard_normal((B, H // 2, W // 2, 32)), "conv3_3": rng.standard_normal((B, H, W, 32))}
+    ep = {k: torch.as_tensor(v.astype(np.float32)).to(cuda_dev) for k, v in ep.items()}
+    cfg = head.DecodeConfig(pixel_thresh=0.6, link_thresh=0.55, min_size=3, max_boxes=256)
+    pix, link, flags = pixellink.pixellink_layers(ep, _pl_params(rng=rng, chans=chans), decode_config=cfg)
+    ref = head.decode_flags_raw(pix, link, cfg)["flags"]
+    assert torch.equal(flags, ref) and int((flags != 0).sum()) > 0
+    a = head.decode_from_flags_raw(flags, cfg, {}, True)
+    b = head.decode_raw(pix, link, cfg, {}, True)
+    assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["n_boxes"], b["n_boxes"])
+    for i, n in enumerate(a["n_boxes"].tolist()):      # rows past n_boxes are not written
+        assert n > 0 and torch.equal(a["boxes"][i, :n], b["boxes"][i, :n]), i
+
+
 def test_argument_errors(cuda_dev):
     import torch
     from tensorflow_ocr_b200 import head
