@@ -7,23 +7,22 @@
 // decode kernels read.  The 2 pixel and 16 link channels go through together (18 columns).
 //
 // One launch per level.  A level is a skinny GEMM [pixels x K] x [K x 18]: 18 FMA per activation read, 4.5 FMA per
-// byte — on a B200 (36 T fp32 FMA/s against 6.5 TB/s) the stream of activations and the fp32 pipe are about
-// equally loaded, so the kernel is built to keep both busy: persistent CTAs, tiles of 128 consecutive pixels, the
-// K axis in 32-channel chunks through a 3-stage cp.async ring that runs ACROSS tile boundaries (activations 16 B
-// at a time, the chunk's weight rows — contiguous in memory — beside them), and plain fp32 FMAs on a 4 pixel x 18
-// output register tile per thread (72 independent accumulators; the four warps of a CTA split the chunk's
-// channels, their partial sums meet in shared memory once per tile and feature).  Per 8 channels a thread
-// issues 8 + 72 shared-memory loads (the weight ones are warp-wide broadcasts) for 576 FMAs.
-// A first version ran the products on the tensor cores (mma.sync m16n8k8 TF32 with the 3xTF32 split, needed for
-// the 1e-5 contract): on this part the legacy MMA path saturated (`math_pipe_throttle`) at 0.34 of the HBM
-// roofline — three TF32 MMAs per fp32 product, padded from 18 to 24 columns, is MORE pipe time than the FMAs
-// (profiles/r02_headfuse.txt).  tcgen05 would need both halves of the split staged in shared memory in the
-// canonical layout; not attempted.
-// The epilogue (one thread per pixel) sums the partials, applies scale / shift / ReLU per feature, adds the
+// byte — on a B200 (36 T fp32 FMA/s against 6.5 TB/s) plain fp32 FMAs would load the fp32 pipe as much as the
+// stream loads HBM.  Two kernels:
+//  * head_fuse_tc_kernel (K % 32 == 0, i.e. every real backbone): the products run on the 5th-generation tensor
+//    cores — tcgen05.mma kind::tf32 with the accumulator in tensor memory — with the 3xTF32 split that the 1e-5
+//    contract needs done while the operands are staged into the swizzled shared-memory tiles; see its comment.
+//  * head_fuse_kernel (any K % 4 == 0): fp32 FMAs on a 4 pixel x 18 output register tile per thread, persistent
+//    CTAs, 32-channel chunks through a 3-stage cp.async ring that runs across tile boundaries, the four warps of a
+//    CTA splitting a chunk's channels (partial sums meet in shared memory once per tile and feature).
+// An earlier tensor-core version on the legacy path (mma.sync m16n8k8 TF32, 3xTF32) saturated that pipe
+// (`math_pipe_throttle`) at 0.34 of the HBM roofline and was dropped (profiles/r02_headfuse.txt).
+// The epilogue (one thread per pixel, shared by both kernels) applies scale / shift / ReLU per feature, adds the
 // bilinear x2 of the previous level (tf.image.resize_bilinear, align_corners = False: taps (y >> 1, x >> 1) and
 // the next row / column, weight 0.5 on odd coordinates, clamped at the far edge), and the last level multiplies
-// by the 18x18 output matrix and stores both tensors.
+// by the 18x18 output matrix and stores both tensors (and, on request, the decode's threshold word).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -72,6 +71,55 @@ struct HfArgs {
   uint16_t* flags;     // [pixels] or null: the decode's threshold word of the pixel just produced
   float tp_logit, tl_logit;
 };
+
+// per-pixel tail shared by both kernels: bilinear x2 of the previous level, output matrix, stores
+__device__ __forceinline__ void hf_pixel_epilogue(const HfArgs& a, long long px, float (&y)[kHfN], const float* s_wout, const float* s_bout) {
+  // bilinear x2 of the previous level (TF: top + (bottom - top) * fy on rows interpolated the same way in x)
+  if (a.prev) {
+    const int hw = a.H * a.W, Hp = a.H >> 1, Wp = a.W >> 1;
+    const int b = (int)(px / hw), r = (int)(px - (long long)b * hw), yy = r / a.W, xx = r - yy * a.W;
+    const int ylo = yy >> 1, yhi = min(ylo + 1, Hp - 1), xlo = xx >> 1, xhi = min(xlo + 1, Wp - 1);
+    const float fy = (yy & 1) ? 0.5f : 0.f, fx = (xx & 1) ? 0.5f : 0.f;
+    const float* P = a.prev + (size_t)b * Hp * Wp * kHfN;
+    const float2* tl = reinterpret_cast<const float2*>(P + ((size_t)ylo * Wp + xlo) * kHfN);
+    const float2* tr = reinterpret_cast<const float2*>(P + ((size_t)ylo * Wp + xhi) * kHfN);
+    const float2* bl = reinterpret_cast<const float2*>(P + ((size_t)yhi * Wp + xlo) * kHfN);
+    const float2* br = reinterpret_cast<const float2*>(P + ((size_t)yhi * Wp + xhi) * kHfN);
+#pragma unroll
+    for (int o = 0; o < kHfN / 2; ++o) {
+      const float2 q0 = tl[o], q1 = tr[o], q2 = bl[o], q3 = br[o];
+      const float top0 = __fadd_rn(q0.x, __fmul_rn(__fsub_rn(q1.x, q0.x), fx)), top1 = __fadd_rn(q0.y, __fmul_rn(__fsub_rn(q1.y, q0.y), fx));
+      const float bot0 = __fadd_rn(q2.x, __fmul_rn(__fsub_rn(q3.x, q2.x), fx)), bot1 = __fadd_rn(q2.y, __fmul_rn(__fsub_rn(q3.y, q2.y), fx));
+      y[2 * o] += __fadd_rn(top0, __fmul_rn(__fsub_rn(bot0, top0), fy));
+      y[2 * o + 1] += __fadd_rn(top1, __fmul_rn(__fsub_rn(bot1, top1), fy));
+    }
+  }
+  if (a.w_out) {
+    float z[kHfN];
+#pragma unroll
+    for (int o = 0; o < kHfN; ++o) z[o] = s_bout[o];
+#pragma unroll
+    for (int i = 0; i < kHfN; ++i)
+#pragma unroll
+      for (int o = 0; o < kHfN; o += 2) {
+        const float2 t2 = *reinterpret_cast<const float2*>(s_wout + i * kHfN + o);
+        z[o] = fmaf(y[i], t2.x, z[o]), z[o + 1] = fmaf(y[i], t2.y, z[o + 1]);
+      }
+    *reinterpret_cast<float2*>(a.pix + px * 2) = make_float2(z[0], z[1]);
+    if (a.flags) {   // decode_flags_kernel's word (decode.cu): bit d = link d passes, bit 8 = the pixel passes, in logit space
+      unsigned f = (z[1] - z[0]) > a.tp_logit ? 256u : 0u;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) f |= ((z[3 + 2 * d] - z[2 + 2 * d]) > a.tl_logit ? 1u : 0u) << d;
+      a.flags[px] = (uint16_t)f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(a.link + px * 16 + 4 * q) = make_float4(z[2 + 4 * q], z[3 + 4 * q], z[4 + 4 * q], z[5 + 4 * q]);
+  } else {
+#pragma unroll
+    for (int o = 0; o < kHfN; o += 2) *reinterpret_cast<float2*>(a.y18 + px * kHfN + o) = make_float2(y[o], y[o + 1]);
+  }
+}
 
 __global__ void __launch_bounds__(kHfThreads, 2) head_fuse_kernel(const HfArgs a) {
   extern __shared__ __align__(16) float hf_smem[];
@@ -187,55 +235,254 @@ __global__ void __launch_bounds__(kHfThreads, 2) head_fuse_kernel(const HfArgs a
       }
     }
 
-    if (px < total) {
-      // bilinear x2 of the previous level (TF: top + (bottom - top) * fy on rows interpolated the same way in x)
-      if (a.prev) {
-        const int hw = a.H * a.W, Hp = a.H >> 1, Wp = a.W >> 1;
-        const int b = (int)(px / hw), r = (int)(px - (long long)b * hw), yy = r / a.W, xx = r - yy * a.W;
-        const int ylo = yy >> 1, yhi = min(ylo + 1, Hp - 1), xlo = xx >> 1, xhi = min(xlo + 1, Wp - 1);
-        const float fy = (yy & 1) ? 0.5f : 0.f, fx = (xx & 1) ? 0.5f : 0.f;
-        const float* P = a.prev + (size_t)b * Hp * Wp * kHfN;
-        const float2* tl = reinterpret_cast<const float2*>(P + ((size_t)ylo * Wp + xlo) * kHfN);
-        const float2* tr = reinterpret_cast<const float2*>(P + ((size_t)ylo * Wp + xhi) * kHfN);
-        const float2* bl = reinterpret_cast<const float2*>(P + ((size_t)yhi * Wp + xlo) * kHfN);
-        const float2* br = reinterpret_cast<const float2*>(P + ((size_t)yhi * Wp + xhi) * kHfN);
-#pragma unroll
-        for (int o = 0; o < kHfN / 2; ++o) {
-          const float2 q0 = tl[o], q1 = tr[o], q2 = bl[o], q3 = br[o];
-          const float top0 = __fadd_rn(q0.x, __fmul_rn(__fsub_rn(q1.x, q0.x), fx)), top1 = __fadd_rn(q0.y, __fmul_rn(__fsub_rn(q1.y, q0.y), fx));
-          const float bot0 = __fadd_rn(q2.x, __fmul_rn(__fsub_rn(q3.x, q2.x), fx)), bot1 = __fadd_rn(q2.y, __fmul_rn(__fsub_rn(q3.y, q2.y), fx));
-          y[2 * o] += __fadd_rn(top0, __fmul_rn(__fsub_rn(bot0, top0), fy));
-          y[2 * o + 1] += __fadd_rn(top1, __fmul_rn(__fsub_rn(bot1, top1), fy));
-        }
-      }
-      if (a.w_out) {
-        float z[kHfN];
-#pragma unroll
-        for (int o = 0; o < kHfN; ++o) z[o] = s_bout[o];
-#pragma unroll
-        for (int i = 0; i < kHfN; ++i)
-#pragma unroll
-          for (int o = 0; o < kHfN; o += 2) {
-            const float2 t2 = *reinterpret_cast<const float2*>(s_wout + i * kHfN + o);
-            z[o] = fmaf(y[i], t2.x, z[o]), z[o + 1] = fmaf(y[i], t2.y, z[o + 1]);
-          }
-        *reinterpret_cast<float2*>(a.pix + px * 2) = make_float2(z[0], z[1]);
-        if (a.flags) {   // decode_flags_kernel's word (decode.cu): bit d = link d passes, bit 8 = the pixel passes, in logit space
-          unsigned f = (z[1] - z[0]) > a.tp_logit ? 256u : 0u;
-#pragma unroll
-          for (int d = 0; d < 8; ++d) f |= ((z[3 + 2 * d] - z[2 + 2 * d]) > a.tl_logit ? 1u : 0u) << d;
-          a.flags[px] = (uint16_t)f;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(a.link + px * 16 + 4 * q) = make_float4(z[2 + 4 * q], z[3 + 4 * q], z[4 + 4 * q], z[5 + 4 * q]);
-      } else {
-#pragma unroll
-        for (int o = 0; o < kHfN; o += 2) *reinterpret_cast<float2*>(a.y18 + px * kHfN + o) = make_float2(y[o], y[o + 1]);
-      }
-    }
+    if (px < total) hf_pixel_epilogue(a, px, y, s_wout, s_bout);
   }
   cp_async_wait<0>();
+}
+
+
+// ------------------------------------------------------------------ the same level on the 5th-generation tensor cores
+// tcgen05.mma kind::tf32, M = 128 (one tile of pixels), N = 32 (18 outputs, zero padded), K = 8 per instruction,
+// accumulator in tensor memory (32 columns).  fp32 accuracy comes from the 3xTF32 split done while the operands are
+// staged: a thread loads 16 bytes of activations from global memory into registers (coalesced, one chunk ahead),
+// splits every value into hi = the top 19 bits (an exact TF32 number) and lo = v - hi (exact in fp32; the tensor
+// core reads its top 19 bits), and writes both into shared memory in the canonical K-major SWIZZLE_128B layout the
+// matrix descriptors name (a 32-channel chunk = one 128-byte row per pixel, 16-byte pieces XOR-ed with the row index
+// modulo 8, 1024 bytes per group of 8 rows); the weights of the chunk go the same way, transposed to [output][channel].
+// A fifth warp issues, per 8 channels, hi*hi + hi*lo + lo*hi into the accumulator and commits the stage's
+// mbarrier; two operand stages and mbarriers both ways (operands ready: 128 arrivals; stage free / accumulator ready:
+// tcgen05.commit; accumulator read: 128 arrivals), so the four staging warps never wait for the issue itself.  When
+// the last chunk of a (tile, feature) is committed they wait for it, read their accumulator row (tcgen05.ld, lane =
+// pixel) and run the same per-pixel epilogue as the FMA kernel.  Needs K % 32 == 0; other shapes take the FMA kernel.
+constexpr int kTcThreads = 160;                  // 4 staging / epilogue warps + 1 warp that issues the MMAs
+constexpr int kTcWorkers = 128;
+constexpr int kTcTile = 128;
+constexpr int kTcKC = 32;
+constexpr int kTcNP = 32;                        // N of the MMA
+constexpr int kTcABytes = kTcTile * kTcKC * 4;   // 16 KB: one operand tile of activations
+constexpr int kTcBBytes = kTcNP * kTcKC * 4;     // 4 KB
+constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // hi + lo of both operands
+constexpr size_t kTcSmem = 1024 + 2 * kTcStageBytes + (kHfN * kHfN + kHfN + 4 * kHfN + 2) * 4 + 64;   // + 6 mbarriers
+
+__device__ __forceinline__ unsigned long long tc_smem_desc(uint32_t saddr) {
+  // start address [0,14) (>>4), leading byte offset [16,30) unused for a swizzled K-major tile, stride byte offset
+  // [32,46) = 1024 B between groups of 8 rows, descriptor version 1 [46,48), layout SWIZZLE_128B = 2 at [61,64)
+  return (unsigned long long)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, unsigned long long da, unsigned long long db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra TC_DONE;\n"
+      "bra TC_WAIT;\n"
+      "TC_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(0x989680)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArgs a) {
+  extern __shared__ __align__(16) unsigned char tc_raw[];
+  const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(tc_raw);
+  unsigned char* base = tc_raw + ((1024u - (raw_s & 1023u)) & 1023u);     // SWIZZLE_128B tiles want 1024-byte alignment
+  float* s_wout = reinterpret_cast<float*>(base + 2 * kTcStageBytes);
+  float* s_bout = s_wout + kHfN * kHfN;
+  float* s_aff = s_bout + kHfN;
+  // mbarriers: [0,1] stage free (commit), [2] accumulator ready (commit), [3,4] operands ready (128), [5] accumulator read (128)
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_aff + 4 * kHfN + 2);
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const long long total = (long long)a.B * a.H * a.W;
+  const long long ntiles = (total + kTcTile - 1) / kTcTile;
+  for (int i = tid; i < kHfN * kHfN; i += kTcThreads) s_wout[i] = a.w_out ? a.w_out[i] : 0.f;
+  if (tid < kHfN) s_bout[tid] = a.b_out ? a.b_out[tid] : 0.f;
+  if (tid < 4 * kHfN) {
+    const int fi = tid / (2 * kHfN), which = (tid / kHfN) & 1, c = tid % kHfN;
+    const float* src = which ? a.f[fi].shift : a.f[fi].scale;
+    s_aff[tid] = (fi < a.nf && src) ? src[c] : (which ? 0.f : 1.f);
+  }
+  // rows 18..31 of the weight tiles stay zero: clear both stages' B tiles once
+  for (int i = tid; i < 2 * 2 * kTcBBytes / 16; i += kTcThreads) {
+    const int st = i / (2 * kTcBBytes / 16), r = i % (2 * kTcBBytes / 16);
+    *reinterpret_cast<float4*>(base + st * kTcStageBytes + 2 * kTcABytes + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + i)), "r"(i < 3 ? 1 : kTcWorkers));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the cleared weight rows
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+  const uint32_t base_s = (uint32_t)__cvta_generic_to_shared(base);
+  // c_format F32 (bits 4-5 = 1), a / b format TF32 (2 at bits 7-9 and 10-12), both K-major, N >> 3 at 17, M >> 4 at 24
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcNP >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+
+  if (warp == 4) {
+    // ---- the issuing warp: same (tile, feature, chunk) sequence as the staging warps
+    uint32_t n_chunk = 0, n_acc = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int fi = 0; fi < a.nf; ++fi) {
+        const int nchunks = a.f[fi].K / kTcKC;
+        if (n_acc >= 1) tc_mbar_wait(bar0 + 8 * 5, (n_acc - 1) & 1);   // the previous accumulator has been read
+        for (int ch = 0; ch < nchunks; ++ch, ++n_chunk) {
+          const int st = n_chunk & 1;
+          tc_mbar_wait(bar0 + 8 * (3 + st), (n_chunk >> 1) & 1);       // operands staged (and fenced) by all 128 threads
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if ((tid & 31) == 0) {
+            const uint32_t sa_hi = base_s + st * kTcStageBytes, sa_lo = sa_hi + kTcABytes, sb_hi = sa_lo + kTcABytes, sb_lo = sb_hi + kTcBBytes;
+#pragma unroll
+            for (int j = 0; j < kTcKC / 8; ++j) {
+              const unsigned long long dah = tc_smem_desc(sa_hi + 32 * j), dal = tc_smem_desc(sa_lo + 32 * j);
+              const unsigned long long dbh = tc_smem_desc(sb_hi + 32 * j), dbl = tc_smem_desc(sb_lo + 32 * j);
+              tc_mma(tmem, dal, dbh, idesc, (ch | j) != 0);
+              tc_mma(tmem, dah, dbl, idesc, 1);
+              tc_mma(tmem, dah, dbh, idesc, 1);
+            }
+            tc_commit(bar0 + 8 * st);
+            if (ch == nchunks - 1) tc_commit(bar0 + 16);
+          }
+          __syncwarp();
+        }
+        ++n_acc;
+      }
+  } else {
+  // this thread's share of a chunk: rows r0 + 16 i of the tile, 16-byte piece c of their 128 bytes; weights e, e + 128, ...
+  // Two chunks are kept in flight in registers (the loads of chunk n + 2 are issued when chunk n has been staged),
+  // following a cursor over the (tile, feature, chunk) stream that runs across tile boundaries.
+  const int r0 = tid >> 3, cpiece = tid & 7;
+  float4 av0[8], av1[8];
+  float wv0[5], wv1[5];
+  long long c_tile = blockIdx.x;
+  int c_f = 0, c_ch = 0;
+  auto load_next = [&](float4 (&av)[8], float (&wv)[5]) {
+    if (c_tile >= ntiles) return;
+    const HfFeature& F = a.f[c_f];
+    const int k0 = c_ch * kTcKC;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long px = c_tile * kTcTile + r0 + 16 * i;
+      av[i] = px < total ? ldg_stream4(reinterpret_cast<const float4*>(F.x + (size_t)px * F.K + k0) + cpiece) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int e = tid + i * kTcWorkers;
+      wv[i] = e < kTcKC * kHfN ? __ldg(F.w + (size_t)k0 * kHfN + e) : 0.f;
+    }
+    if (++c_ch == F.K / kTcKC) {
+      c_ch = 0;
+      if (++c_f == a.nf) c_f = 0, c_tile += gridDim.x;
+    }
+  };
+  auto split = [](float v, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    lo = v - hi;
+  };
+  auto store_chunk = [&](int st, const float4 (&av)[8], const float (&wv)[5]) {
+    unsigned char* A_hi = base + st * kTcStageBytes;
+    unsigned char* A_lo = A_hi + kTcABytes;
+    unsigned char* B_hi = A_lo + kTcABytes;
+    unsigned char* B_lo = B_hi + kTcBBytes;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + 16 * i;
+      const int off = r * 128 + ((cpiece ^ (r & 7)) << 4);
+      float4 h, l;
+      split(av[i].x, h.x, l.x), split(av[i].y, h.y, l.y), split(av[i].z, h.z, l.z), split(av[i].w, h.w, l.w);
+      *reinterpret_cast<float4*>(A_hi + off) = h;
+      *reinterpret_cast<float4*>(A_lo + off) = l;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int e = tid + i * kTcWorkers;
+      if (e < kTcKC * kHfN) {
+        const int k = e / kHfN, n = e - k * kHfN;
+        const int off = n * 128 + (((k >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
+        float h, l;
+        split(wv[i], h, l);
+        *reinterpret_cast<float*>(B_hi + off) = h;
+        *reinterpret_cast<float*>(B_lo + off) = l;
+      }
+    }
+  };
+
+  uint32_t n_chunk = 0, n_acc = 0;   // chunks staged / accumulators finished by this CTA so far
+  load_next(av0, wv0);
+  load_next(av1, wv1);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long px = tile * kTcTile + tid;
+    float y[kHfN];
+#pragma unroll
+    for (int o = 0; o < kHfN; ++o) y[o] = 0.f;
+    for (int fi = 0; fi < a.nf; ++fi) {
+      const int nchunks = a.f[fi].K / kTcKC;
+      for (int ch = 0; ch < nchunks; ++ch, ++n_chunk) {
+        const int st = n_chunk & 1;
+        // the MMAs that read this stage two chunks ago are done (use u of a stage waits for completion u - 1)
+        if (n_chunk >= 2) tc_mbar_wait(bar0 + 8 * st, ((n_chunk >> 1) - 1) & 1);
+        if (st == 0) {
+          store_chunk(0, av0, wv0);
+          load_next(av0, wv0);
+        } else {
+          store_chunk(1, av1, wv1);
+          load_next(av1, wv1);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (3 + st)) : "memory");
+      }
+      // the accumulator of this (tile, feature): lane = pixel, 32 columns (18 used)
+      tc_mbar_wait(bar0 + 16, n_acc & 1);
+      ++n_acc;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(tmem + ((uint32_t)(warp * 32) << 16)));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * 5) : "memory");   // the next accumulation may overwrite it
+      const float* sc = s_aff + fi * 2 * kHfN;
+      const bool relu = a.f[fi].relu != 0;
+#pragma unroll
+      for (int o = 0; o < kHfN; ++o) {
+        float m = __fadd_rn(__fmul_rn(__uint_as_float(v[o]), sc[o]), sc[kHfN + o]);
+        if (relu) m = fmaxf(m, 0.f);
+        y[o] += m;
+      }
+    }
+    if (px < total) hf_pixel_epilogue(a, px, y, s_wout, s_bout);
+  }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
 }
 
 }  // namespace plh
@@ -269,10 +516,17 @@ extern "C" int plh_head_fuse_level(const float* xa, int Ka, const float* wa, con
     a.tp_logit = prob_to_logit_threshold(flag_params->pixel_thresh);
     a.tl_logit = prob_to_logit_threshold(flag_params->link_thresh);
   }
-  static SmemOptIn optin;
+  static SmemOptIn optin, optin_tc;
   int rc;
-  if ((rc = ensure_dynamic_smem(optin, head_fuse_kernel, kHfSmem))) return rc;
   const long long ntiles = ((long long)B * H * W + kHfTile - 1) / kHfTile;
+  static const bool force_fma = getenv("PLH_HEADFUSE_FMA") != nullptr;   // A/B: the fp32-FMA kernel for every shape
+  if (!force_fma && Ka % kTcKC == 0 && (!xb || Kb % kTcKC == 0)) {
+    if ((rc = ensure_dynamic_smem(optin_tc, head_fuse_tc_kernel, kTcSmem))) return rc;
+    const int grid_tc = (int)std::min<long long>(ntiles, 2ll * kNumSMs);
+    head_fuse_tc_kernel<<<grid_tc, kTcThreads, kTcSmem, (cudaStream_t)stream>>>(a);
+    return launch_status();
+  }
+  if ((rc = ensure_dynamic_smem(optin, head_fuse_kernel, kHfSmem))) return rc;
   const int grid = (int)std::min<long long>(ntiles, 2ll * kNumSMs);   // two resident CTAs per SM
   head_fuse_kernel<<<grid, kHfThreads, kHfSmem, (cudaStream_t)stream>>>(a);
   return launch_status();
