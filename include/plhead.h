@@ -278,8 +278,11 @@ PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double r
  *            its inference form); relu != 0: ReLU after it (nets/model.py:103-107 arg_scope)
  *  prev      [B,H/2,W/2,18] optional: the previous level, upsampled like tf.image.resize_bilinear(align_corners =
  *            False) does for an exact factor 2
- *  w_out [18,18] (in, out), b_out [18] optional; y18 [B,H,W,18] (w_out null) or pix_logits [B,H,W,2] +
- *            link_logits [B,H,W,16] (w_out given)
+ *  w_out [18,18] (in, out), b_out [18] optional: y <- y w_out + b_out
+ *  output    either y18 [B,H,W,18] (a level that feeds the next one) or pix_logits [B,H,W,2] + link_logits
+ *            [B,H,W,16] (the last level), independently of w_out: a caller whose fuse convolutions carry no
+ *            activation can fold the output matrix into the weights (x (W w_out) + up2(prev w_out)) and apply w_out
+ *            one level earlier, on a quarter of the pixels
  *  flags [B,H,W] uint16 optional (last level only, with flag_params = the decode's thresholds): the word
  *            plh_decode_flags would compute from the logits just produced (bit-identical: same logit-space
  *            thresholds on the same fp32 values), so that plh_decode_from_flags can start without reading the 72 B

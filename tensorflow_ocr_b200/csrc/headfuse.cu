@@ -94,8 +94,8 @@ __device__ __forceinline__ void hf_pixel_epilogue(const HfArgs& a, long long px,
       y[2 * o + 1] += __fadd_rn(top1, __fmul_rn(__fsub_rn(bot1, top1), fy));
     }
   }
+  float z[kHfN];
   if (a.w_out) {
-    float z[kHfN];
 #pragma unroll
     for (int o = 0; o < kHfN; ++o) z[o] = s_bout[o];
 #pragma unroll
@@ -105,6 +105,11 @@ __device__ __forceinline__ void hf_pixel_epilogue(const HfArgs& a, long long px,
         const float2 t2 = *reinterpret_cast<const float2*>(s_wout + i * kHfN + o);
         z[o] = fmaf(y[i], t2.x, z[o]), z[o + 1] = fmaf(y[i], t2.y, z[o + 1]);
       }
+  } else {
+#pragma unroll
+    for (int o = 0; o < kHfN; ++o) z[o] = y[o];
+  }
+  if (a.pix) {   // the two logit tensors
     *reinterpret_cast<float2*>(a.pix + px * 2) = make_float2(z[0], z[1]);
     if (a.flags) {   // decode_flags_kernel's word (decode.cu): bit d = link d passes, bit 8 = the pixel passes, in logit space
       unsigned f = (z[1] - z[0]) > a.tp_logit ? 256u : 0u;
@@ -115,9 +120,9 @@ __device__ __forceinline__ void hf_pixel_epilogue(const HfArgs& a, long long px,
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       *reinterpret_cast<float4*>(a.link + px * 16 + 4 * q) = make_float4(z[2 + 4 * q], z[3 + 4 * q], z[4 + 4 * q], z[5 + 4 * q]);
-  } else {
+  } else {       // [pixels, 18] for the next level
 #pragma unroll
-    for (int o = 0; o < kHfN; o += 2) *reinterpret_cast<float2*>(a.y18 + px * kHfN + o) = make_float2(y[o], y[o + 1]);
+    for (int o = 0; o < kHfN; o += 2) *reinterpret_cast<float2*>(a.y18 + px * kHfN + o) = make_float2(z[o], z[o + 1]);
   }
 }
 
@@ -344,7 +349,19 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
   if (warp == 4) {
     // ---- the issuing warp: same (tile, feature, chunk) sequence as the staging warps
     uint32_t n_chunk = 0, n_acc = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      // DRAM -> L2 ahead of the staging warps: the activation block of this CTA's NEXT tile is one contiguous
+      // range per feature (128 pixels x K floats); one bulk prefetch each.  The register-staged loads then find
+      // their lines in L2, which takes the DRAM latency out of the 64 KB of loads an SM can keep outstanding.
+      if ((tid & 31) == 0) {
+        const long long nt = tile + gridDim.x;
+        if (nt < ntiles)
+          for (int fi = 0; fi < a.nf; ++fi) {
+            const long long rows = min((long long)kTcTile, total - nt * kTcTile);
+            const size_t bytes = (size_t)rows * a.f[fi].K * 4;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.f[fi].x + (size_t)nt * kTcTile * a.f[fi].K), "r"((uint32_t)bytes) : "memory");
+          }
+      }
       for (int fi = 0; fi < a.nf; ++fi) {
         const int nchunks = a.f[fi].K / kTcKC;
         if (n_acc >= 1) tc_mbar_wait(bar0 + 8 * 5, (n_acc - 1) & 1);   // the previous accumulator has been read
@@ -369,6 +386,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
         }
         ++n_acc;
       }
+    }
   } else {
   // this thread's share of a chunk: rows r0 + 16 i of the tile, 16-byte piece c of their 128 bytes; weights e, e + 128, ...
   // Two chunks are kept in flight in registers (the loads of chunk n + 2 are issued when chunk n has been staged),
@@ -377,30 +395,48 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
   float4 av0[8], av1[8];
   float wv0[5], wv1[5];
   long long c_tile = blockIdx.x;
-  int c_f = 0, c_ch = 0;
-  auto load_next = [&](float4 (&av)[8], float (&wv)[5]) {
+  int c_f = 0, c_ch = 0, c_rows = 0, c_nch = 1;
+  const float* c_ptr = nullptr;   // this thread's 16 bytes of row r0 of the cursor's (tile, feature), chunk 0
+  const float* c_w = nullptr;
+  size_t c_stride = 0;            // 16 rows further
+  auto retarget = [&]() {
     if (c_tile >= ntiles) return;
     const HfFeature& F = a.f[c_f];
-    const int k0 = c_ch * kTcKC;
+    c_ptr = F.x + (size_t)(c_tile * kTcTile + r0) * F.K + 4 * cpiece;
+    c_w = F.w + tid;
+    c_stride = (size_t)16 * F.K;
+    c_rows = (int)min((long long)kTcTile, total - c_tile * kTcTile) - r0;   // row r0 + 16 i exists iff 16 i < c_rows
+    c_nch = F.K / kTcKC;
+  };
+  retarget();
+  auto load_next = [&](float4 (&av)[8], float (&wv)[5]) {
+    if (c_tile >= ntiles) return;
+    const float* p = c_ptr + c_ch * kTcKC;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const long long px = c_tile * kTcTile + r0 + 16 * i;
-      av[i] = px < total ? ldg_stream4(reinterpret_cast<const float4*>(F.x + (size_t)px * F.K + k0) + cpiece) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int i = 0; i < 8; ++i, p += c_stride)
+      av[i] = 16 * i < c_rows ? ldg_stream4(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* q = c_w + (size_t)c_ch * (kTcKC * kHfN);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const int e = tid + i * kTcWorkers;
-      wv[i] = e < kTcKC * kHfN ? __ldg(F.w + (size_t)k0 * kHfN + e) : 0.f;
-    }
-    if (++c_ch == F.K / kTcKC) {
+    for (int i = 0; i < 5; ++i) wv[i] = tid + i * kTcWorkers < kTcKC * kHfN ? __ldg(q + i * kTcWorkers) : 0.f;
+    if (++c_ch == c_nch) {
       c_ch = 0;
       if (++c_f == a.nf) c_f = 0, c_tile += gridDim.x;
+      retarget();
     }
   };
   auto split = [](float v, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     lo = v - hi;
   };
+  // where this thread's pieces go in the swizzled tiles (the same in every chunk): rows r0 + 16 i keep r & 7, so the
+  // activation offsets are a_off + 2048 i; weight element e = (k, n) -> row n, 16-byte piece k >> 2 XOR-ed with n & 7
+  const int a_off = r0 * 128 + ((cpiece ^ (r0 & 7)) << 4);
+  int b_off[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int e = tid + i * kTcWorkers, k = e / kHfN, n = e - k * kHfN;
+    b_off[i] = n * 128 + (((k >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
+  }
   auto store_chunk = [&](int st, const float4 (&av)[8], const float (&wv)[5]) {
     unsigned char* A_hi = base + st * kTcStageBytes;
     unsigned char* A_lo = A_hi + kTcABytes;
@@ -408,8 +444,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
     unsigned char* B_lo = B_hi + kTcBBytes;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int r = r0 + 16 * i;
-      const int off = r * 128 + ((cpiece ^ (r & 7)) << 4);
+      const int off = a_off + 2048 * i;
       float4 h, l;
       split(av[i].x, h.x, l.x), split(av[i].y, h.y, l.y), split(av[i].z, h.z, l.z), split(av[i].w, h.w, l.w);
       *reinterpret_cast<float4*>(A_hi + off) = h;
@@ -419,8 +454,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
     for (int i = 0; i < 5; ++i) {
       const int e = tid + i * kTcWorkers;
       if (e < kTcKC * kHfN) {
-        const int k = e / kHfN, n = e - k * kHfN;
-        const int off = n * 128 + (((k >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
+        const int off = b_off[i];
         float h, l;
         split(wv[i], h, l);
         *reinterpret_cast<float*>(B_hi + off) = h;
@@ -497,7 +531,7 @@ extern "C" int plh_head_fuse_level(const float* xa, int Ka, const float* wa, con
                                    void* stream) {
   if (!xa || !wa) return PLH_E_NULL;
   if (xb && !wb) return PLH_E_NULL;
-  if (w_out ? (!pix_logits || !link_logits) : !y18) return PLH_E_NULL;
+  if (y18 ? (pix_logits || link_logits) : (!pix_logits || !link_logits)) return PLH_E_NULL;   // one output form
   if (B <= 0 || H <= 0 || W <= 0 || (long long)B * H * W > (1ll << 31) - 1) return PLH_E_SHAPE;
   if (Ka <= 0 || (Ka & 3) || (xb && (Kb <= 0 || (Kb & 3)))) return PLH_E_SHAPE;   // 16-byte rows
   if (prev && ((H & 1) || (W & 1))) return PLH_E_SHAPE;                            // the level is exactly twice the previous one
@@ -511,7 +545,7 @@ extern "C" int plh_head_fuse_level(const float* xa, int Ka, const float* wa, con
   a.y18 = y18, a.pix = pix_logits, a.link = link_logits;
   a.flags = nullptr, a.tp_logit = a.tl_logit = 0.f;
   if (flags) {
-    if (!w_out || !flag_params) return PLH_E_NULL;   // the threshold word belongs to the logits of the last level
+    if (!pix_logits || !flag_params) return PLH_E_NULL;   // the threshold word belongs to the logits of the last level
     a.flags = flags;
     a.tp_logit = prob_to_logit_threshold(flag_params->pixel_thresh);
     a.tl_logit = prob_to_logit_threshold(flag_params->link_thresh);

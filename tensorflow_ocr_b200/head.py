@@ -354,13 +354,15 @@ def contour_boxes_raw(mask: torch.Tensor, ratio_w: float = 1.0, ratio_h: float =
 
 
 def head_fuse_level_raw(feats, prev: Optional[torch.Tensor] = None, w_out: Optional[torch.Tensor] = None,
-                        b_out: Optional[torch.Tensor] = None, flags_cfg: Optional["DecodeConfig"] = None):
+                        b_out: Optional[torch.Tensor] = None, flags_cfg: Optional["DecodeConfig"] = None,
+                        logits: Optional[bool] = None):
     """plh_head_fuse_level: one level of the logit producer (nets/pixellink.py:56-67, nets/model.py:129-141).
 
     feats: one or two (x [B,H,W,K], w [K,18], scale [18] | None, shift [18] | None, relu) tuples (CUDA fp32);
     prev [B,H/2,W/2,18] | None; w_out [18,18] (in, out) + b_out [18] for the last level.
-    -> y18 [B,H,W,18], or (pixel logits [B,H,W,2], link logits [B,H,W,16]) when w_out is given; with flags_cfg (a
-    DecodeConfig, last level only) also the decode's threshold words int16 [B,H,W] as third element."""
+    logits (default: w_out is given): the output form — False: y18 [B,H,W,18] for the next level, True: (pixel
+    logits [B,H,W,2], link logits [B,H,W,16]); with flags_cfg (a DecodeConfig, logits form only) also the decode's
+    threshold words int16 [B,H,W] as third element."""
     lib = _lib.load()
     if not 1 <= len(feats) <= 2:
         raise ValueError("a level fuses one or two feature maps")
@@ -382,9 +384,11 @@ def head_fuse_level_raw(feats, prev: Optional[torch.Tensor] = None, w_out: Optio
         if tuple(prev.shape) != (B, H // 2, W // 2, 18) or H % 2 or W % 2:
             raise ValueError("prev must be [B,H/2,W/2,18], got %s for a %dx%d level" % (tuple(prev.shape), H, W))
         prev = prev.contiguous()
+    logits = (w_out is not None) if logits is None else bool(logits)
     if w_out is not None:
         w_out = w_out.contiguous().float()
         b_out = None if b_out is None else b_out.contiguous().float()
+    if logits:
         pix = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev)
         link = torch.empty((B, H, W, 16), dtype=torch.float32, device=dev)
         y18 = None
@@ -393,15 +397,15 @@ def head_fuse_level_raw(feats, prev: Optional[torch.Tensor] = None, w_out: Optio
         pix = link = None
     flags, dp = None, None
     if flags_cfg is not None:
-        if w_out is None:
-            raise ValueError("threshold words belong to the last level (w_out given)")
+        if not logits:
+            raise ValueError("threshold words belong to the logits (the last level)")
         flags = torch.empty((B, H, W), dtype=torch.int16, device=dev)
         dp = flags_cfg.c_struct()
     with torch.cuda.device(dev):
         rc = lib.plh_head_fuse_level(*flat, _p(prev), _p(w_out), _p(b_out), B, H, W, _p(y18), _p(pix), _p(link),
                                      C.byref(dp) if dp is not None else None, _p(flags), _stream(dev))
     _lib.check(rc, "plh_head_fuse_level")
-    if w_out is None:
+    if not logits:
         return y18
     return (pix, link) if flags is None else (pix, link, flags)
 

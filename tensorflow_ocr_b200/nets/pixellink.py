@@ -86,16 +86,22 @@ def pixellink_layers(end_points, params, decode_config=None):
         x[name], was_np = head.to_device(end_points[name], device=dev)
         dev = x[name].device
         np_in = np_in or was_np
+    w_out = torch.zeros((18, 18), dtype=torch.float32, device=dev)     # the two last convolutions as one block matrix
+    w_out[:2, :2], _ = head.to_device(params["text_predication"][0], device=dev)
+    w_out[2:, 2:], _ = head.to_device(params["link_predication"][0], device=dev)
+    b_out = _cat18(params["text_predication"][1], params["link_predication"][1], dev)
     feats = {}
     for name, st in _FUSE_SCOPES:
         w = _cat18(params["stage_%d_pixel_fuse" % st][0], params["stage_%d_link_fuse" % st][0], dev)
         b = _cat18(params["stage_%d_pixel_fuse" % st][1], params["stage_%d_link_fuse" % st][1], dev)
         feats[name] = (x[name], w, None, b, False)
-    w_out = torch.zeros((18, 18), dtype=torch.float32, device=dev)     # the two last convolutions as one block matrix
-    w_out[:2, :2], _ = head.to_device(params["text_predication"][0], device=dev)
-    w_out[2:, 2:], _ = head.to_device(params["link_predication"][0], device=dev)
-    b_out = _cat18(params["text_predication"][1], params["link_predication"][1], dev)
+    # The fuse convolutions carry no activation, so the last 1x1 convolutions commute with everything after stage 2:
+    #   (unpool(s2) + x3 W3 + b3) W_out + b_out = unpool(s2 W_out) + x3 (W3 W_out) + (b3 W_out + b_out).
+    # W_out is applied to s2 (a quarter of the pixels) and folded into the conv3_3 weights; the largest level then
+    # has no per-pixel output matrix left.
+    w3 = (feats["conv3_3"][1].double() @ w_out.double()).float().contiguous()
+    b3 = (feats["conv3_3"][3].double() @ w_out.double() + b_out.double()).float().contiguous()
     s1 = head.head_fuse_level_raw([feats["fc7"], feats["conv5_3"]])
-    s2 = head.head_fuse_level_raw([feats["conv4_3"]], prev=s1)
-    res = head.head_fuse_level_raw([feats["conv3_3"]], prev=s2, w_out=w_out, b_out=b_out, flags_cfg=decode_config)
+    s2 = head.head_fuse_level_raw([feats["conv4_3"]], prev=s1, w_out=w_out, logits=False)
+    res = head.head_fuse_level_raw([(x["conv3_3"], w3, None, b3, False)], prev=s2, logits=True, flags_cfg=decode_config)
     return tuple(t.cpu().numpy() for t in res) if np_in else res
