@@ -259,6 +259,13 @@ __global__ void __launch_bounds__(kHfThreads, 2) head_fuse_kernel(const HfArgs a
 // tcgen05.commit; accumulator read: 128 arrivals), so the four staging warps never wait for the issue itself.  When
 // the last chunk of a (tile, feature) is committed they wait for it, read their accumulator row (tcgen05.ld, lane =
 // pixel) and run the same per-pixel epilogue as the FMA kernel.  Needs K % 32 == 0; other shapes take the FMA kernel.
+// What bounds it (profiles/r02_headfuse.txt): SHARED-MEMORY bandwidth.  Per 16 KB chunk of activations the operand
+// tiles are written once (hi + lo: 32 KB) and read by the tensor core three times (hi twice, lo once: 48 KB — the
+// A operand is re-read by every MMA, whatever N is): 80 KB per chunk = 0.33 us at 128 B/clk, against 0.37 us for
+// the chunk's HBM time.  A fully warp-specialised variant (cp.async loaders writing the swizzled layout directly so
+// that the raw tile serves as the hi operand, converters producing only lo, two accumulators, separate epilogue
+// warps) was built and is bit-compatible, but moves 96 KB per chunk through shared memory and measures the same
+// (314 vs 305 us); the way past this bound is to feed the A operand from tensor memory, not attempted.
 constexpr int kTcThreads = 160;                  // 4 staging / epilogue warps + 1 warp that issues the MMAs
 constexpr int kTcWorkers = 128;
 constexpr int kTcTile = 128;
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
     if (c_tile >= ntiles) return;
     const HfFeature& F = a.f[c_f];
     c_ptr = F.x + (size_t)(c_tile * kTcTile + r0) * F.K + 4 * cpiece;
-    c_w = F.w + tid;
+    c_w = F.w;
     c_stride = (size_t)16 * F.K;
     c_rows = (int)min((long long)kTcTile, total - c_tile * kTcTile) - r0;   // row r0 + 16 i exists iff 16 i < c_rows
     c_nch = F.K / kTcKC;
@@ -415,9 +422,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
 #pragma unroll
     for (int i = 0; i < 8; ++i, p += c_stride)
       av[i] = 16 * i < c_rows ? ldg_stream4(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // weight element e = tid + 128 i is (channel e % 32, output e / 32): a warp then writes one 128-byte row of the
+    // transposed tile (conflict-free), and reads with stride 18
     const float* q = c_w + (size_t)c_ch * (kTcKC * kHfN);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) wv[i] = tid + i * kTcWorkers < kTcKC * kHfN ? __ldg(q + i * kTcWorkers) : 0.f;
+    for (int i = 0; i < 5; ++i) {
+      const int e = tid + i * kTcWorkers;
+      wv[i] = e < kTcKC * kHfN ? __ldg(q + (e & 31) * kHfN + (e >> 5)) : 0.f;
+    }
     if (++c_ch == c_nch) {
       c_ch = 0;
       if (++c_f == a.nf) c_f = 0, c_tile += gridDim.x;
@@ -434,7 +446,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
   int b_off[5];
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
-    const int e = tid + i * kTcWorkers, k = e / kHfN, n = e - k * kHfN;
+    const int e = tid + i * kTcWorkers, k = e & 31, n = e >> 5;
     b_off[i] = n * 128 + (((k >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
   }
   auto store_chunk = [&](int st, const float4 (&av)[8], const float (&wv)[5]) {
@@ -518,6 +530,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
   __syncthreads();
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
 }
+
 
 }  // namespace plh
 
