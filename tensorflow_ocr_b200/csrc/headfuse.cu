@@ -254,15 +254,16 @@ __global__ void __launch_bounds__(kHfThreads, 2) head_fuse_kernel(const HfArgs a
 // core reads its top 19 bits), and writes both into shared memory in the canonical K-major SWIZZLE_128B layout the
 // matrix descriptors name (a 32-channel chunk = one 128-byte row per pixel, 16-byte pieces XOR-ed with the row index
 // modulo 8, 1024 bytes per group of 8 rows); the weights of the chunk go the same way, transposed to [output][channel].
-// A fifth warp issues, per 8 channels, hi*hi + hi*lo + lo*hi into the accumulator and commits the stage's
+// A fifth warp issues, per 8 channels, hi*[hi|lo] (one N = 64 MMA: the two weight tiles lie back to back) and lo*hi
+// into the accumulator (64 columns; the epilogue adds the halves) and commits the stage's
 // mbarrier; two operand stages and mbarriers both ways (operands ready: 128 arrivals; stage free / accumulator ready:
 // tcgen05.commit; accumulator read: 128 arrivals), so the four staging warps never wait for the issue itself.  When
 // the last chunk of a (tile, feature) is committed they wait for it, read their accumulator row (tcgen05.ld, lane =
 // pixel) and run the same per-pixel epilogue as the FMA kernel.  Needs K % 32 == 0; other shapes take the FMA kernel.
 // What bounds it (profiles/r02_headfuse.txt): SHARED-MEMORY bandwidth.  Per 16 KB chunk of activations the operand
-// tiles are written once (hi + lo: 32 KB) and read by the tensor core three times (hi twice, lo once: 48 KB — the
-// A operand is re-read by every MMA, whatever N is): 80 KB per chunk = 0.33 us at 128 B/clk, against 0.37 us for
-// the chunk's HBM time.  A fully warp-specialised variant (cp.async loaders writing the swizzled layout directly so
+// tiles are written once (hi + lo: 32 KB) and read by the tensor core once per MMA that uses them — the A operand is
+// re-read by every MMA, whatever N is, which is why hi*hi and hi*lo share one MMA: 32 KB instead of 48 KB.  64 KB per
+// chunk = 0.26 us at 128 B/clk, against 0.37 us for the chunk's HBM time (80 KB / 0.33 us with three MMAs).  A fully warp-specialised variant (cp.async loaders writing the swizzled layout directly so
 // that the raw tile serves as the hi operand, converters producing only lo, two accumulators, separate epilogue
 // warps) was built and is bit-compatible, but moves 96 KB per chunk through shared memory and measures the same
 // (314 vs 305 us); the way past this bound is to feed the A operand from tensor memory, not attempted.
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the cleared weight rows
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
   const uint32_t base_s = (uint32_t)__cvta_generic_to_shared(base);
   // c_format F32 (bits 4-5 = 1), a / b format TF32 (2 at bits 7-9 and 10-12), both K-major, N >> 3 at 17, M >> 4 at 24
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcNP >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+  const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * kTcNP >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);   // N = 64
 
   if (warp == 4) {
     // ---- the issuing warp: same (tile, feature, chunk) sequence as the staging warps
@@ -380,12 +382,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
             const uint32_t sa_hi = base_s + st * kTcStageBytes, sa_lo = sa_hi + kTcABytes, sb_hi = sa_lo + kTcABytes, sb_lo = sb_hi + kTcBBytes;
 #pragma unroll
             for (int j = 0; j < kTcKC / 8; ++j) {
+              // the hi and lo weight tiles lie back to back: one N = 64 MMA gives hi*hi (columns 0-31) and hi*lo (columns
+              // 32-63) for a single read of the hi activations; lo*hi goes into columns 0-31.  The epilogue adds the halves.
               const unsigned long long dah = tc_smem_desc(sa_hi + 32 * j), dal = tc_smem_desc(sa_lo + 32 * j);
-              const unsigned long long dbh = tc_smem_desc(sb_hi + 32 * j), dbl = tc_smem_desc(sb_lo + 32 * j);
-              tc_mma(tmem, dal, dbh, idesc, (ch | j) != 0);
-              tc_mma(tmem, dah, dbl, idesc, 1);
-              tc_mma(tmem, dah, dbh, idesc, 1);
+              const unsigned long long dbh = tc_smem_desc(sb_hi + 32 * j);
+              tc_mma(tmem, dah, dbh, idesc2, (ch | j) != 0);
+              tc_mma(tmem, dal, dbh, idesc, 1);
             }
+            (void)sb_lo;
             tc_commit(bar0 + 8 * st);
             if (ch == nchunks - 1) tc_commit(bar0 + 16);
           }
@@ -503,17 +507,28 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
       tc_mbar_wait(bar0 + 16, n_acc & 1);
       ++n_acc;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t v[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(tmem + ((uint32_t)(warp * 32) << 16)));
+      // 18 of the 32 columns of each half: x16 + x2 loads (columns 0-17 hold hi*hi + lo*hi, 32-49 hold hi*lo)
+      uint32_t v[kHfN], v2[kHfN];
+      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#define PLH_TLD16(arr, col)                                                                                                  \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"        \
+               : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
+                 "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]),         \
+                 "=r"(arr[15])                                                                                                 \
+               : "r"(trow + (col)))
+#define PLH_TLD2(arr, col) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(arr[16]), "=r"(arr[17]) : "r"(trow + (col) + 16))
+      PLH_TLD16(v, 0);
+      PLH_TLD2(v, 0);
+      PLH_TLD16(v2, 32);
+      PLH_TLD2(v2, 32);
+#undef PLH_TLD16
+#undef PLH_TLD2
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * 5) : "memory");   // the next accumulation may overwrite it
+#pragma unroll
+      for (int o = 0; o < kHfN; ++o) v[o] = __float_as_uint(__uint_as_float(v[o]) + __uint_as_float(v2[o]));
       const float* sc = s_aff + fi * 2 * kHfN;
       const bool relu = a.f[fi].relu != 0;
 #pragma unroll
@@ -528,7 +543,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
 }
 
 
