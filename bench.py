@@ -525,7 +525,96 @@ class LossAblation(Workload):
         return _roofline_loss_main(self, ctx, self.ce, step_bytes=self.bytes_per_px)
 
 
+class LogitProducer(Workload):
+    """SURVEY 8f N3 (not a BASELINE configuration): the fusion that turns the backbone's feature maps into the 2 + 16
+    logits (nets/pixellink.py:56-67) at the PixelLink-4s shapes of config 2 with VGG-16 widths, batch 8 per GPU."""
+    cid = "n3"
+    batch_per_gpu = 8
+    metric = "img/s PixelLink-4s logit producer (fc7 + conv5_3 + conv4_3 + conv3_3 -> 2+16 logits) 512^2 b8"
+    workload = ("PixelLink-4s logit producer: 1x1 fuse convolutions + bilinear x2 unpool + output convolutions over fc7 "
+                "(32x32x1024), conv5_3 (32x32x512), conv4_3 (64x64x512), conv3_3 (128x128x256) -> logits 128x128x(2+16), batch 8 per GPU")
+    bytes_per_px = (256 + 512 // 4 + (1024 + 512) // 16) * 4 + 72     # activations read per output pixel + the logits written
+    cpu_s_per_image = 0.15
+    CH = (("fc7", 1024, 4), ("conv5_3", 512, 4), ("conv4_3", 512, 2), ("conv3_3", 256, 1))
+
+    def _params(self):
+        rng = np.random.default_rng(31)
+        p = {}
+        for kind, n, last in (("pixel", 2, "text_predication"), ("link", 16, "link_predication")):
+            for (name, K, _), st in zip(self.CH, (6, 5, 4, 3)):
+                p["stage_%d_%s_fuse" % (st, kind)] = ((rng.standard_normal((K, n)) / np.sqrt(K)).astype(np.float32),
+                                                      (0.1 * rng.standard_normal(n)).astype(np.float32))
+            p[last] = ((rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32), (0.1 * rng.standard_normal(n)).astype(np.float32))
+        return p
+
+    def host_sets(self, B, rank):
+        rng = np.random.default_rng(77)
+        base = {name: rng.standard_normal((B, self.H // d, self.W // d, K), dtype=np.float32) for name, K, d in self.CH}
+        return [{k: np.ascontiguousarray(np.roll(v, s + rank, axis=0)) for k, v in base.items()} for s in range(NSETS)]
+
+    def setup(self, dev, B):
+        import torch
+        p = self._params()
+        cat = lambda a, b: torch.as_tensor(np.concatenate([a, b], -1)).to(dev)
+        self.w = {name: cat(p["stage_%d_pixel_fuse" % st][0], p["stage_%d_link_fuse" % st][0]) for (name, _, _), st in zip(self.CH, (6, 5, 4, 3))}
+        self.b = {name: cat(p["stage_%d_pixel_fuse" % st][1], p["stage_%d_link_fuse" % st][1]) for (name, _, _), st in zip(self.CH, (6, 5, 4, 3))}
+        w_out = np.zeros((18, 18), np.float32)
+        w_out[:2, :2], w_out[2:, 2:] = p["text_predication"][0], p["link_predication"][0]
+        b_out = np.concatenate([p["text_predication"][1], p["link_predication"][1]])
+        self.w_out = torch.as_tensor(w_out).to(dev)
+        # no activation on the fuse convolutions: the output matrix goes one level up and into the conv3_3 weights
+        self.w3 = (self.w["conv3_3"].double() @ self.w_out.double()).float().contiguous()
+        self.b3 = (self.b["conv3_3"].double() @ self.w_out.double() + torch.as_tensor(b_out).to(dev).double()).float().contiguous()
+
+    def step(self, d, out):
+        from tensorflow_ocr_b200 import head
+        s1 = head.head_fuse_level_raw([(d["fc7"], self.w["fc7"], None, self.b["fc7"], False),
+                                       (d["conv5_3"], self.w["conv5_3"], None, self.b["conv5_3"], False)])
+        s2 = head.head_fuse_level_raw([(d["conv4_3"], self.w["conv4_3"], None, self.b["conv4_3"], False)], prev=s1,
+                                      w_out=self.w_out, logits=False)
+        out["s2"] = s2
+        out["pix"], out["link"] = head.head_fuse_level_raw([(d["conv3_3"], self.w3, None, self.b3, False)], prev=s2, logits=True)
+
+    def results(self, out):
+        return [out["pix"], out["link"]]
+
+    def cpu_step(self, batch, pool):
+        from oracle import head_logits as OH
+        pix, link = OH.pixellink_layers(batch, self._params())
+        return float(np.abs(link).mean()), 0
+
+    def roofline(self, ctx):
+        """head_fuse_tc_kernel on the conv3_3 level (the largest: 55 % of the bytes), relaunched alone over the rotating sets."""
+        import torch
+        from tensorflow_ocr_b200 import head
+        dev_sets, B = ctx["dev_sets"], ctx["B"]
+        s2 = ctx["outs"][0]["s2"] if "outs" in ctx else None
+        if s2 is None:
+            o = {}
+            self.step(dev_sets[0], o)
+            s2 = o["s2"]
+        call = lambda i: head.head_fuse_level_raw([(dev_sets[i % NSETS]["conv3_3"], self.w3, None, self.b3, False)], prev=s2, logits=True)
+        for i in range(NSETS):
+            call(i)
+        torch.cuda.synchronize()
+        reps = 5 * NSETS
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for i in range(reps):
+            call(i)
+        r1.record()
+        torch.cuda.synchronize()
+        per = r0.elapsed_time(r1) * 1e-3 / reps
+        alg = B * (self.H * self.W * (256 + 18) + (self.H // 2) * (self.W // 2) * 18) * 4
+        return {"bound": "hbm", "kernel": "head_fuse_tc_kernel (conv3_3 level)", "achieved": alg / per / 1e9, "unit": "GB/s",
+                "traffic": None, "algorithmic_bytes_per_launch": alg, "us_per_launch": per * 1e6, "launches_timed": reps,
+                "method": "the level relaunched alone back to back over the rotating input sets, CUDA events around the sequence / launches",
+                "traffic_note": "ncu: profiles/r02_headfuse.txt (batch 32: 546 MB read + 8 MB written to DRAM per launch)"}
+
+
 def get_workload(cid) -> Workload:
+    if cid == "n3":
+        return LogitProducer()
     if cid == "2":
         return HeadStep()
     if cid in ("3a", "3b"):
@@ -954,7 +1043,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="2", choices=["2", "3a", "3b", "4", "5"])
+    ap.add_argument("--config", default="2", choices=["2", "3a", "3b", "4", "5", "n3"])
     ap.add_argument("--no-graphs", action="store_true", help="direct launches instead of CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-e2e", action="store_true")
