@@ -28,6 +28,23 @@
 
 namespace plh {
 
+// -DPLH_HF_TRACE (make -C tensorflow_ocr_b200/csrc trace -> libplhead_trace.so): CTA 0 of the tensor-core kernel records
+// %globaltimer at the pipeline's hand-overs for its first 512 chunks; tools/headfuse_trace.py prints them.
+#ifdef PLH_HF_TRACE
+__device__ unsigned long long g_hf_trace[8 * 512];
+__device__ __forceinline__ unsigned long long hf_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define HF_TR(slot, n)                                                                 \
+  do {                                                                                 \
+    if (blockIdx.x == 0 && (n) < 512) g_hf_trace[(slot) * 512 + (n)] = hf_now();       \
+  } while (0)
+#else
+#define HF_TR(slot, n) do { } while (0)
+#endif
+
 float prob_to_logit_threshold(float t);  // loss.cu
 
 constexpr int kHfThreads = 128;                 // 4 warps: each takes 8 of a chunk's 32 channels
@@ -266,7 +283,10 @@ __global__ void __launch_bounds__(kHfThreads, 2) head_fuse_kernel(const HfArgs a
 // chunk = 0.26 us at 128 B/clk, against 0.37 us for the chunk's HBM time (80 KB / 0.33 us with three MMAs).  A fully warp-specialised variant (cp.async loaders writing the swizzled layout directly so
 // that the raw tile serves as the hi operand, converters producing only lo, two accumulators, separate epilogue
 // warps) was built and is bit-compatible, but moves 96 KB per chunk through shared memory and measures the same
-// (314 vs 305 us); the way past this bound is to feed the A operand from tensor memory, not attempted.
+// (314 vs 305 us).  Feeding the A operand from TENSOR memory instead (staging warps transpose the tile through shared
+// memory to thread = pixel, tcgen05.st of hi and lo into two A stages, MMAs with [a_tmem]) was built too and is
+// bit-compatible: it takes the operand fetch off the tensor core but adds a barrier, 8 LDS and 2 tcgen05.st per chunk to
+// the staging warps, which are the longer pole — 166 us on the conv3_3 level against 146 us; not kept.
 constexpr int kTcThreads = 160;                  // 4 staging / epilogue warps + 1 warp that issues the MMAs
 constexpr int kTcWorkers = 128;
 constexpr int kTcTile = 128;
@@ -376,7 +396,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
         if (n_acc >= 1) tc_mbar_wait(bar0 + 8 * 5, (n_acc - 1) & 1);   // the previous accumulator has been read
         for (int ch = 0; ch < nchunks; ++ch, ++n_chunk) {
           const int st = n_chunk & 1;
+          if ((tid & 31) == 0) HF_TR(5, n_chunk);
           tc_mbar_wait(bar0 + 8 * (3 + st), (n_chunk >> 1) & 1);       // operands staged (and fenced) by all 128 threads
+          if ((tid & 31) == 0) HF_TR(6, n_chunk);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if ((tid & 31) == 0) {
             const uint32_t sa_hi = base_s + st * kTcStageBytes, sa_lo = sa_hi + kTcABytes, sb_hi = sa_lo + kTcABytes, sb_lo = sb_hi + kTcBBytes;
@@ -392,6 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
             (void)sb_lo;
             tc_commit(bar0 + 8 * st);
             if (ch == nchunks - 1) tc_commit(bar0 + 16);
+            HF_TR(7, n_chunk);
           }
           __syncwarp();
         }
@@ -492,16 +515,22 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
       for (int ch = 0; ch < nchunks; ++ch, ++n_chunk) {
         const int st = n_chunk & 1;
         // the MMAs that read this stage two chunks ago are done (use u of a stage waits for completion u - 1)
+        if (tid == 0) HF_TR(0, n_chunk);
         if (n_chunk >= 2) tc_mbar_wait(bar0 + 8 * st, ((n_chunk >> 1) - 1) & 1);
+        if (tid == 0) HF_TR(1, n_chunk);
         if (st == 0) {
           store_chunk(0, av0, wv0);
+          if (tid == 0) HF_TR(2, n_chunk);
           load_next(av0, wv0);
         } else {
           store_chunk(1, av1, wv1);
+          if (tid == 0) HF_TR(2, n_chunk);
           load_next(av1, wv1);
         }
+        if (tid == 0) HF_TR(3, n_chunk);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (3 + st)) : "memory");
+        if (tid == 0) HF_TR(4, n_chunk);
       }
       // the accumulator of this (tile, feature): lane = pixel, 32 columns (18 used)
       tc_mbar_wait(bar0 + 16, n_acc & 1);
@@ -547,9 +576,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
 }
 
 
+
 }  // namespace plh
 
 using namespace plh;
+
+#ifdef PLH_HF_TRACE
+extern "C" __attribute__((visibility("default"))) int plh_hf_trace_read(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, plh::g_hf_trace, sizeof(unsigned long long) * 8 * 512);
+}
+#endif
 
 extern "C" int plh_head_fuse_level(const float* xa, int Ka, const float* wa, const float* scale_a, const float* shift_a,
                                    int relu_a, const float* xb, int Kb, const float* wb, const float* scale_b,

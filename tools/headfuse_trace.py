@@ -1,6 +1,10 @@
+"""Device-side trace of the tcgen05 logit producer (needs make -C tensorflow_ocr_b200/csrc trace -> libplhead_trace.so):
+per 32-channel chunk of CTA 0, when the staging warps began / found their stage free / had stored / had issued the next loads /
+had arrived, and when the issuing warp began to wait / found the operands / had issued its MMAs.  Times in us."""
 import os, sys, ctypes, numpy as np, torch
 os.environ["PLH_LIB"] = "libplhead_trace.so"
-sys.path.insert(0, "/root/repo")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 from tensorflow_ocr_b200 import head, _lib
 dev = torch.device("cuda", 0)
 B = 32
@@ -8,7 +12,7 @@ x = torch.randn(B, 128, 128, 256, device=dev); w = torch.randn(256, 18, device=d
 prev = torch.randn(B, 64, 64, 18, device=dev)
 for _ in range(3): head.head_fuse_level_raw([(x, w, None, b, False)], prev=prev, logits=True)
 torch.cuda.synchronize()
-lib = ctypes.CDLL(os.path.join("/root/repo/tensorflow_ocr_b200", "libplhead_trace.so"))
+lib = ctypes.CDLL(os.path.join(ROOT, "tensorflow_ocr_b200", "libplhead_trace.so"))
 buf = (ctypes.c_ulonglong * (8 * 512))()
 lib.plh_hf_trace_read(buf)
 t = np.array(buf, dtype=np.int64).reshape(8, 512)[:, :112]
