@@ -116,3 +116,27 @@ def test_metrics_mirror_equals_the_reference(gold):
     o_pre, o_rec = oe.precision_recall(tot_n, np.concatenate(tot_tp), np.concatenate(tot_fp))
     assert pre == o_pre and rec == o_rec
     assert metrics.precision_recall(0, np.zeros(0, bool), np.zeros(0, bool)) == (0.0, 0.0)   # safe_divide
+
+
+def test_filled_polygon_properties_hypothesis():
+    """Property form of the two tests above: any quadrilateral with vertices in or around any small canvas."""
+    cv2 = pytest.importorskip("cv2")
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+
+    @hyp.settings(max_examples=400, deadline=None)
+    @hyp.given(st.lists(st.tuples(st.integers(-40, 110), st.integers(-40, 110)), min_size=4, max_size=4),
+               st.integers(1, 90), st.integers(1, 90))
+    def check(pts, w, h):
+        arr = np.array(pts, np.int32)
+        ref = np.zeros((h, w), np.uint8)
+        cv2.drawContours(ref, [arr.reshape(-1, 1, 2)], -1, 1, -1)
+        got = oe.mask_from_rows(oe.filled_quad_rows([tuple(p) for p in pts], w, h), (h, w))
+        assert np.array_equal(ref, got)
+        vis, q0, q1 = oe.clip_line(w, h, pts[0], pts[1])
+        line = np.zeros((h, w), np.uint8)
+        cv2.line(line, pts[0], pts[1], 1, 1, 8)
+        got = oe.mask_from_rows({y: [r] for y, r in oe.line_row_runs(q0, q1).items()} if vis else {}, (h, w))
+        assert np.array_equal(line, got)
+
+    check()

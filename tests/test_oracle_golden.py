@@ -216,3 +216,19 @@ def test_head_logits_golden(golden_dir):
     # the ones between are midpoints, the last row / column repeats)
     r = OH.resize_bilinear_x2(np.arange(4.0).reshape(1, 1, 4, 1))
     np.testing.assert_array_equal(r[0, 0, :, 0], [0, 0.5, 1, 1.5, 2, 2.5, 3, 3])
+
+
+def test_resize_bilinear_x2_properties():
+    """tf.image.resize_bilinear(align_corners=False) for an exact factor 2: constants stay constant, every other
+    output sits on a source pixel, the ones between are midpoints, the last row / column repeats."""
+    from oracle import head_logits as OH
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2, 5, 7, 3))
+    y = OH.resize_bilinear_x2(x)
+    assert y.shape == (2, 10, 14, 3)
+    np.testing.assert_array_equal(y[:, ::2, ::2], x)
+    np.testing.assert_allclose(y[:, 1:-1:2, ::2], 0.5 * (x[:, :-1] + x[:, 1:]), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(y[:, ::2, 1:-1:2], 0.5 * (x[:, :, :-1] + x[:, :, 1:]), rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(y[:, -1], y[:, -2])
+    np.testing.assert_array_equal(y[:, :, -1], y[:, :, -2])
+    np.testing.assert_array_equal(OH.resize_bilinear_x2(np.full((1, 3, 4, 2), 1.25)), np.full((1, 6, 8, 2), 1.25))
