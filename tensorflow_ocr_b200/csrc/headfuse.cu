@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
           if ((tid & 31) == 0) HF_TR(6, n_chunk);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if ((tid & 31) == 0) {
-            const uint32_t sa_hi = base_s + st * kTcStageBytes, sa_lo = sa_hi + kTcABytes, sb_hi = sa_lo + kTcABytes, sb_lo = sb_hi + kTcBBytes;
+            const uint32_t sa_hi = base_s + st * kTcStageBytes, sa_lo = sa_hi + kTcABytes, sb_hi = sa_lo + kTcABytes;   // B_lo follows B_hi
 #pragma unroll
             for (int j = 0; j < kTcKC / 8; ++j) {
               // the hi and lo weight tiles lie back to back: one N = 64 MMA gives hi*hi (columns 0-31) and hi*lo (columns
@@ -411,7 +411,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) head_fuse_tc_kernel(const HfArg
               tc_mma(tmem, dah, dbh, idesc2, (ch | j) != 0);
               tc_mma(tmem, dal, dbh, idesc, 1);
             }
-            (void)sb_lo;
             tc_commit(bar0 + 8 * st);
             if (ch == nchunks - 1) tc_commit(bar0 + 16);
             HF_TR(7, n_chunk);
