@@ -270,8 +270,9 @@ PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double r
  * The head's logit producer: one level of the feature fusion that ends both networks,
  * nets/pixellink.py:37-38,56-67 and nets/model.py:14-15,129-141 —
  *     y = bilinear_x2(prev) + act_a(scale_a * (xa Wa) + shift_a) [+ act_b(scale_b * (xb Wb) + shift_b)]
- * and, when w_out is given (the last level),  logits = y w_out + b_out, split into the pixel and link tensors the
- * loss / decode entry points read.  The 2 pixel and 16 link channels go through together: 18 columns, pixel first.
+ * optionally followed by  y <- y w_out + b_out  (the last 1x1 convolutions), written either as [.,18] for the next
+ * level or split into the pixel and link tensors the loss / decode entry points read.  The 2 pixel and 16 link channels
+ * go through together: 18 columns, pixel first.
  *  xa, xb    [B,H,W,Ka] / [B,H,W,Kb] float NHWC feature maps (xb optional: fc7 + conv5_3 share a level); K % 4 == 0
  *  wa, wb    [K,18] float: the 1x1 convolutions' weights, pixel columns 0-1, link columns 2-17
  *  scale, shift [18] optional: per-channel affine after the convolution (shift alone = bias; both = batch norm in
@@ -287,8 +288,9 @@ PLH_API int plh_contour_boxes(const uint8_t* mask, int B, int H, int W, double r
  *            plh_decode_flags would compute from the logits just produced (bit-identical: same logit-space
  *            thresholds on the same fp32 values), so that plh_decode_from_flags can start without reading the 72 B
  *            per pixel of logits again
- * fp32 in, fp32 FMA accumulation, fp32 out: within 1e-5 of an fp64 evaluation relative to the largest logit (the
- * contract tests/test_gpu_headfuse.py states).  wa / wb must be 16-byte aligned like the feature maps.
+ * fp32 in, fp32 out, fp32-accurate accumulation (K % 32 == 0: tcgen05 tensor cores, TF32 products with the 3xTF32
+ * split, fp32 accumulator in tensor memory; other K: fp32 FMAs): within 1e-5 of an fp64 evaluation relative to the
+ * largest logit (the contract tests/test_gpu_headfuse.py states).  wa / wb must be 16-byte aligned like the feature maps.
  */
 PLH_API int plh_head_fuse_level(const float* xa, int Ka, const float* wa, const float* scale_a, const float* shift_a, int relu_a,
                         const float* xb, int Kb, const float* wb, const float* scale_b, const float* shift_b, int relu_b,
